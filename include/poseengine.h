@@ -1,0 +1,152 @@
+/*
+ * poseengine.h -- C ABI of libposeengine.so, the B200 (sm_100a) engine behind the reference's
+ * top-down pose path.  Plain pointers and sizes only; no C++/torch types cross this boundary.
+ *
+ * The reference (peabody124/PosePipeline) has no native FFI: its seam is the Python import inside
+ * each DataJoint make() (pose_pipeline/pipeline.py:526,1021,1271).  Every entry point below names
+ * the reference function (file:line under the reference tree) whose arithmetic it replaces; the
+ * Python shims in posepipeline_b200/wrappers/ keep the reference signatures and call these through
+ * ctypes (see INTEGRATION.md for the binding a maintainer adds on the reference side).
+ *
+ * Conventions: every function returns 0 (PE_OK) or a negative error code; the message is available
+ * from pe_last_error() (thread-local).  Handles are opaque.  One engine per process per GPU; calls
+ * on one engine are serialised by the caller.  All host buffers are caller-owned.  "n" counts
+ * person crops (one bbox on one staged frame).
+ */
+#ifndef POSEENGINE_H
+#define POSEENGINE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PE_ABI_VERSION 1
+
+#define PE_OK 0
+#define PE_ERR_INVALID (-1)   /* bad argument */
+#define PE_ERR_CUDA (-2)      /* CUDA runtime/driver error */
+#define PE_ERR_STATE (-3)     /* call sequence error (e.g. frame index not staged) */
+#define PE_ERR_NOGPU (-4)     /* no CUDA device: the product path has no CPU fallback */
+
+typedef struct pe_engine pe_engine;
+typedef struct pe_model pe_model;
+typedef struct pe_lifter pe_lifter;
+
+/* layer program handed over by the host graph builder (posepipeline_b200/hrnet_spec.py) */
+enum { PE_OP_STEM = 0, PE_OP_CONV = 1, PE_OP_FUSE = 2, PE_OP_HEAD = 3 };
+enum { PE_POST_NONE = 0, PE_POST_DEFAULT = 1, PE_POST_UNBIASED = 2 };
+
+typedef struct pe_op_desc {
+  int32_t kind;        /* PE_OP_* */
+  int32_t out;         /* output tensor id */
+  int32_t in[4];       /* input tensor ids (-1 = unused; STEM reads the uint8 crop) */
+  int32_t up[4];       /* FUSE: nearest-upsample factor of each input */
+  int32_t n_in;
+  int32_t ksize, stride, cin, cout;
+  int32_t relu;
+  int32_t residual;    /* tensor id added before the ReLU, or -1 */
+  int32_t reserved;
+  int64_t w_off;       /* float offset of the packed weights [k*k][cin][cout] in the weight blob */
+  int64_t b_off;       /* float offset of the folded bias [cout] */
+  int64_t wtc_off;     /* float offset of the tensor-core packing, or -1 */
+} pe_op_desc;
+
+typedef struct pe_tensor_desc {
+  int32_t C, H, W;     /* per-image dims (activations live in HBM as padded, tf32 hi/lo split NHWC) */
+  int32_t slot;        /* buffer slot (tensors with disjoint live ranges share one) */
+} pe_tensor_desc;
+
+typedef struct pe_model_desc {
+  int32_t in_h, in_w;          /* network input (crop) size: 384x288, cfg data_cfg.image_size */
+  int32_t hm_h, hm_w;          /* heatmap size: 96x72 */
+  int32_t num_joints;
+  int32_t n_ops, n_tensors, n_slots;
+  int32_t max_crops;           /* crops per internal batch (each crop = 2 images when flip_test) */
+  int32_t flip_test;           /* cfg test_cfg.flip_test */
+  int32_t shift_heatmap;       /* cfg test_cfg.shift_heatmap */
+  int32_t post_process;        /* PE_POST_* : cfg test_cfg.post_process */
+  int32_t blur_kernel;         /* cfg test_cfg.modulate_kernel (17) */
+  int32_t swap_rb;             /* 0 = reproduce the wrapper's double BGR<->RGB swap */
+  int32_t use_tensor_cores;    /* 1 = tcgen05 path for eligible convs, 0 = fp32 SIMT everywhere */
+  int32_t reserved;
+  float padding;               /* bbox padding 1.25 */
+  float pixel_std;             /* 200 */
+} pe_model_desc;
+
+/* ---- library ---- */
+int pe_abi_version(void);
+const char* pe_last_error(void);
+int pe_device_count(int* count);
+
+/* ---- engine: one per GPU.  `cuda_stream` may be NULL (engine creates its own) or a cudaStream_t
+ * the caller times with its own events (bench.py passes torch's current stream). ---- */
+int pe_engine_create(int device, void* cuda_stream, pe_engine** out);
+int pe_engine_destroy(pe_engine* e);
+int pe_engine_sync(pe_engine* e);
+
+/* Frame staging: replaces the per-frame host->device copy buried in
+ * inference_top_down_pose_model (pose_pipeline/wrappers/mmpose.py:75) after cap.read() (:63).
+ * `frames` = n contiguous-or-strided HWC uint8 BGR images exactly as cv2.VideoCapture.read()
+ * returns them (pinned host memory recommended).  Copies asynchronously on the engine stream into
+ * the device frame store; slot i holds frame i until the next call. */
+int pe_stage_frames(pe_engine* e, const uint8_t* frames, int32_t n, int32_t height, int32_t width,
+                    int64_t frame_stride_bytes);
+/* As above but the frames are already in device memory (benchmark "resident" leg). */
+int pe_stage_frames_device(pe_engine* e, const uint8_t* d_frames, int32_t n, int32_t height, int32_t width);
+
+/* PersonBbox.make (pose_pipeline/pipeline.py:656-687): per frame keep the dicts whose track_id is in
+ * keep_tracks; exactly one -> present, bbox = its tlhw; then NaN-mask, bfill(limit 2), ffill(limit 2).
+ * Host-only, bit-exact.  counts[f] = #tracks in frame f; track_ids/tlhw are concatenated over frames. */
+int pe_person_bbox(const int32_t* counts, int32_t n_frames, const int64_t* track_ids, const double* tlhw,
+                   const int64_t* keep_tracks, int32_t n_keep, double* bbox_out /*n_frames*4*/,
+                   uint8_t* present_out /*n_frames*/);
+
+/* ---- top-down model (mmpose init_pose_model, wrappers/mmpose.py:57) ---- */
+int pe_model_create(pe_engine* e, const pe_model_desc* desc, const pe_op_desc* ops, const pe_tensor_desc* tensors,
+                    const int64_t* slot_elems /*n_slots: padded elems per image*/, const float* weights,
+                    int64_t n_weight_floats, const float* norm_lut /*3*256: (v/255-mean_c)/std_c*/,
+                    const int32_t* flip_perm /*num_joints: channel read for joint k in the flipped map*/,
+                    pe_model** out);
+int pe_model_destroy(pe_model* m);
+
+/* The hot path == the body of the reference loop wrappers/mmpose.py:60-76 for n (frame, bbox) pairs:
+ * bbox->center/scale, affine crop (cv2.warpAffine-exact), normalise, HRNet x2 (flip test), flip-merge,
+ * DARK decode, back-projection.  frame_idx[i] indexes the staged frames.  out_kpts: n*K*3 floats
+ * [x_px, y_px, score].  Synchronous on return. */
+int pe_topdown(pe_model* m, const int32_t* frame_idx, const double* bbox_xywh, int32_t n, float* out_kpts);
+/* Same, but results stay on the device until pe_engine_sync(); no host wait (throughput runs). */
+int pe_topdown_async(pe_model* m, const int32_t* frame_idx, const double* bbox_xywh, int32_t n, float* out_kpts_pinned);
+
+/* ---- parity hooks (each stage of the path on its own) ---- */
+/* mmpose bbox_xywh2cs + get_affine_transform (A.1 steps 2,4): center(2) scale(2) f32, trans 2x3 f64 */
+int pe_box_to_affine(const pe_model_desc* desc, const double* bbox_xywh, float* center, float* scale, double* trans);
+/* cv2.warpAffine(INTER_LINEAR, BORDER_CONSTANT 0) of staged frames -> uint8 crops n*in_h*in_w*3 */
+int pe_warp_crops(pe_model* m, const int32_t* frame_idx, const double* bbox_xywh, int32_t n, uint8_t* out_crops,
+                  float* out_center /*n*2*/, float* out_scale /*n*2*/);
+/* network only: uint8 crops -> heatmaps (plain pass and raw flipped pass), each n*K*hm_h*hm_w */
+int pe_forward_heatmaps(pe_model* m, const uint8_t* crops, int32_t n, float* hm_plain, float* hm_flipped);
+/* keypoints_from_heatmaps + flip merge (A.1 step 6-7, A.5) on caller-provided heatmaps */
+int pe_decode_heatmaps(pe_model* m, const float* hm_plain, const float* hm_flipped /*NULL = no flip merge*/,
+                       const float* center, const float* scale, int32_t n, float* out_kpts);
+/* copy one intermediate activation of the last forward (image `img` of the internal batch) as dense CHW fp32 */
+int pe_debug_tensor(pe_model* m, int32_t tensor_id, int32_t img, float* out_chw);
+/* number of kernels this model has launched so far (bench.py "gpu_launches") */
+int pe_model_launch_count(pe_model* m, int64_t* count);
+/* device timing of the dominant (conv) kernels between two marks, for bench.py's roofline */
+int pe_model_profile(pe_model* m, int32_t enable);
+int pe_model_profile_read(pe_model* m, double* conv_ms, double* other_ms, int64_t* conv_launches);
+
+/* ---- VideoPose3D lifter (wrappers/videopose3d.py:46-85; TemporalModelOptimized1f 243 frames) ---- */
+int pe_lifter_create(pe_engine* e, const float* weights, int64_t n_floats, const int64_t* offsets /*see lifter.py*/,
+                     int32_t n_offsets, int32_t channels, pe_lifter** out);
+int pe_lifter_destroy(pe_lifter* l);
+/* kp2d_norm: N*17*2 normalised screen coords; out: N*17*3.  Windows are edge-replicated (pad 121). */
+int pe_lift3d(pe_lifter* l, const float* kp2d_norm, int32_t n_frames, float* out3d);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POSEENGINE_H */

@@ -1,0 +1,623 @@
+// C-ABI host side of libposeengine.so (see include/poseengine.h).
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../../include/poseengine.h"
+#include "kernels.h"
+#include "pe_common.cuh"
+
+// ------------------------------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+static int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define CU(x)                                                                                        \
+  do {                                                                                               \
+    cudaError_t _e = (x);                                                                            \
+    if (_e != cudaSuccess)                                                                           \
+      return fail(PE_ERR_CUDA, "%s failed: %s (%s:%d)", #x, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+int pe_set_error(int code, const char* msg) { g_err = msg ? msg : ""; return code; }
+
+extern "C" int pe_abi_version(void) { return PE_ABI_VERSION; }
+extern "C" const char* pe_last_error(void) { return g_err.c_str(); }
+extern "C" int pe_device_count(int* count) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) { *count = 0; cudaGetLastError(); return fail(PE_ERR_NOGPU, "no CUDA device: %s", cudaGetErrorString(e)); }
+  *count = n;
+  return PE_OK;
+}
+
+// ------------------------------------------------------------------------------------------ engine
+struct pe_engine {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  uint8_t* d_frames = nullptr;       // owned frame store
+  const uint8_t* frames = nullptr;   // current frames (owned store or caller's device memory)
+  size_t frames_cap = 0;
+  int n_frames = 0, fh = 0, fw = 0;
+};
+
+extern "C" int pe_engine_create(int device, void* cuda_stream, pe_engine** out) {
+  if (!out) return fail(PE_ERR_INVALID, "out is NULL");
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return fail(PE_ERR_NOGPU, "libposeengine needs a CUDA device (sm_100a); there is no CPU fallback");
+  }
+  if (device < 0 || device >= n) return fail(PE_ERR_INVALID, "device %d out of range (%d devices)", device, n);
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(PE_ERR_NOGPU, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+  pe_engine* e = new pe_engine();
+  e->device = device;
+  if (cuda_stream) {
+    e->stream = (cudaStream_t)cuda_stream;
+  } else {
+    CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    e->own_stream = true;
+  }
+  *out = e;
+  return PE_OK;
+}
+
+extern "C" int pe_engine_destroy(pe_engine* e) {
+  if (!e) return PE_OK;
+  cudaSetDevice(e->device);
+  cudaStreamSynchronize(e->stream);
+  if (e->d_frames) cudaFree(e->d_frames);
+  if (e->own_stream) cudaStreamDestroy(e->stream);
+  delete e;
+  return PE_OK;
+}
+
+extern "C" int pe_engine_sync(pe_engine* e) {
+  if (!e) return fail(PE_ERR_INVALID, "engine is NULL");
+  CU(cudaStreamSynchronize(e->stream));
+  return PE_OK;
+}
+
+extern "C" int pe_stage_frames(pe_engine* e, const uint8_t* frames, int32_t n, int32_t height, int32_t width,
+                               int64_t frame_stride_bytes) {
+  if (!e || !frames || n <= 0 || height <= 0 || width <= 0) return fail(PE_ERR_INVALID, "bad argument to pe_stage_frames");
+  CU(cudaSetDevice(e->device));
+  const size_t fb = (size_t)height * width * 3;
+  if (frame_stride_bytes == 0) frame_stride_bytes = (int64_t)fb;
+  if ((size_t)frame_stride_bytes < fb) return fail(PE_ERR_INVALID, "frame stride smaller than a frame");
+  if (fb * n > e->frames_cap) {
+    CU(cudaStreamSynchronize(e->stream));
+    if (e->d_frames) CU(cudaFree(e->d_frames));
+    e->d_frames = nullptr;
+    CU(cudaMalloc(&e->d_frames, fb * n));
+    e->frames_cap = fb * n;
+  }
+  CU(cudaMemcpy2DAsync(e->d_frames, fb, frames, (size_t)frame_stride_bytes, fb, n, cudaMemcpyHostToDevice, e->stream));
+  e->frames = e->d_frames;
+  e->n_frames = n; e->fh = height; e->fw = width;
+  return PE_OK;
+}
+
+extern "C" int pe_stage_frames_device(pe_engine* e, const uint8_t* d_frames, int32_t n, int32_t height, int32_t width) {
+  if (!e || !d_frames || n <= 0) return fail(PE_ERR_INVALID, "bad argument to pe_stage_frames_device");
+  e->frames = d_frames;
+  e->n_frames = n; e->fh = height; e->fw = width;
+  return PE_OK;
+}
+
+// ------------------------------------------------------------------------------------------ a3: PersonBbox.make
+extern "C" int pe_person_bbox(const int32_t* counts, int32_t n_frames, const int64_t* track_ids, const double* tlhw,
+                              const int64_t* keep_tracks, int32_t n_keep, double* bbox_out, uint8_t* present_out) {
+  if (n_frames <= 0 || !counts || !bbox_out || !present_out) return fail(PE_ERR_INVALID, "bad argument to pe_person_bbox");
+  const double nan = std::numeric_limits<double>::quiet_NaN();
+  size_t off = 0;
+  for (int f = 0; f < n_frames; ++f) {             // pipeline.py:662-667
+    int hits = 0;
+    size_t which = 0;
+    for (int t = 0; t < counts[f]; ++t) {
+      bool in = false;
+      for (int k = 0; k < n_keep; ++k) in |= (track_ids[off + t] == keep_tracks[k]);
+      if (in) { ++hits; which = off + t; }
+    }
+    for (int c = 0; c < 4; ++c) bbox_out[f * 4 + c] = (hits == 1) ? tlhw[which * 4 + c] : nan;   // :679
+    off += counts[f];
+  }
+  for (int c = 0; c < 4; ++c) {                    // :680 bfill(limit=2): fill from the next valid row
+    double next = nan; int run = 0; bool have = false;
+    for (int f = n_frames - 1; f >= 0; --f) {
+      double& v = bbox_out[f * 4 + c];
+      if (std::isnan(v)) { if (have && run < 2) { v = next; ++run; } }
+      else { next = v; have = true; run = 0; }
+    }
+  }
+  for (int c = 0; c < 4; ++c) {                    // :681 ffill(limit=2)
+    double prev = nan; int run = 0; bool have = false;
+    for (int f = 0; f < n_frames; ++f) {
+      double& v = bbox_out[f * 4 + c];
+      if (std::isnan(v)) { if (have && run < 2) { v = prev; ++run; } }
+      else { prev = v; have = true; run = 0; }
+    }
+  }
+  for (int f = 0; f < n_frames; ++f) {             // :684
+    bool any = false;
+    for (int c = 0; c < 4; ++c) any |= std::isnan(bbox_out[f * 4 + c]);
+    present_out[f] = any ? 0 : 1;
+  }
+  return PE_OK;
+}
+
+// ------------------------------------------------------------------------------------------ a5/a6 host maths
+// 6x6 LU with partial pivoting, operation order of OpenCV's LUImpl (what cv2.getAffineTransform runs).
+static bool lu_solve6(double A[6][6], double b[6]) {
+  const int m = 6;
+  for (int i = 0; i < m; ++i) {
+    int k = i;
+    for (int j = i + 1; j < m; ++j)
+      if (std::fabs(A[j][i]) > std::fabs(A[k][i])) k = j;
+    if (std::fabs(A[k][i]) < std::numeric_limits<double>::epsilon() * 100) return false;
+    if (k != i) {
+      for (int j = i; j < m; ++j) std::swap(A[i][j], A[k][j]);
+      std::swap(b[i], b[k]);
+    }
+    const double d = -1 / A[i][i];
+    for (int j = i + 1; j < m; ++j) {
+      const double alpha = A[j][i] * d;
+      for (int c = i + 1; c < m; ++c) A[j][c] += alpha * A[i][c];
+      b[j] += alpha * b[i];
+    }
+  }
+  for (int i = m - 1; i >= 0; --i) {
+    double s = b[i];
+    for (int k = i + 1; k < m; ++k) s -= A[i][k] * b[k];
+    b[i] = s / A[i][i];
+  }
+  return true;
+}
+
+static void box_to_affine(const pe_model_desc* d, const double* bbox, float* center, float* scale, double* trans) {
+  // mmpose bbox_xywh2cs
+  double x = bbox[0], y = bbox[1], w = bbox[2], h = bbox[3];
+  const double aspect = (double)d->in_w / (double)d->in_h;
+  center[0] = (float)(x + w * 0.5);
+  center[1] = (float)(y + h * 0.5);
+  if (w > aspect * h) h = w * 1.0 / aspect;
+  else if (w < aspect * h) w = h * aspect;
+  scale[0] = ((float)w / d->pixel_std) * d->padding;
+  scale[1] = ((float)h / d->pixel_std) * d->padding;
+  // mmpose get_affine_transform(center, scale, rot=0, image_size) (A.1 step 4)
+  const float src_w = scale[0] * 200.0f;
+  float src[3][2], dst[3][2];
+  src[0][0] = center[0]; src[0][1] = center[1];
+  src[1][0] = (float)((double)center[0] + 0.0);
+  src[1][1] = (float)((double)center[1] + (double)src_w * -0.5);
+  {
+    const float d0 = src[0][0] - src[1][0], d1 = src[0][1] - src[1][1];
+    src[2][0] = src[1][0] + (-d1); src[2][1] = src[1][1] + d0;
+  }
+  const double dw = d->in_w, dh = d->in_h;
+  dst[0][0] = (float)(dw * 0.5); dst[0][1] = (float)(dh * 0.5);
+  dst[1][0] = (float)(dw * 0.5 + 0.0); dst[1][1] = (float)(dh * 0.5 + dw * -0.5);
+  {
+    const float d0 = dst[0][0] - dst[1][0], d1 = dst[0][1] - dst[1][1];
+    dst[2][0] = dst[1][0] + (-d1); dst[2][1] = dst[1][1] + d0;
+  }
+  // cv2.getAffineTransform(src, dst)
+  double A[6][6] = {{0}}, b[6];
+  for (int i = 0; i < 3; ++i) {
+    A[2 * i][0] = A[2 * i + 1][3] = src[i][0];
+    A[2 * i][1] = A[2 * i + 1][4] = src[i][1];
+    A[2 * i][2] = A[2 * i + 1][5] = 1;
+    b[2 * i] = dst[i][0];
+    b[2 * i + 1] = dst[i][1];
+  }
+  if (!lu_solve6(A, b)) for (int i = 0; i < 6; ++i) b[i] = 0;
+  for (int i = 0; i < 6; ++i) trans[i] = b[i];
+}
+
+// cv::warpAffine without WARP_INVERSE_MAP inverts the 2x3 matrix like this (double):
+static void invert_affine(const double* Min, double* M) {
+  for (int i = 0; i < 6; ++i) M[i] = Min[i];
+  double D = M[0] * M[4] - M[1] * M[3];
+  D = D != 0 ? 1. / D : 0;
+  const double A11 = M[4] * D, A22 = M[0] * D;
+  M[0] = A11; M[1] *= -D; M[3] *= -D; M[4] = A22;
+  const double b1 = -M[0] * M[2] - M[1] * M[5];
+  const double b2 = -M[3] * M[2] - M[4] * M[5];
+  M[2] = b1; M[5] = b2;
+}
+
+extern "C" int pe_box_to_affine(const pe_model_desc* desc, const double* bbox_xywh, float* center, float* scale, double* trans) {
+  if (!desc || !bbox_xywh || !center || !scale || !trans) return fail(PE_ERR_INVALID, "bad argument to pe_box_to_affine");
+  box_to_affine(desc, bbox_xywh, center, scale, trans);
+  return PE_OK;
+}
+
+// ------------------------------------------------------------------------------------------ model
+struct pe_model {
+  pe_engine* e = nullptr;
+  pe_model_desc d{};
+  std::vector<pe_op_desc> ops;
+  std::vector<pe_tensor_desc> tensors;
+  std::vector<float*> slots;
+  std::vector<TcConvPlan*> tc;   // per op, or nullptr
+  float* d_w = nullptr;
+  float* d_lut = nullptr;
+  int* d_perm = nullptr;
+  uint8_t* d_crops = nullptr;
+  double* d_minv = nullptr;
+  int32_t* d_fidx = nullptr;
+  float* d_cs = nullptr;        // center[max][2] then scale[max][2]
+  float* d_hm = nullptr;        // [2*max][K][hh][hw]
+  float* d_out = nullptr;       // [max][K][3]
+  // pinned staging
+  double* h_minv = nullptr; int32_t* h_fidx = nullptr; float* h_cs = nullptr; float* h_out = nullptr;
+  int nimg_last = 0, ncrop_last = 0;
+  int64_t launches = 0;
+  int profile = 0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_conv;
+  size_t ev_used = 0;
+  cudaEvent_t ev_fwd0 = nullptr, ev_fwd1 = nullptr;
+  double acc_conv_ms = 0, acc_total_ms = 0; int64_t acc_conv_launches = 0;
+};
+
+static float* act_ptr(pe_model* m, int tid) { return m->slots[m->tensors[tid].slot]; }
+
+static void gauss_taps(int k, float* out) {
+  // cv2.getGaussianKernel(k, sigma<=0 -> 0.3*((k-1)*0.5-1)+0.8, CV_32F): computed in double, normalised, cast
+  const double sigma = 0.3 * ((k - 1) * 0.5 - 1) + 0.8;
+  const double scale2x = -0.5 / (sigma * sigma);
+  std::vector<double> t(k);
+  double sum = 0;
+  for (int i = 0; i < k; ++i) { const double x = i - (k - 1) * 0.5; t[i] = std::exp(scale2x * x * x); sum += t[i]; }
+  sum = 1. / sum;
+  for (int i = 0; i < k; ++i) out[i] = (float)(t[i] * sum);
+}
+
+extern "C" int pe_model_destroy(pe_model* m) {
+  if (!m) return PE_OK;
+  cudaSetDevice(m->e->device);
+  cudaStreamSynchronize(m->e->stream);
+  for (auto* p : m->tc) if (p) tc_conv_plan_destroy(p);
+  for (auto* p : m->slots) if (p) cudaFree(p);
+  cudaFree(m->d_w); cudaFree(m->d_lut); cudaFree(m->d_perm); cudaFree(m->d_crops); cudaFree(m->d_minv);
+  cudaFree(m->d_fidx); cudaFree(m->d_cs); cudaFree(m->d_hm); cudaFree(m->d_out);
+  cudaFreeHost(m->h_minv); cudaFreeHost(m->h_fidx); cudaFreeHost(m->h_cs); cudaFreeHost(m->h_out);
+  for (auto& p : m->ev_conv) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+  if (m->ev_fwd0) cudaEventDestroy(m->ev_fwd0);
+  if (m->ev_fwd1) cudaEventDestroy(m->ev_fwd1);
+  delete m;
+  return PE_OK;
+}
+
+extern "C" int pe_model_create(pe_engine* e, const pe_model_desc* desc, const pe_op_desc* ops, const pe_tensor_desc* tensors,
+                               const int64_t* slot_elems, const float* weights, int64_t n_weight_floats,
+                               const float* norm_lut, const int32_t* flip_perm, pe_model** out) {
+  if (!e || !desc || !ops || !tensors || !slot_elems || !weights || !norm_lut || !flip_perm || !out)
+    return fail(PE_ERR_INVALID, "NULL argument to pe_model_create");
+  if (desc->max_crops <= 0 || desc->n_ops <= 0) return fail(PE_ERR_INVALID, "bad model description");
+  if (desc->post_process == PE_POST_UNBIASED && (desc->blur_kernel < 3 || desc->blur_kernel > 63 || desc->blur_kernel % 2 == 0))
+    return fail(PE_ERR_INVALID, "blur kernel must be odd and in [3,63]");
+  CU(cudaSetDevice(e->device));
+  pe_model* m = new pe_model();
+  m->e = e; m->d = *desc;
+  m->ops.assign(ops, ops + desc->n_ops);
+  m->tensors.assign(tensors, tensors + desc->n_tensors);
+  const int maxc = desc->max_crops, maximg = maxc * (desc->flip_test ? 2 : 1);
+  const int K = desc->num_joints;
+#define CUM(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { int rc = fail(PE_ERR_CUDA, "%s failed: %s", #x, cudaGetErrorString(_e)); pe_model_destroy(m); return rc; } } while (0)
+  m->slots.assign(desc->n_slots, nullptr);
+  for (int s = 0; s < desc->n_slots; ++s) {
+    const size_t bytes = (size_t)slot_elems[s] * 2 * sizeof(float) * maximg;
+    CUM(cudaMalloc(&m->slots[s], bytes));
+    CUM(cudaMemsetAsync(m->slots[s], 0, bytes, e->stream));
+  }
+  CUM(cudaMalloc(&m->d_w, sizeof(float) * n_weight_floats));
+  CUM(cudaMemcpyAsync(m->d_w, weights, sizeof(float) * n_weight_floats, cudaMemcpyHostToDevice, e->stream));
+  CUM(cudaMalloc(&m->d_lut, sizeof(float) * 768));
+  CUM(cudaMemcpyAsync(m->d_lut, norm_lut, sizeof(float) * 768, cudaMemcpyHostToDevice, e->stream));
+  CUM(cudaMalloc(&m->d_perm, sizeof(int) * K));
+  CUM(cudaMemcpyAsync(m->d_perm, flip_perm, sizeof(int) * K, cudaMemcpyHostToDevice, e->stream));
+  CUM(cudaMalloc(&m->d_crops, (size_t)maxc * desc->in_h * desc->in_w * 3));
+  CUM(cudaMalloc(&m->d_minv, sizeof(double) * 6 * maxc));
+  CUM(cudaMalloc(&m->d_fidx, sizeof(int32_t) * maxc));
+  CUM(cudaMalloc(&m->d_cs, sizeof(float) * 4 * maxc));
+  CUM(cudaMalloc(&m->d_hm, sizeof(float) * (size_t)maximg * K * desc->hm_h * desc->hm_w));
+  CUM(cudaMalloc(&m->d_out, sizeof(float) * (size_t)maxc * K * 3));
+  CUM(cudaMallocHost(&m->h_minv, sizeof(double) * 6 * maxc));
+  CUM(cudaMallocHost(&m->h_fidx, sizeof(int32_t) * maxc));
+  CUM(cudaMallocHost(&m->h_cs, sizeof(float) * 4 * maxc));
+  CUM(cudaMallocHost(&m->h_out, sizeof(float) * (size_t)maxc * K * 3));
+  CUM(cudaEventCreate(&m->ev_fwd0));
+  CUM(cudaEventCreate(&m->ev_fwd1));
+  if (desc->post_process == PE_POST_UNBIASED) {
+    float taps[64];
+    gauss_taps(desc->blur_kernel, taps);
+    upload_gauss_kernel(taps, desc->blur_kernel);
+  }
+  // tensor-core plans for eligible convolutions
+  m->tc.assign(desc->n_ops, nullptr);
+  if (desc->use_tensor_cores) {
+    for (int i = 0; i < desc->n_ops; ++i) {
+      const pe_op_desc& op = m->ops[i];
+      if (op.kind != PE_OP_CONV || op.stride != 1 || op.wtc_off < 0) continue;
+      const pe_tensor_desc& to = m->tensors[op.out];
+      TcConvPlan* plan = nullptr;
+      cudaError_t ce = tc_conv_plan_create(&plan, act_ptr(m, op.in[0]), act_ptr(m, op.out),
+                                           op.residual >= 0 ? act_ptr(m, op.residual) : nullptr, m->d_w + op.wtc_off,
+                                           m->d_w + op.b_off, op.cin, op.cout, op.ksize, op.relu, to.H, to.W, maximg);
+      if (ce == cudaSuccess) m->tc[i] = plan;
+      else if (ce != cudaErrorNotSupported) {
+        int rc = fail(PE_ERR_CUDA, "tensor-core plan for op %d failed: %s", i, cudaGetErrorString(ce));
+        pe_model_destroy(m);
+        return rc;
+      }
+    }
+  }
+  CUM(cudaStreamSynchronize(e->stream));
+#undef CUM
+  *out = m;
+  return PE_OK;
+}
+
+// run the layer program on `nimg` images whose uint8 crops are in d_crops (ncrop of them)
+static int forward(pe_model* m, int ncrop, int nimg) {
+  cudaStream_t st = m->e->stream;
+  const pe_model_desc& d = m->d;
+  m->ev_used = 0;
+  if (m->profile) cudaEventRecord(m->ev_fwd0, st);
+  for (size_t i = 0; i < m->ops.size(); ++i) {
+    const pe_op_desc& op = m->ops[i];
+    const pe_tensor_desc& to = m->tensors[op.out];
+    const bool is_conv = (op.kind == PE_OP_CONV);
+    if (m->profile && is_conv) {
+      if (m->ev_used == m->ev_conv.size()) {
+        cudaEvent_t a, b;
+        cudaEventCreate(&a); cudaEventCreate(&b);
+        m->ev_conv.push_back({a, b});
+      }
+      cudaEventRecord(m->ev_conv[m->ev_used].first, st);
+    }
+    switch (op.kind) {
+      case PE_OP_STEM:
+        launch_stem(m->d_crops, ncrop, nimg, d.in_h, d.in_w, m->d_lut, m->d_w + op.w_off, m->d_w + op.b_off,
+                    act_ptr(m, op.out), to.H, to.W, st);
+        break;
+      case PE_OP_CONV: {
+        const pe_tensor_desc& ti = m->tensors[op.in[0]];
+        if (m->tc[i]) {
+          cudaError_t ce = tc_conv_launch(m->tc[i], nimg, st);
+          if (ce != cudaSuccess) return fail(PE_ERR_CUDA, "tensor-core conv op %zu: %s", i, cudaGetErrorString(ce));
+        } else {
+          launch_conv_simt(act_ptr(m, op.in[0]), act_ptr(m, op.out), op.residual >= 0 ? act_ptr(m, op.residual) : nullptr,
+                           m->d_w + op.w_off, m->d_w + op.b_off, op.cin, op.cout, op.ksize, op.stride, op.relu, ti.H, ti.W,
+                           to.H, to.W, nimg, st);
+        }
+        break;
+      }
+      case PE_OP_FUSE: {
+        const float* ins[4];
+        int ups[4];
+        for (int j = 0; j < op.n_in; ++j) { ins[j] = act_ptr(m, op.in[j]); ups[j] = op.up[j]; }
+        launch_fuse(ins, ups, op.n_in, act_ptr(m, op.out), to.C, to.H, to.W, nimg, op.relu, st);
+        break;
+      }
+      case PE_OP_HEAD: {
+        const pe_tensor_desc& ti = m->tensors[op.in[0]];
+        launch_head(act_ptr(m, op.in[0]), op.cin, ti.H, ti.W, nimg, m->d_w + op.w_off, m->d_w + op.b_off, op.cout, m->d_hm, st);
+        break;
+      }
+      default:
+        return fail(PE_ERR_INVALID, "unknown op kind %d", op.kind);
+    }
+    if (m->profile && is_conv) { cudaEventRecord(m->ev_conv[m->ev_used].second, st); ++m->ev_used; }
+    ++m->launches;
+  }
+  if (m->profile) cudaEventRecord(m->ev_fwd1, st);
+  CU(cudaGetLastError());
+  m->nimg_last = nimg; m->ncrop_last = ncrop;
+  return PE_OK;
+}
+
+static int profile_collect(pe_model* m) {
+  if (!m->profile) return PE_OK;
+  CU(cudaEventSynchronize(m->ev_fwd1));
+  float ms = 0;
+  for (size_t i = 0; i < m->ev_used; ++i) {
+    CU(cudaEventElapsedTime(&ms, m->ev_conv[i].first, m->ev_conv[i].second));
+    m->acc_conv_ms += ms;
+  }
+  m->acc_conv_launches += (int64_t)m->ev_used;
+  CU(cudaEventElapsedTime(&ms, m->ev_fwd0, m->ev_fwd1));
+  m->acc_total_ms += ms;
+  return PE_OK;
+}
+
+static int check_crops(pe_model* m, const int32_t* frame_idx, const double* bbox, int n) {
+  if (!m || !frame_idx || !bbox || n < 0) return fail(PE_ERR_INVALID, "bad argument");
+  if (!m->e->frames) return fail(PE_ERR_STATE, "no frames staged: call pe_stage_frames first");
+  for (int i = 0; i < n; ++i)
+    if (frame_idx[i] < 0 || frame_idx[i] >= m->e->n_frames)
+      return fail(PE_ERR_STATE, "frame_idx[%d]=%d is not a staged frame (%d staged)", i, frame_idx[i], m->e->n_frames);
+  return PE_OK;
+}
+
+// host maths + H2D of per-crop parameters + crop kernel for crops [i0, i0+nc)
+static int stage_crops(pe_model* m, const int32_t* frame_idx, const double* bbox, int i0, int nc) {
+  cudaStream_t st = m->e->stream;
+  const int maxc = m->d.max_crops;
+  float* h_center = m->h_cs;
+  float* h_scale = m->h_cs + 2 * maxc;
+  for (int i = 0; i < nc; ++i) {
+    double trans[6];
+    box_to_affine(&m->d, bbox + (size_t)(i0 + i) * 4, h_center + 2 * i, h_scale + 2 * i, trans);
+    invert_affine(trans, m->h_minv + 6 * i);
+    m->h_fidx[i] = frame_idx[i0 + i];
+  }
+  CU(cudaMemcpyAsync(m->d_minv, m->h_minv, sizeof(double) * 6 * nc, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(m->d_fidx, m->h_fidx, sizeof(int32_t) * nc, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(m->d_cs, m->h_cs, sizeof(float) * 4 * maxc, cudaMemcpyHostToDevice, st));
+  launch_warp_crop(m->e->frames, m->e->fh, m->e->fw, m->d_fidx, m->d_minv, m->d_crops, nc, m->d.in_h, m->d.in_w,
+                   m->d.swap_rb, st);
+  ++m->launches;
+  CU(cudaGetLastError());
+  return PE_OK;
+}
+
+static int run_decode(pe_model* m, const float* d_hm, const float* d_hm_flip, const float* d_center, const float* d_scale,
+                      int nc, float* d_out) {
+  cudaError_t ce = launch_decode(d_hm, d_hm_flip, m->d_perm, d_center, d_scale, d_out, nc, m->d.num_joints, m->d.hm_h,
+                                 m->d.hm_w, m->d.shift_heatmap, m->d.post_process, m->d.blur_kernel, m->e->stream);
+  ++m->launches;
+  if (ce != cudaSuccess) return fail(PE_ERR_CUDA, "decode launch: %s", cudaGetErrorString(ce));
+  return PE_OK;
+}
+
+extern "C" int pe_topdown(pe_model* m, const int32_t* frame_idx, const double* bbox_xywh, int32_t n, float* out_kpts) {
+  int rc = check_crops(m, frame_idx, bbox_xywh, n);
+  if (rc) return rc;
+  if (!out_kpts) return fail(PE_ERR_INVALID, "out_kpts is NULL");
+  CU(cudaSetDevice(m->e->device));
+  cudaStream_t st = m->e->stream;
+  const int maxc = m->d.max_crops, K = m->d.num_joints;
+  const size_t hm_img = (size_t)K * m->d.hm_h * m->d.hm_w;
+  for (int i0 = 0; i0 < n; i0 += maxc) {
+    const int nc = std::min(maxc, n - i0);
+    const int nimg = nc * (m->d.flip_test ? 2 : 1);
+    if ((rc = stage_crops(m, frame_idx, bbox_xywh, i0, nc))) return rc;
+    if ((rc = forward(m, nc, nimg))) return rc;
+    if ((rc = run_decode(m, m->d_hm, m->d.flip_test ? m->d_hm + hm_img * nc : nullptr, m->d_cs, m->d_cs + 2 * maxc, nc, m->d_out))) return rc;
+    CU(cudaMemcpyAsync(m->h_out, m->d_out, sizeof(float) * (size_t)nc * K * 3, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if ((rc = profile_collect(m))) return rc;
+    memcpy(out_kpts + (size_t)i0 * K * 3, m->h_out, sizeof(float) * (size_t)nc * K * 3);
+  }
+  return PE_OK;
+}
+
+extern "C" int pe_topdown_async(pe_model* m, const int32_t* frame_idx, const double* bbox_xywh, int32_t n, float* out_kpts_pinned) {
+  // single-chunk variant without the host wait; the caller syncs with pe_engine_sync
+  int rc = check_crops(m, frame_idx, bbox_xywh, n);
+  if (rc) return rc;
+  if (n > m->d.max_crops) return fail(PE_ERR_INVALID, "pe_topdown_async handles at most max_crops=%d crops per call", m->d.max_crops);
+  CU(cudaSetDevice(m->e->device));
+  cudaStream_t st = m->e->stream;
+  const int K = m->d.num_joints;
+  const size_t hm_img = (size_t)K * m->d.hm_h * m->d.hm_w;
+  CU(cudaStreamSynchronize(st));   // pinned parameter staging is single-buffered
+  if ((rc = stage_crops(m, frame_idx, bbox_xywh, 0, n))) return rc;
+  if ((rc = forward(m, n, n * (m->d.flip_test ? 2 : 1)))) return rc;
+  if ((rc = run_decode(m, m->d_hm, m->d.flip_test ? m->d_hm + hm_img * n : nullptr, m->d_cs, m->d_cs + 2 * m->d.max_crops, n, m->d_out))) return rc;
+  if (out_kpts_pinned) CU(cudaMemcpyAsync(out_kpts_pinned, m->d_out, sizeof(float) * (size_t)n * K * 3, cudaMemcpyDeviceToHost, st));
+  return PE_OK;
+}
+
+extern "C" int pe_warp_crops(pe_model* m, const int32_t* frame_idx, const double* bbox_xywh, int32_t n, uint8_t* out_crops,
+                             float* out_center, float* out_scale) {
+  int rc = check_crops(m, frame_idx, bbox_xywh, n);
+  if (rc) return rc;
+  CU(cudaSetDevice(m->e->device));
+  const int maxc = m->d.max_crops;
+  const size_t cb = (size_t)m->d.in_h * m->d.in_w * 3;
+  for (int i0 = 0; i0 < n; i0 += maxc) {
+    const int nc = std::min(maxc, n - i0);
+    if ((rc = stage_crops(m, frame_idx, bbox_xywh, i0, nc))) return rc;
+    if (out_crops) CU(cudaMemcpyAsync(out_crops + cb * i0, m->d_crops, cb * nc, cudaMemcpyDeviceToHost, m->e->stream));
+    CU(cudaStreamSynchronize(m->e->stream));
+    if (out_center) memcpy(out_center + 2 * i0, m->h_cs, sizeof(float) * 2 * nc);
+    if (out_scale) memcpy(out_scale + 2 * i0, m->h_cs + 2 * maxc, sizeof(float) * 2 * nc);
+  }
+  return PE_OK;
+}
+
+extern "C" int pe_forward_heatmaps(pe_model* m, const uint8_t* crops, int32_t n, float* hm_plain, float* hm_flipped) {
+  if (!m || !crops || n <= 0 || !hm_plain) return fail(PE_ERR_INVALID, "bad argument to pe_forward_heatmaps");
+  CU(cudaSetDevice(m->e->device));
+  cudaStream_t st = m->e->stream;
+  const int maxc = m->d.max_crops, K = m->d.num_joints;
+  const size_t cb = (size_t)m->d.in_h * m->d.in_w * 3;
+  const size_t hm_img = (size_t)K * m->d.hm_h * m->d.hm_w;
+  const bool flip = m->d.flip_test && hm_flipped;
+  for (int i0 = 0; i0 < n; i0 += maxc) {
+    const int nc = std::min(maxc, n - i0);
+    CU(cudaMemcpyAsync(m->d_crops, crops + cb * i0, cb * nc, cudaMemcpyHostToDevice, st));
+    int rc = forward(m, nc, nc * (m->d.flip_test ? 2 : 1));
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(hm_plain + hm_img * i0, m->d_hm, sizeof(float) * hm_img * nc, cudaMemcpyDeviceToHost, st));
+    if (flip) CU(cudaMemcpyAsync(hm_flipped + hm_img * i0, m->d_hm + hm_img * nc, sizeof(float) * hm_img * nc, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if ((rc = profile_collect(m))) return rc;
+  }
+  return PE_OK;
+}
+
+extern "C" int pe_decode_heatmaps(pe_model* m, const float* hm_plain, const float* hm_flipped, const float* center,
+                                  const float* scale, int32_t n, float* out_kpts) {
+  if (!m || !hm_plain || !center || !scale || !out_kpts || n <= 0) return fail(PE_ERR_INVALID, "bad argument to pe_decode_heatmaps");
+  CU(cudaSetDevice(m->e->device));
+  cudaStream_t st = m->e->stream;
+  const int maxc = m->d.max_crops, K = m->d.num_joints;
+  const size_t hm_img = (size_t)K * m->d.hm_h * m->d.hm_w;
+  for (int i0 = 0; i0 < n; i0 += maxc) {
+    const int nc = std::min(maxc, n - i0);
+    CU(cudaMemcpyAsync(m->d_hm, hm_plain + hm_img * i0, sizeof(float) * hm_img * nc, cudaMemcpyHostToDevice, st));
+    if (hm_flipped) CU(cudaMemcpyAsync(m->d_hm + hm_img * nc, hm_flipped + hm_img * i0, sizeof(float) * hm_img * nc, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(m->d_cs, center + 2 * i0, sizeof(float) * 2 * nc, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(m->d_cs + 2 * maxc, scale + 2 * i0, sizeof(float) * 2 * nc, cudaMemcpyHostToDevice, st));
+    int rc = run_decode(m, m->d_hm, hm_flipped ? m->d_hm + hm_img * nc : nullptr, m->d_cs, m->d_cs + 2 * maxc, nc, m->d_out);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(out_kpts + (size_t)i0 * K * 3, m->d_out, sizeof(float) * (size_t)nc * K * 3, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+  }
+  return PE_OK;
+}
+
+extern "C" int pe_debug_tensor(pe_model* m, int32_t tensor_id, int32_t img, float* out_chw) {
+  if (!m || !out_chw || tensor_id < 0 || tensor_id >= (int)m->tensors.size()) return fail(PE_ERR_INVALID, "bad argument to pe_debug_tensor");
+  if (img < 0 || img >= m->nimg_last) return fail(PE_ERR_STATE, "image %d not in the last forward batch (%d images)", img, m->nimg_last);
+  CU(cudaSetDevice(m->e->device));
+  const pe_tensor_desc& t = m->tensors[tensor_id];
+  float* tmp = nullptr;
+  const size_t nel = (size_t)t.C * t.H * t.W;
+  CU(cudaMalloc(&tmp, nel * sizeof(float)));
+  launch_ps_to_chw(act_ptr(m, tensor_id), t.C, t.H, t.W, img, tmp, m->e->stream);
+  cudaError_t ce = cudaMemcpyAsync(out_chw, tmp, nel * sizeof(float), cudaMemcpyDeviceToHost, m->e->stream);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(m->e->stream);
+  cudaFree(tmp);
+  if (ce != cudaSuccess) return fail(PE_ERR_CUDA, "pe_debug_tensor: %s", cudaGetErrorString(ce));
+  return PE_OK;
+}
+
+extern "C" int pe_model_launch_count(pe_model* m, int64_t* count) {
+  if (!m || !count) return fail(PE_ERR_INVALID, "bad argument");
+  *count = m->launches;
+  return PE_OK;
+}
+
+extern "C" int pe_model_profile(pe_model* m, int32_t enable) {
+  if (!m) return fail(PE_ERR_INVALID, "bad argument");
+  m->profile = enable;
+  m->acc_conv_ms = m->acc_total_ms = 0; m->acc_conv_launches = 0;
+  return PE_OK;
+}
+
+extern "C" int pe_model_profile_read(pe_model* m, double* conv_ms, double* other_ms, int64_t* conv_launches) {
+  if (!m) return fail(PE_ERR_INVALID, "bad argument");
+  if (conv_ms) *conv_ms = m->acc_conv_ms;
+  if (other_ms) *other_ms = m->acc_total_ms - m->acc_conv_ms;
+  if (conv_launches) *conv_launches = m->acc_conv_launches;
+  return PE_OK;
+}

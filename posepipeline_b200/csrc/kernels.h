@@ -1,0 +1,32 @@
+// Launchers shared between the kernel translation units and the C-ABI host code.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+void launch_warp_crop(const uint8_t* frames, int fh, int fw, const int32_t* frame_idx, const double* minv,
+                      uint8_t* crops, int n, int ch, int cw, int swap_rb, cudaStream_t st);
+void launch_stem(const uint8_t* crops, int ncrop, int nimg, int ih, int iw, const float* lut, const float* w,
+                 const float* bias, float* out, int oh, int ow, cudaStream_t st);
+void launch_conv_simt(const float* in, float* out, const float* res, const float* w, const float* bias, int Cin,
+                      int Cout, int ks, int stride, int relu, int Hin, int Win, int Hout, int Wout, int nimg,
+                      cudaStream_t st);
+void launch_conv_linear(const float* in, float* out, const float* res, const float* w, const float* bias, int Cin,
+                        int Cout, int ntaps, int dil, int relu, long long M, int res_off, int plain_out, int cout_real,
+                        cudaStream_t st);
+void launch_fuse(const float* const* in, const int* up, int n_in, float* out, int C, int H, int W, int nimg, int relu,
+                 cudaStream_t st);
+void launch_head(const float* in, int Cin, int H, int W, int nimg, const float* w, const float* bias, int K, float* out,
+                 cudaStream_t st);
+void launch_ps_to_chw(const float* in, int C, int H, int W, int img, float* out, cudaStream_t st);
+
+void upload_gauss_kernel(const float* taps, int k);
+cudaError_t launch_decode(const float* hm, const float* hm_flip, const int* flip_perm, const float* center,
+                          const float* scale, float* out, int n, int K, int H, int W, int shift, int post, int ksize,
+                          cudaStream_t st);
+
+// Shifted-row GEMM on tensor cores (conv_tc.cu).  Returns cudaErrorNotSupported for shapes it does not cover.
+struct TcConvPlan;
+cudaError_t tc_conv_plan_create(TcConvPlan** plan, const float* in, float* out, const float* res, const float* wtc,
+                                const float* bias, int Cin, int Cout, int ks, int relu, int H, int W, int max_img);
+void tc_conv_plan_destroy(TcConvPlan* plan);
+cudaError_t tc_conv_launch(TcConvPlan* plan, int nimg, cudaStream_t st);

@@ -1,0 +1,352 @@
+"""Python host over the C ABI (include/poseengine.h): engine / top-down model / lifter objects.
+
+This is the layer the reference-compatible wrappers (posepipeline_b200/wrappers/*.py) call.  It owns no
+arithmetic: it builds the layer program (hrnet_spec), folds BatchNorm, packs weights and calls
+libposeengine.so.  There is no CPU fallback; constructing an engine without a B200 raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import ModelDesc, OpDesc, TensorDesc, check, ptr
+from .hrnet_spec import OP_CONV, OP_FUSE, OP_HEAD, OP_STEM, Program, build_program
+from .weights import bn_of, fold_bn
+
+COCO_FLIP_PAIRS = [[1, 2], [3, 4], [5, 6], [7, 8], [9, 10], [11, 12], [13, 14], [15, 16]]
+
+
+@dataclass
+class TopDownSpec:
+    """What the mmpose config of a method contributes to the arithmetic (reference
+    3rdparty/mmpose/config/top_down/darkpose/coco/hrnet_w48_coco_384x288_dark.py:40-102,129-144)."""
+    variant: str = "w48"
+    image_size: Tuple[int, int] = (288, 384)        # (W, H)
+    heatmap_size: Tuple[int, int] = (72, 96)        # (W, H)
+    num_joints: int = 17
+    flip_test: bool = True
+    post_process: Optional[str] = "unbiased"
+    shift_heatmap: bool = True
+    modulate_kernel: int = 17
+    padding: float = 1.25
+    flip_pairs: List[List[int]] = field(default_factory=lambda: [list(p) for p in COCO_FLIP_PAIRS])
+    mean: Tuple[float, float, float] = (0.485, 0.456, 0.406)
+    std: Tuple[float, float, float] = (0.229, 0.224, 0.225)
+    wrapper_double_swap: bool = True
+    checkpoint: Optional[str] = None               # path under MODEL_DATA_DIR (reference wrappers/mmpose.py:33-52)
+
+
+METHODS: Dict[str, TopDownSpec] = {
+    # reference wrappers/mmpose.py:33-36
+    "HRNet_W48_COCO": TopDownSpec(checkpoint="mmpose/checkpoints/hrnet_w48_coco_384x288_dark-e881a4b6_20210203.pth"),
+    # BASELINE config 1 (upstream hrnet_w32_coco_256x192.py; not configured in the reference)
+    "HRNet_W32_COCO": TopDownSpec(variant="w32", image_size=(192, 256), heatmap_size=(48, 64), post_process="default",
+                                  modulate_kernel=11, checkpoint="mmpose/checkpoints/hrnet_w32_coco_256x192-c78dce93_20200708.pth"),
+}
+
+
+def tf32_split(x: np.ndarray):
+    """hi = x rounded to TF32 (nearest, ties away: cvt.rna.tf32.f32), lo = x - hi (exact)."""
+    x = np.ascontiguousarray(x, np.float32)
+    bits = x.view(np.uint32)
+    hi = ((bits + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
+    return hi, (x - hi).astype(np.float32)
+
+
+class WeightBlob:
+    def __init__(self):
+        self.parts: List[np.ndarray] = []
+        self.n = 0
+
+    def add(self, a: np.ndarray) -> int:
+        a = np.ascontiguousarray(a, np.float32).ravel()
+        off = self.n
+        pad = (-a.size) % 64
+        self.parts.append(a)
+        if pad:
+            self.parts.append(np.zeros(pad, np.float32))
+        self.n += a.size + pad
+        return off
+
+    def array(self) -> np.ndarray:
+        return np.concatenate(self.parts) if self.parts else np.zeros(0, np.float32)
+
+
+def pack_tc_weights(w: np.ndarray) -> np.ndarray:
+    """(Cout,Cin,k,k) folded fp32 -> tensor-core operand [tap][Cin/16][Cout][hi16|lo16] (see csrc/conv_tc.cu)."""
+    cout, cin, k, _ = w.shape
+    t = w.transpose(2, 3, 1, 0).reshape(k * k, cin // 16, 16, cout).transpose(0, 1, 3, 2)   # tap, chunk, cout, 16
+    hi, lo = tf32_split(t)
+    return np.concatenate([hi, lo], axis=3)
+
+
+class PoseEngine:
+    """One per process per GPU.  ``stream``: optional cudaStream_t handle (int) to run on."""
+
+    def __init__(self, device: int = 0, stream: Optional[int] = None):
+        self.lib = _lib.load()
+        h = C.c_void_p()
+        check(self.lib.pe_engine_create(int(device), C.c_void_p(stream) if stream else None, C.byref(h)))
+        self.h = h
+        self.device = device
+        self._frames_keepalive = None
+
+    def stage_frames(self, frames: np.ndarray):
+        """frames (n,H,W,3) uint8 BGR as cv2 returns them.  Asynchronous H2D on the engine stream."""
+        if frames.dtype != np.uint8 or frames.ndim != 4 or frames.shape[3] != 3:
+            raise ValueError("frames must be (n,H,W,3) uint8")
+        if not frames.flags.c_contiguous:
+            frames = np.ascontiguousarray(frames)
+        self._frames_keepalive = frames
+        n, H, W, _ = frames.shape
+        check(self.lib.pe_stage_frames(self.h, ptr(frames), n, H, W, 0))
+        self.n_frames = n
+
+    def stage_frames_device(self, dev_ptr: int, n: int, H: int, W: int):
+        check(self.lib.pe_stage_frames_device(self.h, C.c_void_p(dev_ptr), n, H, W))
+        self.n_frames = n
+
+    def sync(self):
+        check(self.lib.pe_engine_sync(self.h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.pe_engine_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def model_desc(spec: TopDownSpec, n_ops=0, n_tensors=0, n_slots=0, max_crops=1, use_tc=False) -> ModelDesc:
+    return ModelDesc(in_h=spec.image_size[1], in_w=spec.image_size[0], hm_h=spec.heatmap_size[1], hm_w=spec.heatmap_size[0],
+                     num_joints=spec.num_joints, n_ops=n_ops, n_tensors=n_tensors, n_slots=n_slots, max_crops=max_crops,
+                     flip_test=int(spec.flip_test), shift_heatmap=int(spec.shift_heatmap),
+                     post_process=_lib.PE_POST[spec.post_process], blur_kernel=spec.modulate_kernel,
+                     swap_rb=0 if spec.wrapper_double_swap else 1, use_tensor_cores=int(use_tc), reserved=0,
+                     padding=spec.padding, pixel_std=200.0)
+
+
+def box_to_affine(spec: TopDownSpec, bbox_xywh):
+    """Host-side a5/a6 maths of the library (no GPU needed): -> center f32(2), scale f32(2), trans f64(2,3)."""
+    lib = _lib.load()
+    d = model_desc(spec)
+    bb = np.ascontiguousarray(bbox_xywh, np.float64)
+    c, s, t = np.zeros(2, np.float32), np.zeros(2, np.float32), np.zeros(6, np.float64)
+    check(lib.pe_box_to_affine(C.byref(d), ptr(bb), ptr(c), ptr(s), ptr(t)))
+    return c, s, t.reshape(2, 3)
+
+
+class TopDownModel:
+    """mmpose ``init_pose_model`` + ``inference_top_down_pose_model`` replacement for one method."""
+
+    def __init__(self, engine: PoseEngine, state_dict: Dict[str, np.ndarray], spec: TopDownSpec, max_crops: int = 32,
+                 use_tensor_cores: bool = True, unique_slots: bool = False):
+        self.engine, self.spec, self.lib = engine, spec, engine.lib
+        self.max_crops = max_crops
+        prog = build_program(spec.variant, spec.image_size[1], spec.image_size[0], spec.num_joints)
+        self.program = prog
+        missing = [k for k in prog.params if k not in state_dict]
+        if missing:
+            raise KeyError(f"checkpoint is missing {len(missing)} tensors, e.g. {missing[:3]}")
+        blob = WeightBlob()
+        ops = (OpDesc * len(prog.ops))()
+        for i, op in enumerate(prog.ops):
+            o = ops[i]
+            o.kind, o.out = op.kind, op.out
+            ins = list(op.ins) + [-1] * (4 - len(op.ins))
+            ups = list(op.ups) + [1] * (4 - len(op.ups))
+            for j in range(4):
+                o.inp[j], o.up[j] = ins[j], ups[j]
+            o.n_in, o.ksize, o.stride, o.cin, o.cout = len(op.ins), op.ksize, op.stride, op.cin, op.cout
+            o.relu, o.residual, o.reserved = int(op.relu), op.residual, 0
+            o.w_off = o.b_off = 0
+            o.wtc_off = -1
+            if op.kind in (OP_STEM, OP_CONV, OP_HEAD):
+                w = state_dict[f"{op.conv}.weight"]
+                cb = state_dict.get(f"{op.conv}.bias") if op.has_bias else None
+                wf, bf = fold_bn(w, bn_of(state_dict, op.bn) if op.bn else None, cb)
+                k = op.ksize
+                if op.kind == OP_HEAD:
+                    o.w_off = blob.add(wf.reshape(op.cout, op.cin).T)                      # [Cin][K]
+                else:
+                    o.w_off = blob.add(wf.transpose(2, 3, 1, 0).reshape(k * k, op.cin, op.cout))   # [tap][Cin][Cout]
+                o.b_off = blob.add(bf)
+                if use_tensor_cores and op.kind == OP_CONV and op.stride == 1 and op.cin % 16 == 0 and op.cout % 16 == 0:
+                    o.wtc_off = blob.add(pack_tc_weights(wf))
+        if unique_slots:
+            slot_of = list(range(len(prog.tensors)))
+            slot_elems = [(t.H + 2) * (t.W + 2) * t.C for t in prog.tensors]
+        else:
+            slot_of, slot_elems = prog.assign_slots()
+        tens = (TensorDesc * len(prog.tensors))()
+        for t in prog.tensors:
+            tens[t.tid].C, tens[t.tid].H, tens[t.tid].W, tens[t.tid].slot = t.C, t.H, t.W, slot_of[t.tid]
+        self.slot_elems = np.asarray(slot_elems, np.int64)
+        desc = model_desc(spec, len(prog.ops), len(prog.tensors), len(slot_elems), max_crops, use_tensor_cores)
+        lut = np.stack([((np.arange(256, dtype=np.float32) / np.float32(255.0)) - np.float32(spec.mean[c])) / np.float32(spec.std[c])
+                        for c in range(3)]).astype(np.float32)
+        perm = np.arange(spec.num_joints, dtype=np.int32)
+        for a, b in spec.flip_pairs:
+            perm[a], perm[b] = b, a
+        weights = blob.array()
+        self.weight_floats = weights.size
+        h = C.c_void_p()
+        check(self.lib.pe_model_create(engine.h, C.byref(desc), ops, tens, ptr(self.slot_elems), ptr(weights), weights.size,
+                                       ptr(lut), ptr(perm), C.byref(h)))
+        self.h = h
+        self.desc = desc
+
+    # ---- the hot path
+    def topdown(self, frame_idx: Sequence[int], bboxes_xywh: np.ndarray) -> np.ndarray:
+        """(n,) staged-frame indices + (n,4) float64 x,y,w,h -> (n,K,3) float32 [x_px, y_px, score]."""
+        fi = np.ascontiguousarray(frame_idx, np.int32)
+        bb = np.ascontiguousarray(bboxes_xywh, np.float64).reshape(-1, 4)
+        out = np.empty((len(fi), self.spec.num_joints, 3), np.float32)
+        if len(fi):
+            check(self.lib.pe_topdown(self.h, ptr(fi), ptr(bb), len(fi), ptr(out)))
+        return out
+
+    def topdown_async(self, frame_idx, bboxes_xywh, out_pinned_ptr: int = 0):
+        fi = np.ascontiguousarray(frame_idx, np.int32)
+        bb = np.ascontiguousarray(bboxes_xywh, np.float64).reshape(-1, 4)
+        check(self.lib.pe_topdown_async(self.h, ptr(fi), ptr(bb), len(fi), C.c_void_p(out_pinned_ptr) if out_pinned_ptr else None))
+
+    # ---- parity hooks
+    def warp_crops(self, frame_idx, bboxes_xywh):
+        fi = np.ascontiguousarray(frame_idx, np.int32)
+        bb = np.ascontiguousarray(bboxes_xywh, np.float64).reshape(-1, 4)
+        n = len(fi)
+        W, H = self.spec.image_size
+        crops = np.empty((n, H, W, 3), np.uint8)
+        c, s = np.empty((n, 2), np.float32), np.empty((n, 2), np.float32)
+        check(self.lib.pe_warp_crops(self.h, ptr(fi), ptr(bb), n, ptr(crops), ptr(c), ptr(s)))
+        return crops, c, s
+
+    def forward_heatmaps(self, crops_u8: np.ndarray):
+        crops = np.ascontiguousarray(crops_u8, np.uint8)
+        n = crops.shape[0]
+        W, H = self.spec.heatmap_size
+        hm = np.empty((n, self.spec.num_joints, H, W), np.float32)
+        hmf = np.empty_like(hm) if self.spec.flip_test else None
+        check(self.lib.pe_forward_heatmaps(self.h, ptr(crops), n, ptr(hm), ptr(hmf) if hmf is not None else None))
+        return hm, hmf
+
+    def decode_heatmaps(self, hm, hm_flipped, center, scale):
+        hm = np.ascontiguousarray(hm, np.float32)
+        n = hm.shape[0]
+        hf = np.ascontiguousarray(hm_flipped, np.float32) if hm_flipped is not None else None
+        c, s = np.ascontiguousarray(center, np.float32), np.ascontiguousarray(scale, np.float32)
+        out = np.empty((n, self.spec.num_joints, 3), np.float32)
+        check(self.lib.pe_decode_heatmaps(self.h, ptr(hm), ptr(hf) if hf is not None else None, ptr(c), ptr(s), n, ptr(out)))
+        return out
+
+    def debug_tensor(self, tensor_id: int, img: int = 0) -> np.ndarray:
+        t = self.program.tensors[tensor_id]
+        out = np.empty((t.C, t.H, t.W), np.float32)
+        check(self.lib.pe_debug_tensor(self.h, tensor_id, img, ptr(out)))
+        return out
+
+    def launch_count(self) -> int:
+        v = C.c_int64()
+        check(self.lib.pe_model_launch_count(self.h, C.byref(v)))
+        return v.value
+
+    def profile(self, enable: bool):
+        check(self.lib.pe_model_profile(self.h, int(enable)))
+
+    def profile_read(self):
+        a, b, n = C.c_double(), C.c_double(), C.c_int64()
+        check(self.lib.pe_model_profile_read(self.h, C.byref(a), C.byref(b), C.byref(n)))
+        return a.value, b.value, n.value
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.pe_model_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Lifter:
+    """VideoPose3D TemporalModelOptimized1f (243 frames) on the GPU (reference wrappers/videopose3d.py:46-85)."""
+
+    def __init__(self, engine: PoseEngine, state_dict: Dict[str, np.ndarray], channels: int = 1024):
+        self.engine, self.lib = engine, engine.lib
+        blob = WeightBlob()
+        offs: List[int] = []
+
+        def add(wname, bnname, pad_in=None, pad_out=None, bias=None):
+            w = state_dict[wname]                                        # (Cout, Cin, k)
+            wf, bf = fold_bn(w, bn_of(state_dict, bnname) if bnname else None, bias)
+            cout, cin, k = wf.shape
+            ci, co = pad_in or cin, pad_out or cout
+            wp = np.zeros((k, ci, co), np.float32)
+            wp[:, :cin, :cout] = wf.transpose(2, 1, 0)
+            bp = np.zeros(co, np.float32)
+            bp[:cout] = bf
+            offs.extend([blob.add(wp), blob.add(bp)])
+
+        add("expand_conv.weight", "expand_bn", pad_in=48)
+        for i in range(4):
+            add(f"layers_conv.{2 * i}.weight", f"layers_bn.{2 * i}")
+            add(f"layers_conv.{2 * i + 1}.weight", f"layers_bn.{2 * i + 1}")
+        add("shrink.weight", None, pad_out=64, bias=state_dict["shrink.bias"])
+        w = blob.array()
+        offs_a = np.asarray(offs, np.int64)
+        h = C.c_void_p()
+        check(self.lib.pe_lifter_create(engine.h, ptr(w), w.size, ptr(offs_a), len(offs), channels, C.byref(h)))
+        self.h = h
+
+    def lift(self, kp2d_norm: np.ndarray) -> np.ndarray:
+        """(N,17,2) normalised screen coordinates -> (N,17,3) float32."""
+        x = np.ascontiguousarray(kp2d_norm, np.float32).reshape(-1, 34)
+        out = np.empty((x.shape[0], 17, 3), np.float32)
+        check(self.lib.pe_lift3d(self.h, ptr(x), x.shape[0], ptr(out)))
+        return out
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.pe_lifter_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def person_bbox(tracks, keep_tracks):
+    """``PersonBbox.make`` arithmetic (reference pipeline.py:661-685) through the C ABI (host-only, bit-exact)."""
+    lib = _lib.load()
+    if len(tracks) == 0:
+        raise IndexError("list index out of range")                    # reference: LD[0] on an empty video
+    counts = np.asarray([len(f) for f in tracks], np.int32)
+    ids = np.asarray([int(t["track_id"]) for f in tracks for t in f], np.int64)
+    boxes = [np.asarray(t["tlhw"]) for f in tracks for t in f]
+    tl = np.asarray(boxes, np.float64).reshape(-1, 4) if boxes else np.zeros((0, 4), np.float64)
+    keep = np.asarray(list(keep_tracks), np.int64).reshape(-1)
+    n = len(tracks)
+    bbox = np.empty((n, 4), np.float64)
+    present = np.empty(n, np.uint8)
+    check(lib.pe_person_bbox(ptr(counts), n, ptr(ids), ptr(tl), ptr(keep), len(keep), ptr(bbox), ptr(present)))
+    present = present.astype(bool)
+    # np.array(list-of-bbox) in the reference is float32 only if every frame contributed a float32 tlhw array
+    if boxes and all(b.dtype == np.float32 for b in boxes):
+        raw_present = np.asarray([sum(int(t["track_id"]) in set(keep.tolist()) for t in f) == 1 for f in tracks])
+        if raw_present.all():
+            bbox = bbox.astype(np.float32)
+    return bbox, present

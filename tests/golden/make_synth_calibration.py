@@ -1,0 +1,78 @@
+"""Generates posepipeline_b200/data/synthetic_head_calibration.npz (run once, here, with the oracle).
+
+Random HRNet weights give flat heatmaps on which DARK's Taylor step is ill-conditioned.  This
+script calibrates (a) a per-channel bias on the last fuse sum so the 48 final features are sparse
+bumps, and (b) a sparse positive head, so synthetic heatmaps look like a trained network's:
+~0 background with O(1) peaks.  Only 48 + 17*48 + 17 numbers per variant are stored.
+
+    python tests/golden/make_synth_calibration.py
+"""
+import os, sys
+import numpy as np
+import torch
+import torch.nn.functional as F
+import cv2
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from posepipeline_b200.hrnet_spec import build_program
+from posepipeline_b200 import weights as W
+from posepipeline_b200.synthetic import synthetic_frames, synthetic_bboxes
+from oracle.hrnet import load_net
+from oracle import topdown as T
+
+OUT = os.path.join(ROOT, "posepipeline_b200", "data", "synthetic_head_calibration.npz")
+
+
+def calibrate(variant, in_h, in_w, K, seed, cfg, n_crops=10, q=0.97):
+    prog = build_program(variant, in_h, in_w, K)
+    sd = W.synthetic_hrnet_state_dict(prog, seed, calibrated=False)
+    net = load_net(sd, variant)
+    frames = synthetic_frames(3, seed0=100)
+    bbs = synthetic_bboxes(n_crops, seed=4321)
+    xs = []
+    for i in range(n_crops):
+        x, _, _, _ = T.preprocess(cv2.cvtColor(frames[i % 3], cv2.COLOR_BGR2RGB), bbs[i], cfg)
+        xs.append(torch.from_numpy(x))
+        xs.append(torch.from_numpy(x).flip(2))
+    x = torch.stack(xs)
+    last = net.backbone.stage4[-1]
+    cap = {}
+    h = last.register_forward_pre_hook(lambda m, inp: cap.__setitem__("xs", inp[0]))
+    with torch.no_grad():
+        net(x)
+        h.remove()
+        ys = [b(t) for b, t in zip(last.branches, cap["xs"])]
+        pre = 0
+        for j in range(4):
+            pre = pre + (ys[j] if j == 0 else last.fuse_layers[0][j](ys[j]))
+    C = pre.shape[1]
+    thr = torch.quantile(pre.permute(1, 0, 2, 3).reshape(C, -1)[:, ::7], q, dim=1)
+    nm = len(net.backbone.stage4)
+    name = f"backbone.stage4.{nm - 1}.fuse_layers.0.1.1.bias"
+    fuse_bias = sd[name] - thr.numpy()
+    feat = F.relu(pre - thr[None, :, None, None])
+    rng = np.random.default_rng(seed + 17)
+    hw = np.zeros((K, C), np.float32)
+    for k in range(K):
+        ch = rng.choice(C, 8, replace=False)
+        hw[k, ch] = rng.uniform(0.5, 1.0, 8)
+    hm = torch.einsum("kc,bchw->bkhw", torch.from_numpy(hw), feat)
+    mx = hm.flatten(2).max(dim=2).values.median(dim=0).values.numpy()
+    assert (mx > 0).all(), mx
+    hw = hw * (0.85 / mx)[:, None]
+    hb = np.full((K,), 0.002, np.float32)
+    return {"fuse_bias": fuse_bias.astype(np.float32), "head_weight": hw.reshape(K, C, 1, 1).astype(np.float32),
+            "head_bias": hb}
+
+
+if __name__ == "__main__":
+    out = {}
+    for variant, h, w, K, seed, cfg in [("w48", 384, 288, 17, 0, T.HRNET_W48_COCO),
+                                        ("w32", 256, 192, 17, 0, T.HRNET_W32_COCO)]:
+        r = calibrate(variant, h, w, K, seed, cfg)
+        for k, v in r.items():
+            out[f"{variant}_{h}x{w}_k{K}_s{seed}/{k}"] = v
+        print(variant, {k: v.shape for k, v in r.items()})
+    np.savez(OUT, **out)
+    print("wrote", OUT)
