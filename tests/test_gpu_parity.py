@@ -1,0 +1,253 @@
+"""GPU parity suite (-m gpu): every stage of the CUDA path, through the C ABI, against the oracle."""
+import os
+
+import cv2
+import numpy as np
+import pytest
+import torch
+
+from oracle import topdown as OT
+from oracle import videopose3d as OV
+from posepipeline_b200 import engine as E
+from posepipeline_b200.hrnet_spec import OP_CONV, OP_FUSE, OP_HEAD, OP_STEM
+from posepipeline_b200.synthetic import synthetic_bboxes, synthetic_keypoints_2d
+from posepipeline_b200.weights import synthetic_videopose3d_state_dict
+
+from conftest import ROOT
+import helpers
+
+pytestmark = pytest.mark.gpu
+USE_TC = os.environ.get("PE_TEST_TC", "1") == "1"
+
+
+@pytest.fixture(scope="module")
+def eng():
+    e = E.PoseEngine(0)
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def model48(eng):
+    m = E.TopDownModel(eng, helpers.state_dict("HRNet_W48_COCO"), E.METHODS["HRNet_W48_COCO"], max_crops=4,
+                       use_tensor_cores=USE_TC)
+    yield m
+    m.close()
+
+
+EDGE_BOXES = np.array([[-200., -100., 500., 900.], [1700., 800., 400., 500.], [5., 5., 30., 40.],
+                       [0., 0., 1920., 1080.], [900.3, 500.7, 1.0, 1.0]])
+
+
+# ------------------------------------------------------------------ K1 crop: bit-exact vs cv2.warpAffine
+def test_crop_bit_exact(eng, model48):
+    frames = helpers.frames(3)
+    eng.stage_frames(frames)
+    bbs = np.concatenate([synthetic_bboxes(9, 11), EDGE_BOXES])
+    fidx = np.arange(len(bbs)) % 3
+    crops, c, s = model48.warp_crops(fidx, bbs)           # 14 crops > max_crops=4: exercises chunking
+    for i, bb in enumerate(bbs):
+        img = cv2.cvtColor(cv2.cvtColor(frames[fidx[i]], cv2.COLOR_BGR2RGB), cv2.COLOR_BGR2RGB)   # wrapper + mmpose swaps
+        x, oc, os_, ref = OT.preprocess(cv2.cvtColor(frames[fidx[i]], cv2.COLOR_BGR2RGB), bb, OT.HRNET_W48_COCO)
+        assert np.array_equal(c[i], oc) and np.array_equal(s[i], os_)
+        assert np.array_equal(crops[i], ref), f"crop {i}: {(crops[i] != ref).sum()} pixels differ"
+
+
+# ------------------------------------------------------------------ K6 decode
+def _rand_heatmaps(rng, n, K, H, W):
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+    hm = np.zeros((n, K, H, W), np.float32)
+    for i in range(n):
+        for k in range(K):
+            cx, cy, s = rng.uniform(-1, W + 1), rng.uniform(-1, H + 1), rng.uniform(1.5, 4.0)
+            hm[i, k] = rng.uniform(0.2, 1.0) * np.exp(-((xx - cx) ** 2 + (yy - cy) ** 2) / (2 * s * s)) + np.abs(rng.normal(0, 0.003, (H, W)))
+    return hm
+
+
+def test_decode_unbiased_with_flip_merge(eng, model48):
+    rng = np.random.default_rng(5)
+    n, K, H, W = 6, 17, 96, 72
+    hm = _rand_heatmaps(rng, n, K, H, W)
+    # a flipped-pass output consistent with hm (mirrored, L/R swapped) plus noise
+    perm = np.arange(K)
+    for a, b in OT.COCO_FLIP_PAIRS:
+        perm[a], perm[b] = b, a
+    hf = hm[:, perm][..., ::-1].copy() + rng.normal(0, 0.002, hm.shape).astype(np.float32)
+    hm[0, 0] = -np.abs(hm[0, 0]); hf[0, 0] = -np.abs(hf[0, 0])          # max <= 0 -> coords -1
+    bbs = synthetic_bboxes(n, 3)
+    cs = [OT.box_to_center_scale(b, OT.HRNET_W48_COCO) for b in bbs]
+    c = np.stack([x[0] for x in cs]); s = np.stack([x[1] for x in cs])
+    got = model48.decode_heatmaps(hm, hf, c, s)
+    ref = OT.decode(OT.flip_test_heatmaps(hm, hf, OT.HRNET_W48_COCO), c, s, OT.HRNET_W48_COCO)
+    assert np.array_equal(got[..., 2], ref[..., 2])                      # scores: bit-exact
+    assert np.abs(got[..., :2] - ref[..., :2]).max() <= 1e-3, np.abs(got[..., :2] - ref[..., :2]).max()
+
+
+def test_decode_golden_reference_vectors(eng, model48):
+    """Heatmaps + refined coordinates produced by the reference's own DarkPose copy (tests/golden)."""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "dark_decode.npz"))
+    hm = z["a_heatmaps"]                                                  # (2,6,96,72), kernel 17
+    n, K = hm.shape[:2]
+    full = np.zeros((n, 17, 96, 72), np.float32)
+    full[:, :K] = hm
+    full[:, K:] = hm[:, :1]
+    # identity back-projection: scale*200 == heatmap size, center == size/2  -> output == heatmap coordinates
+    c = np.tile(np.array([[36.0, 48.0]], np.float32), (n, 1))
+    s = np.tile(np.array([[72 / 200.0, 96 / 200.0]], np.float32), (n, 1))
+    got = model48.decode_heatmaps(full, None, c, s)[:, :K]
+    pos = z["a_maxvals"][..., 0] > 0
+    assert np.array_equal(got[..., 2][pos], z["a_maxvals"][..., 0][pos])
+    assert np.abs(got[..., :2][pos] - z["a_refined"][pos]).max() < 2e-3
+    assert np.all(got[..., :2][~pos] == -1)
+
+
+def test_decode_default_postprocess(eng):
+    m = E.TopDownModel(eng, helpers.state_dict("HRNet_W32_COCO"), E.METHODS["HRNet_W32_COCO"], max_crops=2,
+                       use_tensor_cores=USE_TC)
+    rng = np.random.default_rng(9)
+    hm = _rand_heatmaps(rng, 3, 17, 64, 48)
+    hf = hm[..., ::-1].copy()
+    bbs = synthetic_bboxes(3, 8)
+    cs = [OT.box_to_center_scale(b, OT.HRNET_W32_COCO) for b in bbs]
+    c = np.stack([x[0] for x in cs]); s = np.stack([x[1] for x in cs])
+    got = m.decode_heatmaps(hm, hf, c, s)
+    ref = OT.decode(OT.flip_test_heatmaps(hm, hf, OT.HRNET_W32_COCO), c, s, OT.HRNET_W32_COCO)
+    assert np.array_equal(got, ref)                                       # argmax + sign shift: bit-exact
+    m.close()
+
+
+# ------------------------------------------------------------------ a8 network, layer by layer
+def _oracle_activations(net, prog, x):
+    """value of every program tensor in the oracle network, via hooks."""
+    acts, mods = {}, dict(net.named_modules())
+    hooks = []
+    for name, mod in mods.items():
+        hooks.append(mod.register_forward_hook(lambda m, i, o, name=name: acts.__setitem__(name, o)))
+    with torch.no_grad():
+        net(x)
+    for h in hooks:
+        h.remove()
+    out = {}
+    fuse_seen = {}
+    for op in prog.ops:
+        if op.kind in (OP_STEM, OP_CONV):
+            if op.residual >= 0:
+                v = acts[op.conv.rsplit(".", 1)[0]]                       # the residual block's output
+            else:
+                v = acts[op.bn]
+                if op.relu:
+                    v = torch.relu(v)
+        elif op.kind == OP_FUSE:
+            # fuse ops are emitted module by module, output i in order
+            continue
+        else:
+            v = acts["keypoint_head.final_layer"]
+        out[op.out] = v
+    # fuse outputs: HRModule forward returns the list
+    mod_names = [n for n, m in mods.items() if m.__class__.__name__ == "HRModule"]
+    fuse_ops = [op for op in prog.ops if op.kind == OP_FUSE]
+    k = 0
+    for n in mod_names:
+        for t in acts[n]:
+            out[fuse_ops[k].out] = t
+            k += 1
+    assert k == len(fuse_ops)
+    return out
+
+
+def test_every_layer_matches_oracle(eng):
+    spec = E.METHODS["HRNet_W48_COCO"]
+    m = E.TopDownModel(eng, helpers.state_dict("HRNet_W48_COCO"), spec, max_crops=1, use_tensor_cores=USE_TC, unique_slots=True)
+    frames = helpers.frames(3)
+    bb = synthetic_bboxes(1, 21)[0]
+    x, c, s, crop = OT.preprocess(cv2.cvtColor(frames[1], cv2.COLOR_BGR2RGB), bb, OT.HRNET_W48_COCO)
+    hm, hmf = m.forward_heatmaps(crop[None])
+    net = helpers.oracle_net("HRNet_W48_COCO")
+    xt = torch.from_numpy(x)[None]
+    ref = _oracle_activations(net, m.program, torch.cat([xt, xt.flip(3)]))
+    worst = (0.0, None)
+    for op in m.program.ops:
+        if op.kind == OP_HEAD:
+            continue
+        for img in (0, 1):
+            got = m.debug_tensor(op.out, img)
+            r = ref[op.out][img].numpy()
+            err = np.abs(got - r).max() / (np.abs(r).max() + 1e-20)
+            if err > worst[0]:
+                worst = (err, (op.conv or "fuse", img))
+            assert err < 2e-5, (op.conv, op.kind, img, err)
+    rh = ref[m.program.out_tensor].numpy()
+    assert np.abs(hm[0] - rh[0]).max() <= 2e-5 * np.abs(rh[0]).max()
+    assert np.abs(hmf[0] - rh[1]).max() <= 2e-5 * np.abs(rh[1]).max()
+    print("worst layer rel err", worst)
+    m.close()
+
+
+# ------------------------------------------------------------------ end to end
+def _check_keypoints(got, ref32, ref64, tol=1e-3):
+    """<= tol px wherever the oracle itself is well conditioned (its fp32 and fp64 runs agree to 2e-4 px)."""
+    assert got.shape == ref32.shape
+    cond = np.abs(ref32[..., :2] - ref64[..., :2]).max(-1)
+    good = cond <= 2e-4
+    assert good.mean() > 0.9, good.mean()
+    d = np.abs(got[..., :2] - ref32[..., :2]).max(-1)
+    assert d[good].max() <= tol, (d[good].max(), np.argwhere(d > tol))
+    assert np.all(d[~good] <= 50 * cond[~good] + tol), (d[~good], cond[~good])
+    sc = np.abs(got[..., 2] - ref32[..., 2])
+    assert np.all(sc <= 1e-4 * np.maximum(1.0, np.abs(ref32[..., 2]))), sc.max()
+    return d[good].max(), good.mean()
+
+
+def test_topdown_end_to_end_keypoints(eng, model48):
+    frames = helpers.frames(3)
+    eng.stage_frames(frames)
+    n = 10                                                               # > max_crops: two and a half chunks
+    bbs = synthetic_bboxes(n, 77)
+    fidx = np.arange(n) % 3
+    got = model48.topdown(fidx, bbs)
+    ref32 = helpers.oracle_keypoints("HRNet_W48_COCO", frames, fidx, bbs, "float32")
+    ref64 = helpers.oracle_keypoints("HRNet_W48_COCO", frames, fidx, bbs, "float64")
+    worst, frac = _check_keypoints(got, ref32, ref64)
+    print(f"max |dx| over well-conditioned keypoints = {worst:.2e} px ({frac:.1%} well conditioned)")
+    again = model48.topdown(fidx, bbs)
+    assert np.array_equal(got, again)                                    # deterministic
+    assert model48.topdown([], np.zeros((0, 4))).shape == (0, 17, 3)     # empty input
+
+
+def test_topdown_w32_config1(eng):
+    """BASELINE config 1: HRNet-W32 256x192, one crop, bbox [700.3,200.7,310.2,640.9] on frame seed 0."""
+    m = E.TopDownModel(eng, helpers.state_dict("HRNet_W32_COCO"), E.METHODS["HRNet_W32_COCO"], max_crops=2,
+                       use_tensor_cores=USE_TC)
+    frame = np.random.default_rng(0).integers(0, 256, (1, 1080, 1920, 3), dtype=np.uint8)
+    eng.stage_frames(frame)
+    bb = np.array([[700.3, 200.7, 310.2, 640.9]])
+    got = m.topdown([0], bb)
+    ref = helpers.oracle_keypoints("HRNet_W32_COCO", frame, [0], bb)
+    assert got.shape == (1, 17, 3)
+    # 'default' post-processing quantises to quarter pixels: equal unless the argmax itself is a near-tie
+    same = np.abs(got[..., :2] - ref[..., :2]).max(-1) <= 1e-3
+    assert same.mean() >= 0.9, (got, ref)
+    assert np.abs(got[..., 2] - ref[..., 2]).max() <= 1e-4 * max(1.0, np.abs(ref[..., 2]).max())
+    m.close()
+
+
+def test_unstaged_frame_is_an_error(eng, model48):
+    eng.stage_frames(helpers.frames(3))
+    with pytest.raises(E._lib.PoseEngineError):
+        model48.topdown([5], np.array([[0., 0., 10., 10.]]))
+
+
+# ------------------------------------------------------------------ a10 lifter
+def test_lifter_matches_oracle(eng):
+    sd = synthetic_videopose3d_state_dict()
+    lf = E.Lifter(eng, sd)
+    net = OV.load_lifter(sd)
+    for n in (1, 7, 300):
+        kp = synthetic_keypoints_2d(n, seed=n)
+        ref = OV.process_videopose3d(kp, 1080, 1920, net)["keypoints_3d"]
+        x = OV.normalize_screen_coordinates(kp[:, :, :2], 1920, 1080)
+        got = lf.lift(x)
+        assert got.shape == (n, 17, 3)
+        assert np.abs(got - ref).max() <= 1e-3, np.abs(got - ref).max()
+        assert np.abs(got - ref).max() <= 5e-5 * np.abs(ref).max()
+    lf.close()
