@@ -1,0 +1,271 @@
+#!/usr/bin/env python
+"""bench.py -- top-down 2D keypoint crops/sec, HRNet-W48 384x288 (BASELINE.json metric, configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One step = one pass of the whole hot path (bbox -> affine crop -> HRNet-W48 x2 flip-test -> flip-merge ->
+DARK decode -> keypoints) over one batch of 256 synthetic person crops (32 synthetic 1080p frames x 8
+boxes) per GPU.  `value` is timed with the frames already resident in HBM; `e2e` re-stages the frames
+from pinned host memory and reads the keypoints back every step, through the public Python API
+(posepipeline_b200.engine, i.e. the C ABI).  Every rank processes its own batch (frames shard by rank,
+no data-path collective): weak scaling.  Weights are seeded synthetic tensors under the mmpose key
+names (no checkpoint exists offline); data is synthetic.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METHOD = "HRNet_W48_COCO"
+FRAMES_PER_STEP = 32
+BOXES_PER_FRAME = 8
+CROPS_PER_STEP = FRAMES_PER_STEP * BOXES_PER_FRAME            # 256 (BASELINE configs[1])
+FLOP_PER_PASS = 2 * 35306606592                                # conv MACs x2, one forward pass
+FLOP_PER_CROP = 2 * FLOP_PER_PASS                              # flip test = two passes per crop
+METRIC = "top-down 2D keypoint crops/sec (HRNet-W48 384x288, flip-test + DARK decode)"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", d["bf16_tflops"]), d["hbm_gbs"], "measured (MEASURED_PEAKS.json, bf16 sustained)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md: 1.59 PF burst / ~1.4 PF sustained, 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (profiling recipe's clocks line)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.rows = index, threading.Event(), []
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons, "samples": len(sm)}
+
+
+class CpuReference:
+    """The reference path restated (oracle/: torch fp32 CPU convs + cv2 warp + numpy/cv2 DARK), batch 1 per frame
+    exactly like pose_pipeline/wrappers/mmpose.py:60-76, on all host cores."""
+
+    def __init__(self):
+        import torch
+        from oracle import hrnet as OH
+        from oracle import topdown as OT
+        from posepipeline_b200.engine import METHODS
+        from posepipeline_b200.hrnet_spec import build_program
+        from posepipeline_b200.synthetic import cheap_frames, synthetic_bboxes
+        from posepipeline_b200.weights import synthetic_hrnet_state_dict
+        spec = METHODS[METHOD]
+        sd = synthetic_hrnet_state_dict(build_program(spec.variant, spec.image_size[1], spec.image_size[0], spec.num_joints), 0)
+        self.OT = OT
+        self.net = OH.load_net(sd, spec.variant)
+        self.frames = cheap_frames(2, 0)
+        self.bbs = synthetic_bboxes(512, 1234)
+        self.cores = torch.get_num_threads()
+        self.torch_version = torch.__version__
+        self.i = 0
+        self.run(1)                                                      # warm-up
+
+    def run(self, n_crops, seconds_cap=1e9):
+        """-> (seconds, crops done)"""
+        t0 = time.perf_counter()
+        done = 0
+        for _ in range(n_crops):
+            i = self.i = (self.i + 1) % 500
+            self.OT.top_down_video(self.net, [self.frames[i % 2]], self.bbs[i:i + 1], self.OT.HRNET_W48_COCO)
+            done += 1
+            if time.perf_counter() - t0 > seconds_cap:
+                break
+        return time.perf_counter() - t0, done
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    per_step = 4
+    ref = CpuReference()
+    for _ in range(args.warmup):
+        ref.run(1)
+    total, dt = 0, 0.0
+    for _ in range(args.steps):
+        t, done = ref.run(per_step)
+        total += done
+        dt += t
+    v = total / dt
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "crops/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic frames, seeded synthetic weights",
+            "config": {"workload": "HRNet-W48 384x288 top-down, reference CPU path (oracle port of wrappers/mmpose.py loop), "
+                                   f"{per_step} crops per step, batch 1 per frame"},
+            "cpu_baseline": {"value": v, "unit": "crops/s", "cores": ref.cores, "kind": "port",
+                             "sample": f"{total} crops of the 256-crop workload, batch 1, torch {ref.torch_version} CPU"},
+            "e2e": {"value": v, "unit": "crops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--max-crops", type=int, default=int(os.environ.get("PE_MAX_CROPS", "64")))
+    ap.add_argument("--no-tc", action="store_true", help="fp32 SIMT convolutions only")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    from posepipeline_b200 import engine as E
+    from posepipeline_b200.hrnet_spec import build_program
+    from posepipeline_b200.synthetic import cheap_frames, synthetic_bboxes
+    from posepipeline_b200.weights import synthetic_hrnet_state_dict
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    stream = torch.cuda.Stream()
+    spec = E.METHODS[METHOD]
+    prog = build_program(spec.variant, spec.image_size[1], spec.image_size[0], spec.num_joints)
+    sd = synthetic_hrnet_state_dict(prog, 0)
+    eng = E.PoseEngine(local, stream.cuda_stream)
+    model = E.TopDownModel(eng, sd, spec, max_crops=args.max_crops, use_tensor_cores=not args.no_tc)
+
+    # this rank's shard of the synthetic video: 32 frames, 8 boxes each
+    frames_np = cheap_frames(FRAMES_PER_STEP, seed=1000 * rank)
+    pinned = torch.empty(frames_np.shape, dtype=torch.uint8, pin_memory=True)
+    pinned.numpy()[...] = frames_np
+    frames = pinned.numpy()
+    bboxes = synthetic_bboxes(CROPS_PER_STEP, seed=1234 + rank)
+    fidx = np.repeat(np.arange(FRAMES_PER_STEP, dtype=np.int32), BOXES_PER_FRAME)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    # ---- resident leg: frames already in HBM
+    eng.stage_frames(frames)
+    eng.sync()
+    step_resident = lambda: model.topdown(fidx, bboxes)
+    for _ in range(args.warmup):
+        kp = step_resident()
+    l0 = model.launch_count()
+    model.profile(True)
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms = timed(step_resident, args.steps)
+    sampler.stop_flag.set()
+    sampler.join()
+    conv_ms, other_ms, conv_launches = model.profile_read()
+    model.profile(False)
+    launches = model.launch_count() - l0
+    ms_step = ms / args.steps
+    value = world * CROPS_PER_STEP / (ms_step / 1e3)
+
+    # ---- end-to-end leg: pinned host frames -> H2D -> path -> keypoints on host, every step
+    def step_e2e():
+        eng.stage_frames(frames)
+        return model.topdown(fidx, bboxes)
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps) / args.steps
+    e2e_value = world * CROPS_PER_STEP / (ms_e2e / 1e3)
+    h2d = int(frames.nbytes + CROPS_PER_STEP * (6 * 8 + 4 + 16))
+    d2h = int(CROPS_PER_STEP * spec.num_joints * 3 * 4)
+
+    if rank == 0:
+        tf_peak, hbm_peak, peak_src = peaks()
+        conv_flop = FLOP_PER_CROP * CROPS_PER_STEP * args.steps
+        achieved = conv_flop / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else None
+        line = {
+            "metric": METRIC, "value": value, "unit": "crops/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (tf32x3 split-precision tensor-core MMAs, fp32 accumulate)" if not args.no_tc else "f32",
+            "data": "synthetic 1080p frames + seeded synthetic weights (no checkpoints/videos offline)",
+            "config": {"workload": "HRNet-W48 384x288 top-down, 256 synthetic crops per step per GPU (32 frames x 8 boxes), "
+                                   "flip_test + DARK decode (BASELINE configs[1])",
+                       "crops_per_step_per_gpu": CROPS_PER_STEP, "internal_batch_crops": args.max_crops,
+                       "l2_policy": "step input (199 MB of frames) and activation working set exceed the 126 MB L2; no explicit flush",
+                       "parallelism": f"frames sharded over {world} rank(s), no data-path collective"},
+            "e2e": {"value": e2e_value, "unit": "crops/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e},
+            "gpu_launches": int(launches),
+            "clocks": sampler.summary(),
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s",
+                         "frac": (achieved / tf_peak) if achieved else None, "traffic": None,
+                         "kernel": "convolution kernels (conv_tc / conv_simt), all launches of the timed region",
+                         "algorithmic_flop_per_crop": FLOP_PER_CROP, "conv_ms_total": conv_ms, "other_ms_total": other_ms,
+                         "conv_launches": int(conv_launches), "peak_source": peak_src,
+                         "note": "algorithmic FLOPs count each MAC once; the tf32x3 path executes 3 MMAs per MAC"},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            ref = CpuReference()
+            t, done = ref.run(40, seconds_cap=20.0)
+            v, cores = done / t, ref.cores
+            line["cpu_baseline"] = {"value": v, "unit": "crops/s", "cores": cores, "kind": "port",
+                                    "sample": f"{done} crops of the same workload, batch 1 per frame as wrappers/mmpose.py:60-76"}
+        print(json.dumps(line), flush=True)
+    model.close()
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,6 +1,404 @@
-// placeholder until the tcgen05 kernel lands
+// K2: stride-1 3x3 / 1x1 convolution as a tap-shifted GEMM on the 5th-gen tensor cores (sm_100a).
+//
+//   out[m][n] = act( sum_{tap} sum_{c} in[m + shift(tap)][c] * w[tap][c][n] + bias[n] (+ res[m][n]) )
+//
+// over the flat padded ("PS") activation matrix of pe_common.cuh: because every image carries a zero
+// 1-pixel border, a 3x3/pad-1 convolution is nine GEMMs whose A operand is the SAME matrix shifted by
+// (ky-1)*(W+2) + (kx-1) rows.  Replaces the cuDNN conv + BN + ReLU (+ residual) sequences that mmpose's
+// HRNet.forward launches (reference call site pose_pipeline/wrappers/mmpose.py:75).
+//
+// Precision: 3xTF32.  Activations and weights are stored as (hi, lo) TF32 pairs; each logical MAC is
+// hi*hi + hi*lo + lo*hi on tcgen05.mma kind::tf32 with FP32 accumulation in TMEM (error ~2^-21, the
+// oracle's own fp32 noise level; plain TF32/BF16 cannot hold the 1e-3 px keypoint gate).
+//
+// One CTA: MT accumulators of 128 rows x NC channels in TMEM.  Per 16-channel chunk, TMA loads ONE halo
+// window of (128*MT + 2*(W+3)) activation rows (SWIZZLE_128B, 128 B per row = hi16|lo16) that serves
+// all nine taps: each tap's A operand is an UMMA shared-memory descriptor into the same window at a row
+// offset (descriptor base_offset carries the swizzle phase of the unaligned start).  Weights stream
+// through a second TMA ring, one stage = TPS taps x NC rows x 128 B, and are amortised over MT tiles.
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warps 2-5 = epilogue
+// (tcgen05.ld -> bias / residual / ReLU -> tf32 split -> 128-byte row-chunk stores).
+#include <cuda.h>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
 #include "kernels.h"
-struct TcConvPlan { int dummy; };
-cudaError_t tc_conv_plan_create(TcConvPlan**, const float*, float*, const float*, const float*, const float*, int, int, int, int, int, int, int) { return cudaErrorNotSupported; }
-void tc_conv_plan_destroy(TcConvPlan*) {}
-cudaError_t tc_conv_launch(TcConvPlan*, int, cudaStream_t) { return cudaErrorNotSupported; }
+#include "pe_common.cuh"
+
+struct TcParams {
+  float* out;
+  const float* res;
+  const float* bias;
+  long long M;     // rows (padded positions) of this launch
+  int H, W, Hp, Wp;
+  int nchunk, ntaps, Cout, NC, MT, TPS, SA, SB;
+  int Rpad, RB, nbA, halo;
+  int nsub, Nsub, nboxW, NCbox;
+  int relu, tmem_cols, bo_mode;
+};
+
+// ------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol bug must trap (launch failure) instead of hanging the GPU box
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("conv_tc: mbarrier timeout (block %d,%d thread %d bar %u parity %u)\n", blockIdx.x, blockIdx.y, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"((uint64_t)tm), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, int bo_mode) {
+  uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;                         // leading-dim byte offset (unused for swizzled K-major) = 16 B
+  d |= (uint64_t)(1024 >> 4) << 32;               // stride-dim byte offset: next 8-row group
+  d |= (uint64_t)1 << 46;                         // descriptor version (sm_100)
+  if (bo_mode == 0) d |= (uint64_t)((saddr >> 7) & 7u) << 49;   // base offset = swizzle phase of an unaligned start
+  d |= (uint64_t)2 << 61;                         // SWIZZLE_128B
+  return d;
+}
+
+// ------------------------------------------------------------------------------------------ kernel
+__global__ void __launch_bounds__(192, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t a_bytes = (uint32_t)p.Rpad * 128u;
+  const uint32_t b_bytes = (uint32_t)p.TPS * p.NC * 128u;
+  const uint32_t sA = base;
+  const uint32_t sB = sA + p.SA * a_bytes;
+  const uint32_t sBar = sB + p.SB * b_bytes;       // 8-byte barriers
+  const uint32_t bar_a_full = sBar, bar_a_empty = sBar + 8 * p.SA;
+  const uint32_t bar_b_full = bar_a_empty + 8 * p.SA, bar_b_empty = bar_b_full + 8 * p.SB;
+  const uint32_t bar_acc = bar_b_empty + 8 * p.SB;
+  const uint32_t s_tmem = bar_acc + 8;
+  const uint32_t s_bias = s_tmem + 8;
+  uint8_t* gen = smem_raw + (base - raw);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen + (s_tmem - base));
+  float* bias_s = reinterpret_cast<float*>(gen + (s_bias - base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long m0 = (long long)blockIdx.x * 128 * p.MT;
+  const int n0 = blockIdx.y * p.NC;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.SA; ++i) { mbar_init(bar_a_full + 8 * i, 1); mbar_init(bar_a_empty + 8 * i, 1); }
+    for (int i = 0; i < p.SB; ++i) { mbar_init(bar_b_full + 8 * i, 1); mbar_init(bar_b_empty + 8 * i, 1); }
+    mbar_init(bar_acc, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_tmem), "r"((uint32_t)p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < p.NC; i += blockDim.x) bias_s[i] = p.bias[n0 + i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int ngroups = p.ntaps / p.TPS;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmW) : "memory");
+      auto load_a = [&](int j) {
+        const int sa = j % p.SA;
+        const uint32_t ph = (uint32_t)(j / p.SA) & 1u;
+        mbar_wait(bar_a_empty + 8 * sa, ph ^ 1u);
+        mbar_expect_tx(bar_a_full + 8 * sa, a_bytes);
+        for (int b = 0; b < p.nbA; ++b)
+          tma_load_2d(sA + sa * a_bytes + (uint32_t)b * p.RB * 128u, &tmA, j * 32, (int)(m0 - p.halo + (long long)b * p.RB),
+                      bar_a_full + 8 * sa);
+      };
+      load_a(0);
+      int it = 0;
+      for (int j = 0; j < p.nchunk; ++j) {
+        if (j + 1 < p.nchunk) load_a(j + 1);
+        for (int g = 0; g < ngroups; ++g, ++it) {
+          const int sb = it % p.SB;
+          const uint32_t ph = (uint32_t)(it / p.SB) & 1u;
+          mbar_wait(bar_b_empty + 8 * sb, ph ^ 1u);
+          mbar_expect_tx(bar_b_full + 8 * sb, b_bytes);
+          for (int t = 0; t < p.TPS; ++t) {
+            const int tap = g * p.TPS + t;
+            for (int h = 0; h < p.nboxW; ++h)
+              tma_load_2d(sB + sb * b_bytes + (uint32_t)(t * p.NC + h * p.NCbox) * 128u, &tmW, 0,
+                          (tap * p.nchunk + j) * p.Cout + n0 + h * p.NCbox, bar_b_full + 8 * sb);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      // instruction descriptor: D=F32, A=B=TF32, K-major both, N = Nsub, M = 128
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.Nsub >> 3) << 17) | ((128u >> 4) << 24);
+      int it = 0;
+      for (int j = 0; j < p.nchunk; ++j) {
+        const int sa = j % p.SA;
+        mbar_wait(bar_a_full + 8 * sa, (uint32_t)(j / p.SA) & 1u);
+        tc_fence_after();
+        const uint32_t a_slot = sA + sa * a_bytes;
+        for (int g = 0; g < ngroups; ++g, ++it) {
+          const int sb = it % p.SB;
+          mbar_wait(bar_b_full + 8 * sb, (uint32_t)(it / p.SB) & 1u);
+          tc_fence_after();
+          const uint32_t b_slot = sB + sb * b_bytes;
+          for (int t = 0; t < p.TPS; ++t) {
+            const int tap = g * p.TPS + t;
+            const int shift = (p.ntaps == 9) ? (tap / 3) * p.Wp + (tap % 3) : 0;
+            for (int mt = 0; mt < p.MT; ++mt) {
+              const uint32_t a_row = a_slot + (uint32_t)(mt * 128 + shift) * 128u;
+#pragma unroll
+              for (int ks = 0; ks < 2; ++ks) {
+                const uint64_t a_hi = umma_desc(a_row + ks * 32, p.bo_mode);
+                const uint64_t a_lo = umma_desc(a_row + 64 + ks * 32, p.bo_mode);
+                for (int h = 0; h < p.nsub; ++h) {
+                  const uint32_t b_row = b_slot + (uint32_t)(t * p.NC + h * p.Nsub) * 128u;
+                  const uint64_t b_hi = umma_desc(b_row + ks * 32, 1);
+                  const uint64_t b_lo = umma_desc(b_row + 64 + ks * 32, 1);
+                  const uint32_t d = tmem_base + (uint32_t)(mt * p.NC + h * p.Nsub);
+                  const uint32_t first = (j == 0 && tap == 0 && ks == 0) ? 0u : 1u;
+                  tc_mma_tf32(d, a_hi, b_hi, idesc, first);
+                  tc_mma_tf32(d, a_hi, b_lo, idesc, 1u);
+                  tc_mma_tf32(d, a_lo, b_hi, idesc, 1u);
+                }
+              }
+            }
+          }
+          tc_commit(bar_b_empty + 8 * sb);     // weights stage free once these MMAs retire
+        }
+        tc_commit(bar_a_empty + 8 * sa);       // activation window free
+      }
+      tc_commit(bar_acc);                      // accumulators complete
+    }
+  } else {
+    // ===================== epilogue (warps 2..5; TMEM lane quarter = warp % 4) =====================
+    const int q = warp & 3;
+    mbar_wait(bar_acc, 0);
+    tc_fence_after();
+    const int rowF = 2 * p.Cout;
+    for (int mt = 0; mt < p.MT; ++mt) {
+      const long long m = m0 + mt * 128 + q * 32 + lane;
+      const bool valid = m < p.M;
+      bool interior = false;
+      if (valid) {
+        const int r = (int)(m % ((long long)p.Hp * p.Wp));
+        const int py = r / p.Wp, px = r % p.Wp;
+        interior = py >= 1 && py <= p.H && px >= 1 && px <= p.W;
+      }
+      float* orow = p.out + m * rowF + 2 * n0;
+      const float* rrow = p.res ? p.res + m * rowF + 2 * n0 : nullptr;
+      for (int c0 = 0; c0 < p.NC; c0 += 16) {
+        uint32_t r[16];
+        tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * p.NC + c0), r);
+        if (!valid) continue;
+        float4* o = reinterpret_cast<float4*>(orow + 2 * c0);
+        if (!interior) {
+          const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = z;
+          continue;
+        }
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + bias_s[c0 + i];
+        if (rrow) {
+          const float4* rp = reinterpret_cast<const float4*>(rrow + 2 * c0);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 h = rp[i], l = rp[4 + i];
+            v[4 * i + 0] += h.x + l.x; v[4 * i + 1] += h.y + l.y; v[4 * i + 2] += h.z + l.z; v[4 * i + 3] += h.w + l.w;
+          }
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float4 hi, lo;
+          split4(make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]), hi, lo);
+          o[i] = hi;
+          o[4 + i] = lo;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+struct TcConvPlan {
+  CUtensorMap tmA, tmW;
+  TcParams p;
+  int rows_per_img;
+  size_t smem;
+  int ns;
+};
+
+static int env_int(const char* name, int dflt) {
+  const char* s = getenv(name);
+  return s ? atoi(s) : dflt;
+}
+
+static CUresult encode_2d(CUtensorMap* tm, const void* gptr, uint64_t dim0, uint64_t dim1, uint64_t stride1_bytes, uint32_t box0,
+                          uint32_t box1) {
+  cuuint64_t gdim[2] = {dim0, dim1};
+  cuuint64_t gstr[1] = {stride1_bytes};
+  cuuint32_t box[2] = {box0, box1};
+  cuuint32_t estr[2] = {1, 1};
+  return cuTensorMapEncodeTiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(gptr), gdim, gstr, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+}
+
+cudaError_t tc_conv_plan_create(TcConvPlan** out, const float* in, float* outp, const float* res, const float* wtc,
+                                const float* bias, int Cin, int Cout, int ks, int relu, int H, int W, int max_img) {
+  if (env_int("PE_TC_DISABLE", 0)) return cudaErrorNotSupported;
+  if ((ks != 1 && ks != 3) || Cin % 16 || Cout % 16 || Cout > 512) return cudaErrorNotSupported;
+  const int Hp = H + 2, Wp = W + 2, ntaps = ks * ks, nchunk = Cin / 16;
+  const int halo = ks == 3 ? Wp + 1 : 0;
+  const long long Mmax = (long long)max_img * Hp * Wp;
+  const size_t smem_cap = 200 * 1024;
+  double best = 1e30;
+  TcParams bp{};
+  size_t bsmem = 0;
+  int bns = 0;
+  const int force_mt = env_int("PE_TC_MT", 0), force_ns = env_int("PE_TC_NS", 0);
+  for (int ns = 1; ns <= 8; ns *= 2) {
+    if (Cout % ns) continue;
+    const int NC = Cout / ns;
+    if (NC % 16 || NC > 256) continue;
+    if (force_ns && ns != force_ns) continue;
+    for (int MT = 4; MT >= 1; MT >>= 1) {
+      if (MT * NC > 512) continue;
+      if (force_mt && MT != force_mt) continue;
+      TcParams p{};
+      p.NC = NC; p.MT = MT; p.nchunk = nchunk; p.ntaps = ntaps; p.Cout = Cout; p.halo = halo;
+      p.TPS = (ntaps == 9 && NC <= 64) ? 3 : 1;
+      const int R = 128 * MT + 2 * halo;
+      p.nbA = (R + 255) / 256;
+      p.Rpad = ((R + 8 * p.nbA - 1) / (8 * p.nbA)) * (8 * p.nbA);
+      p.RB = p.Rpad / p.nbA;
+      p.SA = nchunk > 1 ? 2 : 1;
+      p.nsub = 1; p.Nsub = NC; p.nboxW = 1; p.NCbox = NC;
+      const size_t a_bytes = (size_t)p.Rpad * 128, b_bytes = (size_t)p.TPS * NC * 128;
+      int SB = 6;
+      while (SB > 2 && p.SA * a_bytes + SB * b_bytes + 4096 > smem_cap) --SB;
+      if (p.SA * a_bytes + SB * b_bytes + 4096 > smem_cap) continue;
+      const int nstages = (ntaps / p.TPS) * nchunk;
+      p.SB = SB < nstages ? SB : nstages;
+      int cols = 32;
+      while (cols < MT * NC) cols <<= 1;
+      p.tmem_cols = cols;
+      const long long ctas = ((Mmax + 128LL * MT - 1) / (128LL * MT)) * ns;
+      const double waves = (double)((ctas + 147) / 148);
+      const double mma = 3.0 * ntaps * nchunk * NC * MT;                              // clocks at 2048 tf32 MAC/clk/SM
+      const double bytes = (double)nchunk * (a_bytes + (double)ntaps * NC * 128) + (double)MT * 128 * NC * 8 * (res ? 2 : 1);
+      const double t = waves * (std::max(mma, bytes / 36.0) + 3500.0 + (double)MT * (NC / 16) * 220.0);
+      if (t < best) { best = t; bp = p; bsmem = p.SA * a_bytes + p.SB * b_bytes + 4096 + NC * 4; bns = ns; }
+    }
+  }
+  if (best >= 1e30) return cudaErrorNotSupported;
+  TcConvPlan* pl = new TcConvPlan();
+  pl->p = bp;
+  pl->p.out = outp; pl->p.res = res; pl->p.bias = bias;
+  pl->p.H = H; pl->p.W = W; pl->p.Hp = Hp; pl->p.Wp = Wp; pl->p.relu = relu;
+  pl->p.bo_mode = env_int("PE_TC_BO_MODE", 0);
+  pl->rows_per_img = Hp * Wp;
+  pl->smem = bsmem;
+  pl->ns = bns;
+  CUresult r1 = encode_2d(&pl->tmA, in, (uint64_t)2 * Cin, (uint64_t)Mmax, (uint64_t)2 * Cin * 4, 32, (uint32_t)bp.RB);
+  CUresult r2 = encode_2d(&pl->tmW, wtc, 32, (uint64_t)ntaps * nchunk * Cout, 128, 32, (uint32_t)bp.NCbox);
+  if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) {
+    fprintf(stderr, "conv_tc: cuTensorMapEncodeTiled failed (%d, %d) Cin=%d Cout=%d RB=%d NCbox=%d\n", (int)r1, (int)r2, Cin, Cout, bp.RB, bp.NCbox);
+    delete pl;
+    return cudaErrorInvalidValue;
+  }
+  static size_t attr_set = 0;
+  if (pl->smem > attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(210 * 1024));
+    if (e != cudaSuccess) { delete pl; return e; }
+    attr_set = 210 * 1024;
+  }
+  if (env_int("PE_TC_VERBOSE", 0))
+    fprintf(stderr, "conv_tc plan: Cin=%d Cout=%d ks=%d %dx%d  MT=%d NS=%d NC=%d TPS=%d SA=%d SB=%d Rpad=%d RB=%d smem=%zu tmem=%d\n", Cin, Cout, ks, H, W,
+            bp.MT, bns, bp.NC, bp.TPS, bp.SA, bp.SB, bp.Rpad, bp.RB, pl->smem, bp.tmem_cols);
+  *out = pl;
+  return cudaSuccess;
+}
+
+void tc_conv_plan_destroy(TcConvPlan* plan) { delete plan; }
+
+cudaError_t tc_conv_launch(TcConvPlan* pl, int nimg, cudaStream_t st) {
+  TcParams p = pl->p;
+  p.M = (long long)nimg * pl->rows_per_img;
+  const unsigned gx = (unsigned)((p.M + 128LL * p.MT - 1) / (128LL * p.MT));
+  conv_tc_kernel<<<dim3(gx, pl->ns), 192, pl->smem, st>>>(pl->tmA, pl->tmW, p);
+  return cudaGetLastError();
+}
