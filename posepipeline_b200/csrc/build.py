@@ -47,7 +47,7 @@ def build(force=False, verbose=False):
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    cmd = [NVCC, "-shared", "-o", OUT, *objs, "-lcudart", "-lcuda"]
+    cmd = [NVCC, "-shared", "-o", OUT, *objs]
     subprocess.run(cmd, check=True)
     open(stamp, "w").write(dig)
     return OUT

@@ -14,7 +14,7 @@
 // One CTA: MT accumulators of 128 rows x NC channels in TMEM.  Per 16-channel chunk, TMA loads ONE halo
 // window of (128*MT + 2*(W+3)) activation rows (SWIZZLE_128B, 128 B per row = hi16|lo16) that serves
 // all nine taps: each tap's A operand is an UMMA shared-memory descriptor into the same window at a row
-// offset (descriptor base_offset carries the swizzle phase of the unaligned start).  Weights stream
+// offset (base_offset 0: the swizzle is a function of absolute smem address bits, measured).  Weights stream
 // through a second TMA ring, one stage = TPS taps x NC rows x 128 B, and are amortised over MT tiles.
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warps 2-5 = epilogue
 // (tcgen05.ld -> bias / residual / ReLU -> tf32 split -> 128-byte row-chunk stores).
@@ -108,7 +108,10 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, int bo_mode) {
   d |= (uint64_t)1 << 16;                         // leading-dim byte offset (unused for swizzled K-major) = 16 B
   d |= (uint64_t)(1024 >> 4) << 32;               // stride-dim byte offset: next 8-row group
   d |= (uint64_t)1 << 46;                         // descriptor version (sm_100)
-  if (bo_mode == 0) d |= (uint64_t)((saddr >> 7) & 7u) << 49;   // base offset = swizzle phase of an unaligned start
+  // Measured on B200 (tests/tc_bringup.py): the 128B swizzle XOR is applied to ABSOLUTE shared-memory address bits,
+  // so a descriptor that starts at an arbitrary row of a TMA-written window needs base_offset = 0; setting the
+  // "swizzle phase" there (bo_mode 0, kept for the experiment) reads the wrong 16-byte chunks.
+  if (bo_mode == 0) d |= (uint64_t)((saddr >> 7) & 7u) << 49;
   d |= (uint64_t)2 << 61;                         // SWIZZLE_128B
   return d;
 }
@@ -306,8 +309,26 @@ static int env_int(const char* name, int dflt) {
   return s ? atoi(s) : dflt;
 }
 
+// libcuda is resolved at run time through the runtime API so the library still loads (for its host-only entry points
+// and the export check) on a box without a driver.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
 static CUresult encode_2d(CUtensorMap* tm, const void* gptr, uint64_t dim0, uint64_t dim1, uint64_t stride1_bytes, uint32_t box0,
                           uint32_t box1) {
+  EncodeTiledFn cuTensorMapEncodeTiled = get_encode_fn();
+  if (!cuTensorMapEncodeTiled) return CUDA_ERROR_NOT_INITIALIZED;
   cuuint64_t gdim[2] = {dim0, dim1};
   cuuint64_t gstr[1] = {stride1_bytes};
   cuuint32_t box[2] = {box0, box1};
@@ -369,7 +390,7 @@ cudaError_t tc_conv_plan_create(TcConvPlan** out, const float* in, float* outp, 
   pl->p = bp;
   pl->p.out = outp; pl->p.res = res; pl->p.bias = bias;
   pl->p.H = H; pl->p.W = W; pl->p.Hp = Hp; pl->p.Wp = Wp; pl->p.relu = relu;
-  pl->p.bo_mode = env_int("PE_TC_BO_MODE", 0);
+  pl->p.bo_mode = env_int("PE_TC_BO_MODE", 1);
   pl->rows_per_img = Hp * Wp;
   pl->smem = bsmem;
   pl->ns = bns;

@@ -621,3 +621,71 @@ extern "C" int pe_model_profile_read(pe_model* m, double* conv_ms, double* other
   if (conv_launches) *conv_launches = m->acc_conv_launches;
   return PE_OK;
 }
+
+// ------------------------------------------------------------------------------------------ single-layer parity hook
+extern "C" int pe_conv_test(pe_engine* e, const float* in_nchw, int32_t nimg, int32_t Cin, int32_t H, int32_t W,
+                            const float* w_simt, const float* w_tc, const float* bias, const float* res_nchw, int32_t Cout,
+                            int32_t ks, int32_t relu, int32_t use_tc, float* out_nchw) {
+  if (!e || !in_nchw || !w_simt || !bias || !out_nchw || nimg <= 0) return fail(PE_ERR_INVALID, "bad argument to pe_conv_test");
+  if (Cin % 16 || Cout % 16) return fail(PE_ERR_INVALID, "pe_conv_test needs channel counts that are multiples of 16");
+  CU(cudaSetDevice(e->device));
+  cudaStream_t st = e->stream;
+  const size_t rows = (size_t)nimg * (H + 2) * (W + 2);
+  const size_t taps = (size_t)ks * ks;
+  float *d_in = nullptr, *d_out = nullptr, *d_res = nullptr, *d_dense = nullptr, *d_w = nullptr, *d_wtc = nullptr, *d_b = nullptr;
+  int rc = PE_OK;
+  TcConvPlan* plan = nullptr;
+  const size_t dense_in = (size_t)nimg * Cin * H * W, dense_out = (size_t)nimg * Cout * H * W;
+#define CT(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { rc = fail(PE_ERR_CUDA, "%s: %s", #x, cudaGetErrorString(_e)); goto done; } } while (0)
+  CT(cudaMalloc(&d_in, rows * 2 * Cin * sizeof(float)));
+  CT(cudaMalloc(&d_out, rows * 2 * Cout * sizeof(float)));
+  CT(cudaMalloc(&d_dense, std::max(dense_in, dense_out) * sizeof(float)));
+  CT(cudaMalloc(&d_w, taps * Cin * Cout * sizeof(float)));
+  CT(cudaMalloc(&d_b, Cout * sizeof(float)));
+  CT(cudaMemsetAsync(d_out, 0xff, rows * 2 * Cout * sizeof(float), st));     // poison: every position must be written
+  CT(cudaMemcpyAsync(d_w, w_simt, taps * Cin * Cout * sizeof(float), cudaMemcpyHostToDevice, st));
+  CT(cudaMemcpyAsync(d_b, bias, Cout * sizeof(float), cudaMemcpyHostToDevice, st));
+  if (res_nchw) {
+    CT(cudaMalloc(&d_res, rows * 2 * Cout * sizeof(float)));
+    CT(cudaMemcpyAsync(d_dense, res_nchw, dense_out * sizeof(float), cudaMemcpyHostToDevice, st));
+    launch_chw_to_ps(d_dense, Cout, H, W, nimg, d_res, st);
+  }
+  CT(cudaMemcpyAsync(d_dense, in_nchw, dense_in * sizeof(float), cudaMemcpyHostToDevice, st));
+  launch_chw_to_ps(d_dense, Cin, H, W, nimg, d_in, st);
+  if (use_tc) {
+    if (!w_tc) { rc = fail(PE_ERR_INVALID, "w_tc is NULL"); goto done; }
+    CT(cudaMalloc(&d_wtc, taps * Cin * Cout * 2 * sizeof(float)));
+    CT(cudaMemcpyAsync(d_wtc, w_tc, taps * Cin * Cout * 2 * sizeof(float), cudaMemcpyHostToDevice, st));
+    cudaError_t ce = tc_conv_plan_create(&plan, d_in, d_out, d_res, d_wtc, d_b, Cin, Cout, ks, relu, H, W, nimg);
+    if (ce != cudaSuccess) { rc = fail(PE_ERR_CUDA, "tc_conv_plan_create: %s", cudaGetErrorString(ce)); goto done; }
+    CT(tc_conv_launch(plan, nimg, st));
+  } else {
+    launch_conv_simt(d_in, d_out, d_res, d_w, d_b, Cin, Cout, ks, 1, relu, H, W, H, W, nimg, st);
+  }
+  CT(cudaGetLastError());
+  {
+    // halo must be zero: check on the device side by converting with the halo included is overkill; the dense read
+    // only covers the interior, so verify the halo by reading the PS buffer back
+    std::vector<float> ps(rows * 2 * Cout);
+    CT(cudaMemcpyAsync(ps.data(), d_out, ps.size() * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CT(cudaStreamSynchronize(st));
+    const int Hp = H + 2, Wp = W + 2;
+    for (size_t m = 0; m < rows; ++m) {
+      const int r = (int)(m % ((size_t)Hp * Wp)), py = r / Wp, px = r % Wp;
+      if (py >= 1 && py <= H && px >= 1 && px <= W) continue;
+      for (int c = 0; c < 2 * Cout; ++c)
+        if (ps[m * 2 * Cout + c] != 0.f) { rc = fail(PE_ERR_STATE, "halo position %zu (py=%d px=%d) col %d not zero", m, py, px, c); goto done; }
+    }
+  }
+  for (int img = 0; img < nimg; ++img) {
+    launch_ps_to_chw(d_out, Cout, H, W, img, d_dense + (size_t)img * Cout * H * W, st);
+  }
+  CT(cudaMemcpyAsync(out_nchw, d_dense, dense_out * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CT(cudaStreamSynchronize(st));
+#undef CT
+done:
+  if (plan) tc_conv_plan_destroy(plan);
+  cudaStreamSynchronize(st);
+  cudaFree(d_in); cudaFree(d_out); cudaFree(d_res); cudaFree(d_dense); cudaFree(d_w); cudaFree(d_wtc); cudaFree(d_b);
+  return rc;
+}

@@ -19,6 +19,8 @@ void launch_head(const float* in, int Cin, int H, int W, int nimg, const float* 
                  cudaStream_t st);
 void launch_ps_to_chw(const float* in, int C, int H, int W, int img, float* out, cudaStream_t st);
 
+void launch_chw_to_ps(const float* in, int C, int H, int W, int nimg, float* out, cudaStream_t st);
+
 void upload_gauss_kernel(const float* taps, int k);
 cudaError_t launch_decode(const float* hm, const float* hm_flip, const int* flip_perm, const float* center,
                           const float* scale, float* out, int n, int K, int H, int W, int shift, int post, int ksize,

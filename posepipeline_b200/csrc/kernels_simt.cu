@@ -417,3 +417,26 @@ void launch_ps_to_chw(const float* in, int C, int H, int W, int img, float* out,
   long long total = (long long)C * H * W;
   ps_to_chw_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, C, H, W, img, out);
 }
+
+// debug: dense NCHW fp32 -> PS tensor (zero halo, tf32 hi/lo split)
+__global__ void chw_to_ps_kernel(const float* __restrict__ in, int C, int H, int W, int nimg, float* __restrict__ out) {
+  const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+  const int Hp = H + 2, Wp = W + 2;
+  if (t >= (long long)nimg * Hp * Wp * C) return;
+  const int c = (int)(t % C);
+  const long long m = t / C;
+  const int img = (int)(m / (Hp * Wp));
+  const int r = (int)(m % (Hp * Wp));
+  const int py = r / Wp, px = r % Wp;
+  float v = 0.f;
+  if (py >= 1 && py <= H && px >= 1 && px <= W) v = in[(((long long)img * C + c) * H + py - 1) * W + px - 1];
+  const float hi = tf32_round(v);
+  float* o = out + m * (2 * C) + ((c >> 4) << 5) + (c & 15);
+  o[0] = hi;
+  o[16] = v - hi;
+}
+
+void launch_chw_to_ps(const float* in, int C, int H, int W, int nimg, float* out, cudaStream_t st) {
+  long long total = (long long)nimg * (H + 2) * (W + 2) * C;
+  chw_to_ps_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, C, H, W, nimg, out);
+}

@@ -126,6 +126,22 @@ class PoseEngine:
             pass
 
 
+def conv_test(engine: PoseEngine, x: np.ndarray, w: np.ndarray, bias: np.ndarray, res: Optional[np.ndarray] = None,
+              relu: bool = True, use_tc: bool = True) -> np.ndarray:
+    """One stride-1 conv layer through the library (parity hook): x (n,Cin,H,W), w (Cout,Cin,k,k) folded -> (n,Cout,H,W)."""
+    x = np.ascontiguousarray(x, np.float32)
+    n, cin, H, W = x.shape
+    cout, _, k, _ = w.shape
+    ws = np.ascontiguousarray(w.transpose(2, 3, 1, 0).reshape(k * k, cin, cout), np.float32)
+    wt = np.ascontiguousarray(pack_tc_weights(w), np.float32)
+    b = np.ascontiguousarray(bias, np.float32)
+    r = np.ascontiguousarray(res, np.float32) if res is not None else None
+    out = np.empty((n, cout, H, W), np.float32)
+    check(engine.lib.pe_conv_test(engine.h, ptr(x), n, cin, H, W, ptr(ws), ptr(wt), ptr(b), ptr(r) if r is not None else None,
+                                  cout, k, int(relu), int(use_tc), ptr(out)))
+    return out
+
+
 def model_desc(spec: TopDownSpec, n_ops=0, n_tensors=0, n_slots=0, max_crops=1, use_tc=False) -> ModelDesc:
     return ModelDesc(in_h=spec.image_size[1], in_w=spec.image_size[0], hm_h=spec.heatmap_size[1], hm_w=spec.heatmap_size[0],
                      num_joints=spec.num_joints, n_ops=n_ops, n_tensors=n_tensors, n_slots=n_slots, max_crops=max_crops,
