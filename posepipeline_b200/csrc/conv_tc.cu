@@ -36,6 +36,7 @@ struct TcParams {
   int Rpad, RB, nbA, halo;
   int nsub, Nsub, nboxW, NCbox;
   int relu, tmem_cols, bo_mode;
+  int tiles_m, total_work, dbuf;   // persistent schedule: work item w -> (tile = w % tiles_m, n-slice = w / tiles_m)
 };
 
 // ------------------------------------------------------------------------------------------ PTX helpers
@@ -102,6 +103,31 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n"
+      ".reg .b32 rx;\n"
+      ".reg .pred px;\n"
+      "elect.sync rx|px, 0xFFFFFFFF;\n"
+      "@px mov.s32 %0, 1;\n"
+      "}\n"
+      : "+r"(pred));
+  return pred;
+}
+
+__device__ __forceinline__ void tc_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
 // UMMA shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart.
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, int bo_mode) {
   uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
@@ -117,6 +143,11 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, int bo_mode) {
 }
 
 // ------------------------------------------------------------------------------------------ kernel
+// Persistent: gridDim.x CTAs walk the work list; the TMA and MMA warps run ahead into the next tile while the
+// epilogue warps drain the previous accumulators (double-buffered in TMEM when 4*MT*NC <= 512 columns).
+// TMEM columns of buffer b: [main(mt=0..MT-1) | corr(mt=0..MT-1)], NC columns each.  hi*hi accumulates in `main`;
+// the two small cross terms hi*lo + lo*hi accumulate in `corr`, so the tensor core's truncating FP32 accumulation
+// only sees K/8 steps per accumulator (measured: error grows ~2^-24.7 per step) and the epilogue adds them in FP32.
 __global__ void __launch_bounds__(192, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -129,162 +160,200 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t sBar = sB + p.SB * b_bytes;       // 8-byte barriers
   const uint32_t bar_a_full = sBar, bar_a_empty = sBar + 8 * p.SA;
   const uint32_t bar_b_full = bar_a_empty + 8 * p.SA, bar_b_empty = bar_b_full + 8 * p.SB;
-  const uint32_t bar_acc = bar_b_empty + 8 * p.SB;
-  const uint32_t s_tmem = bar_acc + 8;
-  const uint32_t s_bias = s_tmem + 8;
+  const uint32_t bar_acc_full = bar_b_empty + 8 * p.SB;   // [2]
+  const uint32_t bar_acc_empty = bar_acc_full + 16;       // [2]
+  const uint32_t s_tmem = bar_acc_empty + 16;
   uint8_t* gen = smem_raw + (base - raw);
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen + (s_tmem - base));
-  float* bias_s = reinterpret_cast<float*>(gen + (s_bias - base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long m0 = (long long)blockIdx.x * 128 * p.MT;
-  const int n0 = blockIdx.y * p.NC;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.SA; ++i) { mbar_init(bar_a_full + 8 * i, 1); mbar_init(bar_a_empty + 8 * i, 1); }
     for (int i = 0; i < p.SB; ++i) { mbar_init(bar_b_full + 8 * i, 1); mbar_init(bar_b_empty + 8 * i, 1); }
-    mbar_init(bar_acc, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_acc_full + 8 * i, 1); mbar_init(bar_acc_empty + 8 * i, 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_tmem), "r"((uint32_t)p.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < p.NC; i += blockDim.x) bias_s[i] = p.bias[n0 + i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   const int ngroups = p.ntaps / p.TPS;
+  const uint32_t buf_cols = 2u * p.MT * p.NC;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (one lane) =====================
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmW) : "memory");
-      auto load_a = [&](int j) {
-        const int sa = j % p.SA;
-        const uint32_t ph = (uint32_t)(j / p.SA) & 1u;
-        mbar_wait(bar_a_empty + 8 * sa, ph ^ 1u);
-        mbar_expect_tx(bar_a_full + 8 * sa, a_bytes);
-        for (int b = 0; b < p.nbA; ++b)
-          tma_load_2d(sA + sa * a_bytes + (uint32_t)b * p.RB * 128u, &tmA, j * 32, (int)(m0 - p.halo + (long long)b * p.RB),
-                      bar_a_full + 8 * sa);
-      };
-      load_a(0);
-      int it = 0;
-      for (int j = 0; j < p.nchunk; ++j) {
-        if (j + 1 < p.nchunk) load_a(j + 1);
-        for (int g = 0; g < ngroups; ++g, ++it) {
-          const int sb = it % p.SB;
-          const uint32_t ph = (uint32_t)(it / p.SB) & 1u;
-          mbar_wait(bar_b_empty + 8 * sb, ph ^ 1u);
-          mbar_expect_tx(bar_b_full + 8 * sb, b_bytes);
-          for (int t = 0; t < p.TPS; ++t) {
-            const int tap = g * p.TPS + t;
-            for (int h = 0; h < p.nboxW; ++h)
-              tma_load_2d(sB + sb * b_bytes + (uint32_t)(t * p.NC + h * p.NCbox) * 128u, &tmW, 0,
-                          (tap * p.nchunk + j) * p.Cout + n0 + h * p.NCbox, bar_b_full + 8 * sb);
+      uint32_t ita = 0, itb = 0;
+      for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+        const long long m0 = (long long)(w % p.tiles_m) * 128 * p.MT;
+        const int n0 = (w / p.tiles_m) * p.NC;
+        auto load_a = [&](int j) {
+          const uint32_t sa = ita % p.SA, ph = (ita / p.SA) & 1u;
+          ++ita;
+          mbar_wait(bar_a_empty + 8 * sa, ph ^ 1u);
+          mbar_expect_tx(bar_a_full + 8 * sa, a_bytes);
+          for (int b = 0; b < p.nbA; ++b)
+            tma_load_2d(sA + sa * a_bytes + (uint32_t)b * p.RB * 128u, &tmA, j * 32, (int)(m0 - p.halo + (long long)b * p.RB),
+                        bar_a_full + 8 * sa);
+        };
+        load_a(0);
+        for (int j = 0; j < p.nchunk; ++j) {
+          for (int g = 0; g < ngroups; ++g) {
+            const uint32_t sb = itb % p.SB, ph = (itb / p.SB) & 1u;
+            ++itb;
+            mbar_wait(bar_b_empty + 8 * sb, ph ^ 1u);
+            mbar_expect_tx(bar_b_full + 8 * sb, b_bytes);
+            for (int t = 0; t < p.TPS; ++t) {
+              const int tap = g * p.TPS + t;
+              tma_load_2d(sB + sb * b_bytes + (uint32_t)(t * p.NC) * 128u, &tmW, 0, (tap * p.nchunk + j) * p.Cout + n0,
+                          bar_b_full + 8 * sb);
+            }
+            if (g == 0 && j + 1 < p.nchunk) load_a(j + 1);   // next activation window right behind the first weights
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      // instruction descriptor: D=F32, A=B=TF32, K-major both, N = Nsub, M = 128
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.Nsub >> 3) << 17) | ((128u >> 4) << 24);
-      int it = 0;
+    // ===================== MMA issuer: warp-uniform control flow, one elected lane issues =====================
+    const uint32_t leader = elect_one();
+    // instruction descriptor: D=F32, A=B=TF32, K-major both, N = NC, M = 128
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.NC >> 3) << 17) | ((128u >> 4) << 24);
+    const uint64_t a_desc0 = umma_desc(sA, p.bo_mode), b_desc0 = umma_desc(sB, p.bo_mode);
+    uint32_t ita = 0, itb = 0, tl = 0;
+    for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++tl) {
+      const uint32_t buf = p.dbuf ? (tl & 1u) : 0u;
+      const uint32_t use = p.dbuf ? (tl >> 1) : tl;
+      mbar_wait(bar_acc_empty + 8 * buf, (use & 1u) ^ 1u);        // epilogue has drained this accumulator buffer
+      tc_fence_after();
+      const uint32_t d_main = tmem_base + buf * buf_cols;
+      const uint32_t d_corr = d_main + (uint32_t)(p.MT * p.NC);
       for (int j = 0; j < p.nchunk; ++j) {
-        const int sa = j % p.SA;
-        mbar_wait(bar_a_full + 8 * sa, (uint32_t)(j / p.SA) & 1u);
+        const uint32_t sa = ita % p.SA;
+        mbar_wait(bar_a_full + 8 * sa, (ita / p.SA) & 1u);
+        ++ita;
         tc_fence_after();
-        const uint32_t a_slot = sA + sa * a_bytes;
-        for (int g = 0; g < ngroups; ++g, ++it) {
-          const int sb = it % p.SB;
-          mbar_wait(bar_b_full + 8 * sb, (uint32_t)(it / p.SB) & 1u);
+        const uint64_t a_slot = a_desc0 + (uint64_t)((sa * a_bytes) >> 4);
+        for (int g = 0; g < ngroups; ++g) {
+          const uint32_t sb = itb % p.SB;
+          mbar_wait(bar_b_full + 8 * sb, (itb / p.SB) & 1u);
+          ++itb;
           tc_fence_after();
-          const uint32_t b_slot = sB + sb * b_bytes;
+          const uint64_t b_slot = b_desc0 + (uint64_t)((sb * b_bytes) >> 4);
           for (int t = 0; t < p.TPS; ++t) {
             const int tap = g * p.TPS + t;
-            const int shift = (p.ntaps == 9) ? (tap / 3) * p.Wp + (tap % 3) : 0;
+            const uint32_t shift = (p.ntaps == 9) ? (uint32_t)((tap / 3) * p.Wp + (tap % 3)) : 0u;
+            const uint64_t b_tap = b_slot + (uint64_t)(t * p.NC * 8);          // 128 B per row = 8 x 16 B
+            const uint32_t fresh = (j == 0 && tap == 0) ? 0u : 1u;
             for (int mt = 0; mt < p.MT; ++mt) {
-              const uint32_t a_row = a_slot + (uint32_t)(mt * 128 + shift) * 128u;
-#pragma unroll
-              for (int ks = 0; ks < 2; ++ks) {
-                const uint64_t a_hi = umma_desc(a_row + ks * 32, p.bo_mode);
-                const uint64_t a_lo = umma_desc(a_row + 64 + ks * 32, p.bo_mode);
-                for (int h = 0; h < p.nsub; ++h) {
-                  const uint32_t b_row = b_slot + (uint32_t)(t * p.NC + h * p.Nsub) * 128u;
-                  const uint64_t b_hi = umma_desc(b_row + ks * 32, 1);
-                  const uint64_t b_lo = umma_desc(b_row + 64 + ks * 32, 1);
-                  const uint32_t d = tmem_base + (uint32_t)(mt * p.NC + h * p.Nsub);
-                  const uint32_t first = (j == 0 && tap == 0 && ks == 0) ? 0u : 1u;
-                  tc_mma_tf32(d, a_hi, b_hi, idesc, first);
-                  tc_mma_tf32(d, a_hi, b_lo, idesc, 1u);
-                  tc_mma_tf32(d, a_lo, b_hi, idesc, 1u);
-                }
+              const uint64_t a_mt = a_slot + (uint64_t)((mt * 128 + shift) * 8);
+              const uint32_t dm = d_main + (uint32_t)(mt * p.NC), dc = d_corr + (uint32_t)(mt * p.NC);
+              if (leader) {
+                // k-step 0: floats 0..7 of hi (bytes 0..31) and of lo (bytes 64..95); k-step 1: +32 B
+                tc_mma_tf32(dm, a_mt, b_tap, idesc, fresh);              // hi * hi
+                tc_mma_tf32(dc, a_mt, b_tap + 4, idesc, fresh);          // hi * lo
+                tc_mma_tf32(dc, a_mt + 4, b_tap, idesc, 1u);             // lo * hi
+                tc_mma_tf32(dm, a_mt + 2, b_tap + 2, idesc, 1u);
+                tc_mma_tf32(dc, a_mt + 2, b_tap + 6, idesc, 1u);
+                tc_mma_tf32(dc, a_mt + 6, b_tap + 2, idesc, 1u);
               }
             }
           }
-          tc_commit(bar_b_empty + 8 * sb);     // weights stage free once these MMAs retire
+          if (leader) tc_commit(bar_b_empty + 8 * sb);     // weights stage free once these MMAs retire
+          __syncwarp();
         }
-        tc_commit(bar_a_empty + 8 * sa);       // activation window free
+        if (leader) tc_commit(bar_a_empty + 8 * sa);       // activation window free
+        __syncwarp();
       }
-      tc_commit(bar_acc);                      // accumulators complete
+      if (leader) tc_commit(bar_acc_full + 8 * buf);       // accumulators of this tile complete
+      __syncwarp();
     }
   } else {
     // ===================== epilogue (warps 2..5; TMEM lane quarter = warp % 4) =====================
     const int q = warp & 3;
-    mbar_wait(bar_acc, 0);
-    tc_fence_after();
     const int rowF = 2 * p.Cout;
-    for (int mt = 0; mt < p.MT; ++mt) {
-      const long long m = m0 + mt * 128 + q * 32 + lane;
-      const bool valid = m < p.M;
-      bool interior = false;
-      if (valid) {
-        const int r = (int)(m % ((long long)p.Hp * p.Wp));
-        const int py = r / p.Wp, px = r % p.Wp;
-        interior = py >= 1 && py <= p.H && px >= 1 && px <= p.W;
-      }
-      float* orow = p.out + m * rowF + 2 * n0;
-      const float* rrow = p.res ? p.res + m * rowF + 2 * n0 : nullptr;
-      for (int c0 = 0; c0 < p.NC; c0 += 16) {
-        uint32_t r[16];
-        tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * p.NC + c0), r);
-        if (!valid) continue;
-        float4* o = reinterpret_cast<float4*>(orow + 2 * c0);
-        if (!interior) {
-          const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) o[i] = z;
-          continue;
+    uint32_t tl = 0;
+    for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++tl) {
+      const long long m0 = (long long)(w % p.tiles_m) * 128 * p.MT;
+      const int n0 = (w / p.tiles_m) * p.NC;
+      const uint32_t buf = p.dbuf ? (tl & 1u) : 0u;
+      const uint32_t use = p.dbuf ? (tl >> 1) : tl;
+      mbar_wait(bar_acc_full + 8 * buf, use & 1u);
+      tc_fence_after();
+      const uint32_t t_main = tmem_base + buf * buf_cols + ((uint32_t)(q * 32) << 16);
+      const uint32_t t_corr = t_main + (uint32_t)(p.MT * p.NC);
+      for (int mt = 0; mt < p.MT; ++mt) {
+        const long long m = m0 + mt * 128 + q * 32 + lane;
+        const bool valid = m < p.M;
+        bool interior = false;
+        if (valid) {
+          const int r = (int)(m % ((long long)p.Hp * p.Wp));
+          const int py = r / p.Wp, px = r % p.Wp;
+          interior = py >= 1 && py <= p.H && px >= 1 && px <= p.W;
         }
-        float v[16];
+        float* orow = p.out + m * rowF + 2 * n0;
+        const float* rrow = p.res ? p.res + m * rowF + 2 * n0 : nullptr;
+        for (int c0 = 0; c0 < p.NC; c0 += 16) {
+          uint32_t r[16], rc[16];
+          tc_ld16_nowait(t_main + (uint32_t)(mt * p.NC + c0), r);
+          tc_ld16_nowait(t_corr + (uint32_t)(mt * p.NC + c0), rc);
+          float4 rh[4], rl[4];
+          const bool do_res = rrow && valid && interior;
+          if (do_res) {
+            const float4* rp = reinterpret_cast<const float4*>(rrow + 2 * c0);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + bias_s[c0 + i];
-        if (rrow) {
-          const float4* rp = reinterpret_cast<const float4*>(rrow + 2 * c0);
+            for (int i = 0; i < 4; ++i) { rh[i] = __ldg(rp + i); rl[i] = __ldg(rp + 4 + i); }
+          }
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (!valid) continue;
+          float4* o = reinterpret_cast<float4*>(orow + 2 * c0);
+          if (!interior) {
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = z;
+            continue;
+          }
+          const float4* bp = reinterpret_cast<const float4*>(p.bias + n0 + c0);
+          float v[16];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const float4 h = rp[i], l = rp[4 + i];
-            v[4 * i + 0] += h.x + l.x; v[4 * i + 1] += h.y + l.y; v[4 * i + 2] += h.z + l.z; v[4 * i + 3] += h.w + l.w;
+            const float4 b4 = __ldg(bp + i);
+            v[4 * i + 0] = (__uint_as_float(r[4 * i + 0]) + __uint_as_float(rc[4 * i + 0])) + b4.x;
+            v[4 * i + 1] = (__uint_as_float(r[4 * i + 1]) + __uint_as_float(rc[4 * i + 1])) + b4.y;
+            v[4 * i + 2] = (__uint_as_float(r[4 * i + 2]) + __uint_as_float(rc[4 * i + 2])) + b4.z;
+            v[4 * i + 3] = (__uint_as_float(r[4 * i + 3]) + __uint_as_float(rc[4 * i + 3])) + b4.w;
+          }
+          if (do_res) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              v[4 * i + 0] += rh[i].x + rl[i].x; v[4 * i + 1] += rh[i].y + rl[i].y;
+              v[4 * i + 2] += rh[i].z + rl[i].z; v[4 * i + 3] += rh[i].w + rl[i].w;
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float4 hi, lo;
+            split4(make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]), hi, lo);
+            o[i] = hi;
+            o[4 + i] = lo;
           }
         }
-        if (p.relu) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float4 hi, lo;
-          split4(make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]), hi, lo);
-          o[i] = hi;
-          o[4 + i] = lo;
-        }
       }
+      // all tcgen05.ld of this buffer have completed (wait::ld above): hand the accumulators back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_acc_empty + 8 * buf);
     }
   }
   tc_fence_before();
@@ -301,7 +370,7 @@ struct TcConvPlan {
   TcParams p;
   int rows_per_img;
   size_t smem;
-  int ns;
+  int ns, num_sms;
 };
 
 static int env_int(const char* name, int dflt) {
@@ -350,39 +419,55 @@ cudaError_t tc_conv_plan_create(TcConvPlan** out, const float* in, float* outp, 
   TcParams bp{};
   size_t bsmem = 0;
   int bns = 0;
-  const int force_mt = env_int("PE_TC_MT", 0), force_ns = env_int("PE_TC_NS", 0);
+  const int force_mt = env_int("PE_TC_MT", 0), force_ns = env_int("PE_TC_NS", 0), force_dbuf = env_int("PE_TC_DBUF", -1);
+  int num_sms = 148;
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
   for (int ns = 1; ns <= 8; ns *= 2) {
     if (Cout % ns) continue;
     const int NC = Cout / ns;
     if (NC % 16 || NC > 256) continue;
     if (force_ns && ns != force_ns) continue;
-    for (int MT = 4; MT >= 1; MT >>= 1) {
-      if (MT * NC > 512) continue;
+    for (int MT = 4; MT >= 1; --MT) {
+      if (2 * MT * NC > 512) continue;
       if (force_mt && MT != force_mt) continue;
-      TcParams p{};
-      p.NC = NC; p.MT = MT; p.nchunk = nchunk; p.ntaps = ntaps; p.Cout = Cout; p.halo = halo;
-      p.TPS = (ntaps == 9 && NC <= 64) ? 3 : 1;
-      const int R = 128 * MT + 2 * halo;
-      p.nbA = (R + 255) / 256;
-      p.Rpad = ((R + 8 * p.nbA - 1) / (8 * p.nbA)) * (8 * p.nbA);
-      p.RB = p.Rpad / p.nbA;
-      p.SA = nchunk > 1 ? 2 : 1;
-      p.nsub = 1; p.Nsub = NC; p.nboxW = 1; p.NCbox = NC;
-      const size_t a_bytes = (size_t)p.Rpad * 128, b_bytes = (size_t)p.TPS * NC * 128;
-      int SB = 6;
-      while (SB > 2 && p.SA * a_bytes + SB * b_bytes + 4096 > smem_cap) --SB;
-      if (p.SA * a_bytes + SB * b_bytes + 4096 > smem_cap) continue;
-      const int nstages = (ntaps / p.TPS) * nchunk;
-      p.SB = SB < nstages ? SB : nstages;
-      int cols = 32;
-      while (cols < MT * NC) cols <<= 1;
-      p.tmem_cols = cols;
-      const long long ctas = ((Mmax + 128LL * MT - 1) / (128LL * MT)) * ns;
-      const double waves = (double)((ctas + 147) / 148);
-      const double mma = 3.0 * ntaps * nchunk * NC * MT;                              // clocks at 2048 tf32 MAC/clk/SM
-      const double bytes = (double)nchunk * (a_bytes + (double)ntaps * NC * 128) + (double)MT * 128 * NC * 8 * (res ? 2 : 1);
-      const double t = waves * (std::max(mma, bytes / 36.0) + 3500.0 + (double)MT * (NC / 16) * 220.0);
-      if (t < best) { best = t; bp = p; bsmem = p.SA * a_bytes + p.SB * b_bytes + 4096 + NC * 4; bns = ns; }
+      for (int dbuf = 1; dbuf >= 0; --dbuf) {
+        if (dbuf && 4 * MT * NC > 512) continue;
+        if (force_dbuf >= 0 && dbuf != force_dbuf) continue;
+        TcParams p{};
+        p.NC = NC; p.MT = MT; p.nchunk = nchunk; p.ntaps = ntaps; p.Cout = Cout; p.halo = halo; p.dbuf = dbuf;
+        p.TPS = (ntaps == 9 && NC <= 64) ? 3 : 1;
+        const int R = 128 * MT + 2 * halo;
+        p.nbA = (R + 255) / 256;
+        p.Rpad = ((R + 8 * p.nbA - 1) / (8 * p.nbA)) * (8 * p.nbA);
+        p.RB = p.Rpad / p.nbA;
+        p.SA = 2;
+        p.nsub = 1; p.Nsub = NC; p.nboxW = 1; p.NCbox = NC;
+        const size_t a_bytes = (size_t)p.Rpad * 128, b_bytes = (size_t)p.TPS * NC * 128;
+        int SB = 6;
+        while (SB > 2 && p.SA * a_bytes + SB * b_bytes + 4096 > smem_cap) --SB;
+        if (p.SA * a_bytes + SB * b_bytes + 4096 > smem_cap) continue;
+        p.SB = SB;
+        int cols = 32;
+        while (cols < (dbuf ? 2 : 1) * 2 * MT * NC) cols <<= 1;
+        p.tmem_cols = cols;
+        p.tiles_m = (int)((Mmax + 128LL * MT - 1) / (128LL * MT));
+        p.total_work = p.tiles_m * ns;
+        const int ctas = p.total_work < num_sms ? p.total_work : num_sms;
+        const double items = (double)((p.total_work + ctas - 1) / ctas);
+        // clocks per work item: tf32 MMA at 2048 MAC/clk/SM, but never faster than the operands can be read from
+        // shared memory (128 B/clk: A 4 KB + B NC*32 B per MMA) or fetched from L2 (~32 B/clk/SM)
+        const double n_mma = 6.0 * ntaps * nchunk * MT;
+        const double mma = n_mma * std::max(NC / 2.0, (4096.0 + NC * 32.0) / 128.0);
+        const double bytes = (double)nchunk * (a_bytes + (double)ntaps * NC * 128);
+        const double epi = (double)MT * (NC / 16) * 260.0 + 1500.0;
+        const double item = std::max(mma, bytes / 32.0) + (dbuf ? 0.0 : epi);
+        const double t = items * std::max(item, dbuf ? epi : 0.0) + 4000.0;
+        if (t < best) { best = t; bp = p; bsmem = p.SA * a_bytes + p.SB * b_bytes + 4096; bns = ns; }
+      }
     }
   }
   if (best >= 1e30) return cudaErrorNotSupported;
@@ -407,9 +492,10 @@ cudaError_t tc_conv_plan_create(TcConvPlan** out, const float* in, float* outp, 
     if (e != cudaSuccess) { delete pl; return e; }
     attr_set = 210 * 1024;
   }
+  pl->num_sms = num_sms;
   if (env_int("PE_TC_VERBOSE", 0))
-    fprintf(stderr, "conv_tc plan: Cin=%d Cout=%d ks=%d %dx%d  MT=%d NS=%d NC=%d TPS=%d SA=%d SB=%d Rpad=%d RB=%d smem=%zu tmem=%d\n", Cin, Cout, ks, H, W,
-            bp.MT, bns, bp.NC, bp.TPS, bp.SA, bp.SB, bp.Rpad, bp.RB, pl->smem, bp.tmem_cols);
+    fprintf(stderr, "conv_tc plan: Cin=%d Cout=%d ks=%d %dx%d  MT=%d NS=%d NC=%d dbuf=%d TPS=%d SA=%d SB=%d Rpad=%d RB=%d smem=%zu tmem=%d work=%d\n", Cin, Cout, ks, H, W,
+            bp.MT, bns, bp.NC, bp.dbuf, bp.TPS, bp.SA, bp.SB, bp.Rpad, bp.RB, pl->smem, bp.tmem_cols, bp.total_work);
   *out = pl;
   return cudaSuccess;
 }
@@ -419,7 +505,9 @@ void tc_conv_plan_destroy(TcConvPlan* plan) { delete plan; }
 cudaError_t tc_conv_launch(TcConvPlan* pl, int nimg, cudaStream_t st) {
   TcParams p = pl->p;
   p.M = (long long)nimg * pl->rows_per_img;
-  const unsigned gx = (unsigned)((p.M + 128LL * p.MT - 1) / (128LL * p.MT));
-  conv_tc_kernel<<<dim3(gx, pl->ns), 192, pl->smem, st>>>(pl->tmA, pl->tmW, p);
+  p.tiles_m = (int)((p.M + 128LL * p.MT - 1) / (128LL * p.MT));
+  p.total_work = p.tiles_m * pl->ns;
+  const unsigned grid = (unsigned)(p.total_work < pl->num_sms ? p.total_work : pl->num_sms);
+  conv_tc_kernel<<<grid, 192, pl->smem, st>>>(pl->tmA, pl->tmW, p);
   return cudaGetLastError();
 }
