@@ -138,6 +138,8 @@ int pe_model_launch_count(pe_model* m, int64_t* count);
 /* device timing of the dominant (conv) kernels between two marks, for bench.py's roofline */
 int pe_model_profile(pe_model* m, int32_t enable);
 int pe_model_profile_read(pe_model* m, double* conv_ms, double* other_ms, int64_t* conv_launches);
+/* per-op accumulated device milliseconds since pe_model_profile(m, 2) (enable=2 times every op, 1 only the convolutions) */
+int pe_model_profile_ops(pe_model* m, double* ms_per_op, int32_t n_ops);
 
 /* one convolution layer on its own (stride 1, k in {1,3}, BN already folded): dense NCHW in/out; the library packs to its
  * HBM layout, runs the SIMT (use_tc=0) or tcgen05 (use_tc=1) kernel, verifies the zero halo and unpacks.

@@ -37,6 +37,8 @@ struct TcParams {
   int nsub, Nsub, nboxW, NCbox;
   int relu, tmem_cols, bo_mode;
   int tiles_m, total_work, dbuf;   // persistent schedule: work item w -> (tile = w % tiles_m, n-slice = w / tiles_m)
+  int dbg;                         // PE_TC_DBG experiment bits: 1 = issue no MMAs, 2 = no epilogue global traffic
+  int CPD;                         // chunks per drain group (accumulation length bound, see kernel comment)
 };
 
 // ------------------------------------------------------------------------------------------ PTX helpers
@@ -48,12 +50,15 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// Non-suspending poll.  Measured on B200: a thread parked in mbarrier.try_wait is NOT woken promptly by the
+// completing arrive -- every wait that was not already satisfied cost a ~1300-cycle sleep quantum, which made the
+// pipeline skeleton (not the MMAs, not the loads) 70 % of this kernel's time.  test_wait never parks the thread.
 __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
       "selp.u32 %0, 1, 0, p;\n"
       "}\n"
       : "=r"(ok)
@@ -63,10 +68,9 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
 }
 // bounded wait: a protocol bug must trap (launch failure) instead of hanging the GPU box
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try(bar, parity)) return;
-  const long long t0 = clock64();
+  uint32_t spins = 0;
   while (!mbar_try(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
+    if (++spins > 200000000u) {
       printf("conv_tc: mbarrier timeout (block %d,%d thread %d bar %u parity %u)\n", blockIdx.x, blockIdx.y, threadIdx.x, bar, parity);
       __trap();
     }
@@ -143,26 +147,58 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, int bo_mode) {
 }
 
 // ------------------------------------------------------------------------------------------ kernel
-// Persistent: gridDim.x CTAs walk the work list; the TMA and MMA warps run ahead into the next tile while the
-// epilogue warps drain the previous accumulators (double-buffered in TMEM when 4*MT*NC <= 512 columns).
-// TMEM columns of buffer b: [main(mt=0..MT-1) | corr(mt=0..MT-1)], NC columns each.  hi*hi accumulates in `main`;
-// the two small cross terms hi*lo + lo*hi accumulate in `corr`, so the tensor core's truncating FP32 accumulation
-// only sees K/8 steps per accumulator (measured: error grows ~2^-24.7 per step) and the epilogue adds them in FP32.
+// Persistent: gridDim.x CTAs walk the work list; TMA and MMA warps run ahead while the epilogue warps drain.
+//
+// Accumulation-length bound.  Measured on B200 (tests/tc_bringup.py): tcgen05 kind::tf32 accumulates into TMEM with
+// truncation, a bias of ~1.2e-8 (relative) per MMA step that grows linearly with K -- 1.6e-5 at K=3456, too much for
+// the 1e-3 px keypoint gate after ~100 layers.  So no TMEM accumulator ever sees more than CPD*ntaps*2 (<= ~18-32)
+// hi*hi steps: the MMA warp ping-pongs between two `main` accumulators, one drain group (CPD channel chunks) each,
+// and the epilogue warps add every drained partial into FP32 registers (round-to-nearest).  The two cross terms
+// hi*lo + lo*hi are 2^-11 smaller, so their truncation is harmless and they accumulate over the whole K in `corr`
+// (double-buffered per tile).  TMEM columns: main0 | main1 | corr0 | corr1, MT*NC = NG*16 columns each.
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, int c0, int c1, uint32_t src) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+               ::"l"((uint64_t)tm), "r"(c0), "r"(c1), "r"(src)
+               : "memory");
+}
+
+// Ring cursor without integer division (the issue loops are latency-critical: ONE warp's scalar instruction stream
+// paces the tensor core; runtime div/mod per pipeline stage cost more than the MMAs themselves -- measured).
+struct Ring {
+  uint32_t idx = 0, phase = 0;
+  __device__ __forceinline__ void advance(uint32_t n) { if (++idx == n) { idx = 0; phase ^= 1u; } }
+};
+
+__device__ __forceinline__ uint64_t desc64(uint32_t hi, uint32_t lo) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
+
+template <int NG, int MT, int TPS>
 __global__ void __launch_bounds__(192, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const TcParams p) {
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+               const __grid_constant__ CUtensorMap tmO, const TcParams p) {
+  constexpr int NC = NG * 16 / MT;                 // output channels per CTA
+  constexpr uint32_t GC = NG * 16;                 // columns of one accumulator set (= MT*NC)
+  constexpr uint32_t b_bytes = (uint32_t)TPS * NC * 128u;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   const uint32_t a_bytes = (uint32_t)p.Rpad * 128u;
-  const uint32_t b_bytes = (uint32_t)p.TPS * p.NC * 128u;
   const uint32_t sA = base;
   const uint32_t sB = sA + p.SA * a_bytes;
-  const uint32_t sBar = sB + p.SB * b_bytes;       // 8-byte barriers
+  const uint32_t sStage = sB + p.SB * b_bytes;     // epilogue store staging: 4 warps x 2 buffers x (32 rows x 128 B), SWIZZLE_128B
+  const uint32_t sBar = sStage + 4u * 2u * 4096u;  // 8-byte barriers
   const uint32_t bar_a_full = sBar, bar_a_empty = sBar + 8 * p.SA;
   const uint32_t bar_b_full = bar_a_empty + 8 * p.SA, bar_b_empty = bar_b_full + 8 * p.SB;
-  const uint32_t bar_acc_full = bar_b_empty + 8 * p.SB;   // [2]
-  const uint32_t bar_acc_empty = bar_acc_full + 16;       // [2]
-  const uint32_t s_tmem = bar_acc_empty + 16;
+  const uint32_t bar_main_full = bar_b_empty + 8 * p.SB;    // [2]
+  const uint32_t bar_main_empty = bar_main_full + 16;       // [2]
+  const uint32_t bar_corr_empty = bar_main_empty + 16;      // [2]
+  const uint32_t s_tmem = bar_corr_empty + 16;
   uint8_t* gen = smem_raw + (base - raw);
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen + (s_tmem - base));
 
@@ -171,7 +207,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.SA; ++i) { mbar_init(bar_a_full + 8 * i, 1); mbar_init(bar_a_empty + 8 * i, 1); }
     for (int i = 0; i < p.SB; ++i) { mbar_init(bar_b_full + 8 * i, 1); mbar_init(bar_b_empty + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(bar_acc_full + 8 * i, 1); mbar_init(bar_acc_empty + 8 * i, 4); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_main_full + 8 * i, 1); mbar_init(bar_main_empty + 8 * i, 4); mbar_init(bar_corr_empty + 8 * i, 4);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -181,180 +219,253 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  // broadcast through a shuffle so the compiler knows the value is warp-uniform (UTCHMMA operands live in uniform registers)
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
-  const int ngroups = p.ntaps / p.TPS;
-  const uint32_t buf_cols = 2u * p.MT * p.NC;
+  const int ngroups = p.ntaps / TPS;
 
   if (warp == 0) {
     // ===================== TMA producer (one lane) =====================
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmW) : "memory");
-      uint32_t ita = 0, itb = 0;
+      Ring ra, rb;
+      int tile = blockIdx.x % p.tiles_m, nsl = blockIdx.x / p.tiles_m;
       for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
-        const long long m0 = (long long)(w % p.tiles_m) * 128 * p.MT;
-        const int n0 = (w / p.tiles_m) * p.NC;
+        const int m0 = tile * 128 * MT;            // row index fits 31 bits (asserted on the host)
+        const int n0 = nsl * NC;
         auto load_a = [&](int j) {
-          const uint32_t sa = ita % p.SA, ph = (ita / p.SA) & 1u;
-          ++ita;
-          mbar_wait(bar_a_empty + 8 * sa, ph ^ 1u);
-          mbar_expect_tx(bar_a_full + 8 * sa, a_bytes);
-          for (int b = 0; b < p.nbA; ++b)
-            tma_load_2d(sA + sa * a_bytes + (uint32_t)b * p.RB * 128u, &tmA, j * 32, (int)(m0 - p.halo + (long long)b * p.RB),
-                        bar_a_full + 8 * sa);
+          mbar_wait(bar_a_empty + 8 * ra.idx, ra.phase ^ 1u);
+          const uint32_t full = bar_a_full + 8 * ra.idx, dst = sA + ra.idx * a_bytes;
+          if (p.dbg & 8) { mbar_arrive(full); }
+          else {
+            mbar_expect_tx(full, a_bytes);
+            for (int b = 0; b < p.nbA; ++b) tma_load_2d(dst + (uint32_t)b * p.RB * 128u, &tmA, j * 32, m0 - p.halo + b * p.RB, full);
+          }
+          ra.advance(p.SA);
         };
         load_a(0);
-        for (int j = 0; j < p.nchunk; ++j) {
+        int wrow = n0;                              // row of W tile (tap 0, chunk j): (tap*nchunk + j)*Cout + n0
+        const int tap_stride = p.nchunk * p.Cout;
+        for (int j = 0; j < p.nchunk; ++j, wrow += p.Cout) {
+          int wr = wrow;
           for (int g = 0; g < ngroups; ++g) {
-            const uint32_t sb = itb % p.SB, ph = (itb / p.SB) & 1u;
-            ++itb;
-            mbar_wait(bar_b_empty + 8 * sb, ph ^ 1u);
-            mbar_expect_tx(bar_b_full + 8 * sb, b_bytes);
-            for (int t = 0; t < p.TPS; ++t) {
-              const int tap = g * p.TPS + t;
-              tma_load_2d(sB + sb * b_bytes + (uint32_t)(t * p.NC) * 128u, &tmW, 0, (tap * p.nchunk + j) * p.Cout + n0,
-                          bar_b_full + 8 * sb);
+            mbar_wait(bar_b_empty + 8 * rb.idx, rb.phase ^ 1u);
+            const uint32_t full = bar_b_full + 8 * rb.idx, dst = sB + rb.idx * b_bytes;
+            if (p.dbg & 4) mbar_arrive(full);
+            else {
+              mbar_expect_tx(full, b_bytes);
+#pragma unroll
+              for (int t = 0; t < TPS; ++t, wr += tap_stride) tma_load_2d(dst + (uint32_t)(t * NC) * 128u, &tmW, 0, wr, full);
             }
+            rb.advance(p.SB);
             if (g == 0 && j + 1 < p.nchunk) load_a(j + 1);   // next activation window right behind the first weights
           }
         }
+        tile += gridDim.x;
+        while (tile >= p.tiles_m) { tile -= p.tiles_m; ++nsl; }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer: warp-uniform control flow, one elected lane issues =====================
-    const uint32_t leader = elect_one();
+    const bool no_mma = (p.dbg & 1) != 0;
     // instruction descriptor: D=F32, A=B=TF32, K-major both, N = NC, M = 128
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.NC >> 3) << 17) | ((128u >> 4) << 24);
-    const uint64_t a_desc0 = umma_desc(sA, p.bo_mode), b_desc0 = umma_desc(sB, p.bo_mode);
-    uint32_t ita = 0, itb = 0, tl = 0;
+    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NC >> 3) << 17) | ((128u >> 4) << 24);
+    const uint64_t d0 = umma_desc(sA, p.bo_mode);
+    const uint32_t desc_hi = (uint32_t)(d0 >> 32);                    // identical for A and B tiles
+    const uint32_t a_lo0 = (uint32_t)d0, b_lo0 = (uint32_t)umma_desc(sB, p.bo_mode);
+    const uint32_t a_step = a_bytes >> 4;
+    const uint32_t wp8 = (uint32_t)p.Wp * 8u;                         // one image row down, in 16-byte units of the window
+    Ring ra, rb;
+    uint32_t dg = 0, dgp = 0, tl = 0;       // drain-group buffer / phase, tile counter
+    bool b_ready = false;                   // result of an early poll of the current weight stage
     for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++tl) {
-      const uint32_t buf = p.dbuf ? (tl & 1u) : 0u;
-      const uint32_t use = p.dbuf ? (tl >> 1) : tl;
-      mbar_wait(bar_acc_empty + 8 * buf, (use & 1u) ^ 1u);        // epilogue has drained this accumulator buffer
+      const uint32_t cbuf = tl & 1u;
+      mbar_wait(bar_corr_empty + 8 * cbuf, ((tl >> 1) & 1u) ^ 1u);     // epilogue has read this corr buffer
       tc_fence_after();
-      const uint32_t d_main = tmem_base + buf * buf_cols;
-      const uint32_t d_corr = d_main + (uint32_t)(p.MT * p.NC);
+      const uint32_t d_corr = tmem_base + (2u + cbuf) * GC;
+      uint32_t d_main = tmem_base;
+      int jj = 0;
       for (int j = 0; j < p.nchunk; ++j) {
-        const uint32_t sa = ita % p.SA;
-        mbar_wait(bar_a_full + 8 * sa, (ita / p.SA) & 1u);
-        ++ita;
-        tc_fence_after();
-        const uint64_t a_slot = a_desc0 + (uint64_t)((sa * a_bytes) >> 4);
-        for (int g = 0; g < ngroups; ++g) {
-          const uint32_t sb = itb % p.SB;
-          mbar_wait(bar_b_full + 8 * sb, (itb / p.SB) & 1u);
-          ++itb;
+        if (jj == 0) {
+          mbar_wait(bar_main_empty + 8 * dg, dgp ^ 1u);               // epilogue has drained this main buffer
           tc_fence_after();
-          const uint64_t b_slot = b_desc0 + (uint64_t)((sb * b_bytes) >> 4);
-          for (int t = 0; t < p.TPS; ++t) {
-            const int tap = g * p.TPS + t;
-            const uint32_t shift = (p.ntaps == 9) ? (uint32_t)((tap / 3) * p.Wp + (tap % 3)) : 0u;
-            const uint64_t b_tap = b_slot + (uint64_t)(t * p.NC * 8);          // 128 B per row = 8 x 16 B
-            const uint32_t fresh = (j == 0 && tap == 0) ? 0u : 1u;
-            for (int mt = 0; mt < p.MT; ++mt) {
-              const uint64_t a_mt = a_slot + (uint64_t)((mt * 128 + shift) * 8);
-              const uint32_t dm = d_main + (uint32_t)(mt * p.NC), dc = d_corr + (uint32_t)(mt * p.NC);
-              if (leader) {
+          d_main = tmem_base + dg * GC;
+        }
+        mbar_wait(bar_a_full + 8 * ra.idx, ra.phase);
+        tc_fence_after();
+        const uint32_t a_slot = a_lo0 + ra.idx * a_step;
+        uint32_t sh8 = 0;                   // window row shift of the group's first tap, in 16-byte units
+        uint32_t kx = 0;
+        for (int g = 0; g < ngroups; ++g) {
+          if (!b_ready) mbar_wait(bar_b_full + 8 * rb.idx, rb.phase);
+          tc_fence_after();
+          const uint32_t b_slot = b_lo0 + rb.idx * (b_bytes >> 4);
+          const uint32_t b_empty_bar = bar_b_empty + 8 * rb.idx;
+          rb.advance(p.SB);
+          b_ready = mbar_try(bar_b_full + 8 * rb.idx, rb.phase);   // poll the NEXT stage now; its latency hides behind the MMA issue
+          const uint32_t acc_main = (jj == 0 && g == 0) ? 0u : 1u;
+          const uint32_t acc_corr = (j == 0 && g == 0) ? 0u : 1u;
+          if (!no_mma && elect_one()) {
+#pragma unroll
+            for (int t = 0; t < TPS; ++t) {
+#pragma unroll
+              for (int mt = 0; mt < MT; ++mt) {
+                const uint32_t a = a_slot + sh8 + (uint32_t)(t * 8 + mt * 1024);      // +1 row per tap, +128 rows per mt
+                const uint32_t b = b_slot + (uint32_t)(t * NC * 8);
+                const uint32_t dm = d_main + (uint32_t)(mt * NC), dc = d_corr + (uint32_t)(mt * NC);
                 // k-step 0: floats 0..7 of hi (bytes 0..31) and of lo (bytes 64..95); k-step 1: +32 B
-                tc_mma_tf32(dm, a_mt, b_tap, idesc, fresh);              // hi * hi
-                tc_mma_tf32(dc, a_mt, b_tap + 4, idesc, fresh);          // hi * lo
-                tc_mma_tf32(dc, a_mt + 4, b_tap, idesc, 1u);             // lo * hi
-                tc_mma_tf32(dm, a_mt + 2, b_tap + 2, idesc, 1u);
-                tc_mma_tf32(dc, a_mt + 2, b_tap + 6, idesc, 1u);
-                tc_mma_tf32(dc, a_mt + 6, b_tap + 2, idesc, 1u);
+                tc_mma_tf32(dm, desc64(desc_hi, a), desc64(desc_hi, b), idesc, t == 0 ? acc_main : 1u);     // hi * hi
+                tc_mma_tf32(dc, desc64(desc_hi, a), desc64(desc_hi, b + 4), idesc, t == 0 ? acc_corr : 1u); // hi * lo
+                tc_mma_tf32(dc, desc64(desc_hi, a + 4), desc64(desc_hi, b), idesc, 1u);                     // lo * hi
+                tc_mma_tf32(dm, desc64(desc_hi, a + 2), desc64(desc_hi, b + 2), idesc, 1u);
+                tc_mma_tf32(dc, desc64(desc_hi, a + 2), desc64(desc_hi, b + 6), idesc, 1u);
+                tc_mma_tf32(dc, desc64(desc_hi, a + 6), desc64(desc_hi, b + 2), idesc, 1u);
               }
             }
+            tc_commit(b_empty_bar);                         // weights stage free once these MMAs retire
+          } else if (no_mma && lane == 0) {
+            mbar_arrive(b_empty_bar);
           }
-          if (leader) tc_commit(bar_b_empty + 8 * sb);     // weights stage free once these MMAs retire
+          // next group's first tap: TPS==3 -> one image row down; TPS==1 -> next tap of the 3x3 stencil
+          if (TPS == 3) sh8 += wp8;
+          else if (p.ntaps == 9) { if (++kx == 3) { kx = 0; sh8 += wp8 - 16; } else sh8 += 8; }
           __syncwarp();
         }
-        if (leader) tc_commit(bar_a_empty + 8 * sa);       // activation window free
+        if (no_mma) { if (lane == 0) mbar_arrive(bar_a_empty + 8 * ra.idx); }
+        else if (elect_one()) tc_commit(bar_a_empty + 8 * ra.idx);     // activation window free
+        ra.advance(p.SA);
+        if (++jj == p.CPD || j == p.nchunk - 1) {
+          if (no_mma) { if (lane == 0) mbar_arrive(bar_main_full + 8 * dg); }
+          else if (elect_one()) tc_commit(bar_main_full + 8 * dg);     // this drain group's partial sums are complete
+          jj = 0;
+          if (++dg == 2) { dg = 0; dgp ^= 1u; }
+        }
         __syncwarp();
       }
-      if (leader) tc_commit(bar_acc_full + 8 * buf);       // accumulators of this tile complete
-      __syncwarp();
     }
   } else {
     // ===================== epilogue (warps 2..5; TMEM lane quarter = warp % 4) =====================
     const int q = warp & 3;
     const int rowF = 2 * p.Cout;
-    uint32_t tl = 0;
+    constexpr int gpm = NC / 16;                            // 16-column groups per 128-row accumulator
+    const int ndrain = (p.nchunk + p.CPD - 1) / p.CPD;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int hpwp = p.Hp * p.Wp;
+    const uint32_t st_base = sStage + (uint32_t)q * 8192u;
+    uint32_t st_cnt = 0;
+    uint32_t tl = 0, dg = 0, dgp = 0;
+    int tile = blockIdx.x % p.tiles_m, nsl = blockIdx.x / p.tiles_m;
     for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++tl) {
-      const long long m0 = (long long)(w % p.tiles_m) * 128 * p.MT;
-      const int n0 = (w / p.tiles_m) * p.NC;
-      const uint32_t buf = p.dbuf ? (tl & 1u) : 0u;
-      const uint32_t use = p.dbuf ? (tl >> 1) : tl;
-      mbar_wait(bar_acc_full + 8 * buf, use & 1u);
-      tc_fence_after();
-      const uint32_t t_main = tmem_base + buf * buf_cols + ((uint32_t)(q * 32) << 16);
-      const uint32_t t_corr = t_main + (uint32_t)(p.MT * p.NC);
-      for (int mt = 0; mt < p.MT; ++mt) {
-        const long long m = m0 + mt * 128 + q * 32 + lane;
-        const bool valid = m < p.M;
-        bool interior = false;
-        if (valid) {
-          const int r = (int)(m % ((long long)p.Hp * p.Wp));
-          const int py = r / p.Wp, px = r % p.Wp;
-          interior = py >= 1 && py <= p.H && px >= 1 && px <= p.W;
-        }
-        float* orow = p.out + m * rowF + 2 * n0;
-        const float* rrow = p.res ? p.res + m * rowF + 2 * n0 : nullptr;
-        for (int c0 = 0; c0 < p.NC; c0 += 16) {
-          uint32_t r[16], rc[16];
-          tc_ld16_nowait(t_main + (uint32_t)(mt * p.NC + c0), r);
-          tc_ld16_nowait(t_corr + (uint32_t)(mt * p.NC + c0), rc);
-          float4 rh[4], rl[4];
-          const bool do_res = rrow && valid && interior;
-          if (do_res) {
-            const float4* rp = reinterpret_cast<const float4*>(rrow + 2 * c0);
+      const long long m0 = (long long)tile * 128 * MT;
+      const int n0 = nsl * NC;
+      float acc[NG][16];
+      for (int d = 0; d < ndrain; ++d) {
+        mbar_wait(bar_main_full + 8 * dg, dgp);
+        tc_fence_after();
+        if (!(p.dbg & 16)) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { rh[i] = __ldg(rp + i); rl[i] = __ldg(rp + 4 + i); }
-          }
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          if (!valid) continue;
-          float4* o = reinterpret_cast<float4*>(orow + 2 * c0);
-          if (!interior) {
-            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int g = 0; g < NG; ++g) {
+            uint32_t r[16];
+            tc_ld16_nowait(t_lane + dg * GC + g * 16, r);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (d == 0) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = z;
-            continue;
-          }
-          const float4* bp = reinterpret_cast<const float4*>(p.bias + n0 + c0);
-          float v[16];
+              for (int i = 0; i < 16; ++i) acc[g][i] = __uint_as_float(r[i]);
+            } else {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 b4 = __ldg(bp + i);
-            v[4 * i + 0] = (__uint_as_float(r[4 * i + 0]) + __uint_as_float(rc[4 * i + 0])) + b4.x;
-            v[4 * i + 1] = (__uint_as_float(r[4 * i + 1]) + __uint_as_float(rc[4 * i + 1])) + b4.y;
-            v[4 * i + 2] = (__uint_as_float(r[4 * i + 2]) + __uint_as_float(rc[4 * i + 2])) + b4.z;
-            v[4 * i + 3] = (__uint_as_float(r[4 * i + 3]) + __uint_as_float(rc[4 * i + 3])) + b4.w;
-          }
-          if (do_res) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              v[4 * i + 0] += rh[i].x + rl[i].x; v[4 * i + 1] += rh[i].y + rl[i].y;
-              v[4 * i + 2] += rh[i].z + rl[i].z; v[4 * i + 3] += rh[i].w + rl[i].w;
+              for (int i = 0; i < 16; ++i) acc[g][i] += __uint_as_float(r[i]);
             }
           }
-          if (p.relu) {
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_main_empty + 8 * dg);
+        if (++dg == 2) { dg = 0; dgp ^= 1u; }
+      }
+      // the commit behind the last drain group also covers every hi*lo / lo*hi MMA of this tile
+      const uint32_t cbuf = tl & 1u;
+      if (!(p.dbg & 16)) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
-          }
+        for (int g = 0; g < NG; ++g) {
+          uint32_t r[16];
+          tc_ld16(t_lane + (2u + cbuf) * GC + g * 16, r);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            float4 hi, lo;
-            split4(make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]), hi, lo);
-            o[i] = hi;
-            o[4 + i] = lo;
-          }
+          for (int i = 0; i < 16; ++i) acc[g][i] += __uint_as_float(r[i]);
         }
       }
-      // all tcgen05.ld of this buffer have completed (wait::ld above): hand the accumulators back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_acc_empty + 8 * buf);
+      if (lane == 0) mbar_arrive(bar_corr_empty + 8 * cbuf);
+      // ---- bias / residual / ReLU / tf32 split / store (the MMA warp is already on the next tile)
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        const long long m = m0 + mt * 128 + q * 32 + lane;
+        if (p.dbg & 2) continue;
+        bool interior = false;
+        if (m < p.M) {
+          const int r = (int)(m % hpwp);
+          const int py = r / p.Wp, px = r - py * p.Wp;
+          interior = py >= 1 && py <= p.H && px >= 1 && px <= p.W;
+        }
+        const float* rrow = p.res ? p.res + m * rowF + 2 * n0 : nullptr;
+#pragma unroll
+        for (int gg = 0; gg < gpm; ++gg) {
+          const int g = mt * gpm + gg, c0 = gg * 16;
+          float4 hi[4], lo[4];
+          if (!interior) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) hi[i] = lo[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          } else {
+            const float4* bp = reinterpret_cast<const float4*>(p.bias + n0 + c0);
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 b4 = __ldg(bp + i);
+              v[4 * i + 0] = acc[g][4 * i + 0] + b4.x; v[4 * i + 1] = acc[g][4 * i + 1] + b4.y;
+              v[4 * i + 2] = acc[g][4 * i + 2] + b4.z; v[4 * i + 3] = acc[g][4 * i + 3] + b4.w;
+            }
+            if (rrow) {
+              const float4* rp = reinterpret_cast<const float4*>(rrow + 2 * c0);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float4 h = __ldg(rp + i), l = __ldg(rp + 4 + i);
+                v[4 * i + 0] += h.x + l.x; v[4 * i + 1] += h.y + l.y; v[4 * i + 2] += h.z + l.z; v[4 * i + 3] += h.w + l.w;
+              }
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) split4(make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]), hi[i], lo[i]);
+          }
+          // stage this warp's 32 rows x 128 B (hi16|lo16) in shared memory (128B-swizzled: conflict-free 16-byte stores),
+          // then ONE bulk tensor store writes them as full 128-byte lines (a per-thread row store would scatter 16-byte
+          // pieces over 32 lines per instruction).  Rows past the tensor end are clipped by the TMA unit.
+          const uint32_t sbuf = st_base + (st_cnt & 1u) * 4096u;
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the buffer used two stores ago is free
+          __syncwarp();
+          const uint32_t srow = sbuf + (uint32_t)lane * 128u;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            st_shared_v4(srow + (((uint32_t)i ^ (lane & 7u)) << 4), hi[i]);
+            st_shared_v4(srow + (((uint32_t)(4 + i) ^ (lane & 7u)) << 4), lo[i]);
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            const long long mrow = m0 + mt * 128 + q * 32;
+            if (mrow < p.M) tma_store_2d(&tmO, 2 * (n0 + c0), (int)mrow, sbuf);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          ++st_cnt;
+        }
+      }
+      tile += gridDim.x;
+      while (tile >= p.tiles_m) { tile -= p.tiles_m; ++nsl; }
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // staged rows fully written before smem goes away
   }
   tc_fence_before();
   __syncthreads();
@@ -364,13 +475,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
+typedef void (*TcKernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams);
+// (MT, NC, TPS) instantiations: NC*MT in {16..128} columns, TPS = 3 taps per weight stage for NC <= 64 3x3 convs
+static TcKernelFn tc_kernel_for(int MT, int NC, int TPS) {
+#define TCK(mt, nc, tps) if (MT == mt && NC == nc && TPS == tps) return conv_tc_kernel<(mt) * (nc) / 16, mt, tps>;
+  TCK(1, 16, 1) TCK(1, 16, 3) TCK(1, 32, 1) TCK(1, 32, 3) TCK(2, 32, 1) TCK(2, 32, 3)
+  TCK(1, 48, 1) TCK(1, 48, 3) TCK(2, 48, 1) TCK(2, 48, 3)
+  TCK(1, 64, 1) TCK(1, 64, 3) TCK(2, 64, 1) TCK(2, 64, 3)
+  TCK(1, 96, 1) TCK(1, 128, 1)
+#undef TCK
+  return nullptr;
+}
+
 // ------------------------------------------------------------------------------------------ host side
 struct TcConvPlan {
-  CUtensorMap tmA, tmW;
+  CUtensorMap tmA, tmW, tmO;
   TcParams p;
   int rows_per_img;
   size_t smem;
   int ns, num_sms;
+  TcKernelFn kernel;
 };
 
 static int env_int(const char* name, int dflt) {
@@ -414,7 +538,8 @@ cudaError_t tc_conv_plan_create(TcConvPlan** out, const float* in, float* outp, 
   const int Hp = H + 2, Wp = W + 2, ntaps = ks * ks, nchunk = Cin / 16;
   const int halo = ks == 3 ? Wp + 1 : 0;
   const long long Mmax = (long long)max_img * Hp * Wp;
-  const size_t smem_cap = 200 * 1024;
+  if (Mmax + 1024 >= (1LL << 31)) return cudaErrorNotSupported;   // TMA row coordinates are int32
+  const size_t smem_cap = 200 * 1024 - 32 * 1024;   // rings; 32 KB more for the epilogue store staging
   double best = 1e30;
   TcParams bp{};
   size_t bsmem = 0;
@@ -432,42 +557,43 @@ cudaError_t tc_conv_plan_create(TcConvPlan** out, const float* in, float* outp, 
     if (NC % 16 || NC > 256) continue;
     if (force_ns && ns != force_ns) continue;
     for (int MT = 4; MT >= 1; --MT) {
-      if (2 * MT * NC > 512) continue;
+      const int tps = (ntaps == 9 && NC <= 64) ? 3 : 1;
+      if (!tc_kernel_for(MT, NC, tps)) continue;
       if (force_mt && MT != force_mt) continue;
-      for (int dbuf = 1; dbuf >= 0; --dbuf) {
-        if (dbuf && 4 * MT * NC > 512) continue;
-        if (force_dbuf >= 0 && dbuf != force_dbuf) continue;
-        TcParams p{};
-        p.NC = NC; p.MT = MT; p.nchunk = nchunk; p.ntaps = ntaps; p.Cout = Cout; p.halo = halo; p.dbuf = dbuf;
-        p.TPS = (ntaps == 9 && NC <= 64) ? 3 : 1;
-        const int R = 128 * MT + 2 * halo;
-        p.nbA = (R + 255) / 256;
-        p.Rpad = ((R + 8 * p.nbA - 1) / (8 * p.nbA)) * (8 * p.nbA);
-        p.RB = p.Rpad / p.nbA;
-        p.SA = 2;
-        p.nsub = 1; p.Nsub = NC; p.nboxW = 1; p.NCbox = NC;
-        const size_t a_bytes = (size_t)p.Rpad * 128, b_bytes = (size_t)p.TPS * NC * 128;
-        int SB = 6;
-        while (SB > 2 && p.SA * a_bytes + SB * b_bytes + 4096 > smem_cap) --SB;
-        if (p.SA * a_bytes + SB * b_bytes + 4096 > smem_cap) continue;
-        p.SB = SB;
-        int cols = 32;
-        while (cols < (dbuf ? 2 : 1) * 2 * MT * NC) cols <<= 1;
-        p.tmem_cols = cols;
-        p.tiles_m = (int)((Mmax + 128LL * MT - 1) / (128LL * MT));
-        p.total_work = p.tiles_m * ns;
-        const int ctas = p.total_work < num_sms ? p.total_work : num_sms;
-        const double items = (double)((p.total_work + ctas - 1) / ctas);
-        // clocks per work item: tf32 MMA at 2048 MAC/clk/SM, but never faster than the operands can be read from
-        // shared memory (128 B/clk: A 4 KB + B NC*32 B per MMA) or fetched from L2 (~32 B/clk/SM)
-        const double n_mma = 6.0 * ntaps * nchunk * MT;
-        const double mma = n_mma * std::max(NC / 2.0, (4096.0 + NC * 32.0) / 128.0);
-        const double bytes = (double)nchunk * (a_bytes + (double)ntaps * NC * 128);
-        const double epi = (double)MT * (NC / 16) * 260.0 + 1500.0;
-        const double item = std::max(mma, bytes / 32.0) + (dbuf ? 0.0 : epi);
-        const double t = items * std::max(item, dbuf ? epi : 0.0) + 4000.0;
-        if (t < best) { best = t; bp = p; bsmem = p.SA * a_bytes + p.SB * b_bytes + 4096; bns = ns; }
-      }
+      TcParams p{};
+      p.NC = NC; p.MT = MT; p.nchunk = nchunk; p.ntaps = ntaps; p.Cout = Cout; p.halo = halo; p.dbuf = 1;
+      p.TPS = tps;
+      // accumulation-length bound: at most ~max_steps hi*hi MMA steps per TMEM accumulator before a drain
+      const int max_steps = env_int("PE_TC_MAXSTEPS", 18);
+      p.CPD = std::max(1, max_steps / (2 * ntaps));
+      if (p.CPD > nchunk) p.CPD = nchunk;
+      const int R = 128 * MT + 2 * halo;
+      p.nbA = (R + 255) / 256;
+      p.Rpad = ((R + 8 * p.nbA - 1) / (8 * p.nbA)) * (8 * p.nbA);
+      p.RB = p.Rpad / p.nbA;
+      p.SA = 2;
+      p.nsub = 1; p.Nsub = NC; p.nboxW = 1; p.NCbox = NC;
+      const size_t a_bytes = (size_t)p.Rpad * 128, b_bytes = (size_t)p.TPS * NC * 128;
+      int SB = 6;
+      while (SB > 2 && p.SA * a_bytes + SB * b_bytes + 4096 > smem_cap) --SB;
+      if (p.SA * a_bytes + SB * b_bytes + 4096 > smem_cap) continue;
+      p.SB = SB;
+      int cols = 32;
+      while (cols < 4 * MT * NC) cols <<= 1;
+      p.tmem_cols = cols;
+      p.tiles_m = (int)((Mmax + 128LL * MT - 1) / (128LL * MT));
+      p.total_work = p.tiles_m * ns;
+      const int ctas = p.total_work < num_sms ? p.total_work : num_sms;
+      const double items = (double)((p.total_work + ctas - 1) / ctas);
+      // clocks per work item: tf32 MMA at 2048 MAC/clk/SM, but never faster than the operands can be read from
+      // shared memory (128 B/clk: A 4 KB + B NC*32 B per MMA) or fetched from L2 (~32 B/clk/SM)
+      const double n_mma = 6.0 * ntaps * nchunk * MT;
+      const double mma = n_mma * std::max(NC / 2.0, (4096.0 + NC * 32.0) / 128.0);
+      const double bytes = (double)nchunk * (a_bytes + (double)ntaps * NC * 128);
+      const double epi = (double)MT * (NC / 16) * 260.0 + 1500.0;
+      const double item = std::max(std::max(mma, bytes / 32.0), epi);
+      const double t = items * item + 4000.0;
+      if (t < best) { best = t; bp = p; bsmem = p.SA * a_bytes + p.SB * b_bytes + 32768 + 4096; bns = ns; }
     }
   }
   if (best >= 1e30) return cudaErrorNotSupported;
@@ -476,26 +602,28 @@ cudaError_t tc_conv_plan_create(TcConvPlan** out, const float* in, float* outp, 
   pl->p.out = outp; pl->p.res = res; pl->p.bias = bias;
   pl->p.H = H; pl->p.W = W; pl->p.Hp = Hp; pl->p.Wp = Wp; pl->p.relu = relu;
   pl->p.bo_mode = env_int("PE_TC_BO_MODE", 1);
+  pl->p.dbg = env_int("PE_TC_DBG", 0);
   pl->rows_per_img = Hp * Wp;
   pl->smem = bsmem;
   pl->ns = bns;
   CUresult r1 = encode_2d(&pl->tmA, in, (uint64_t)2 * Cin, (uint64_t)Mmax, (uint64_t)2 * Cin * 4, 32, (uint32_t)bp.RB);
   CUresult r2 = encode_2d(&pl->tmW, wtc, 32, (uint64_t)ntaps * nchunk * Cout, 128, 32, (uint32_t)bp.NCbox);
+  CUresult r3 = encode_2d(&pl->tmO, outp, (uint64_t)2 * Cout, (uint64_t)Mmax, (uint64_t)2 * Cout * 4, 32, 32);
+  if (r3 != CUDA_SUCCESS) r1 = r3;
   if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) {
     fprintf(stderr, "conv_tc: cuTensorMapEncodeTiled failed (%d, %d) Cin=%d Cout=%d RB=%d NCbox=%d\n", (int)r1, (int)r2, Cin, Cout, bp.RB, bp.NCbox);
     delete pl;
     return cudaErrorInvalidValue;
   }
-  static size_t attr_set = 0;
-  if (pl->smem > attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(210 * 1024));
+  pl->kernel = tc_kernel_for(bp.MT, bp.NC, bp.TPS);
+  {
+    cudaError_t e = cudaFuncSetAttribute(pl->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(210 * 1024));
     if (e != cudaSuccess) { delete pl; return e; }
-    attr_set = 210 * 1024;
   }
   pl->num_sms = num_sms;
   if (env_int("PE_TC_VERBOSE", 0))
-    fprintf(stderr, "conv_tc plan: Cin=%d Cout=%d ks=%d %dx%d  MT=%d NS=%d NC=%d dbuf=%d TPS=%d SA=%d SB=%d Rpad=%d RB=%d smem=%zu tmem=%d work=%d\n", Cin, Cout, ks, H, W,
-            bp.MT, bns, bp.NC, bp.dbuf, bp.TPS, bp.SA, bp.SB, bp.Rpad, bp.RB, pl->smem, bp.tmem_cols, bp.total_work);
+    fprintf(stderr, "conv_tc plan: Cin=%d Cout=%d ks=%d %dx%d  MT=%d NS=%d NC=%d CPD=%d TPS=%d SA=%d SB=%d Rpad=%d RB=%d smem=%zu tmem=%d work=%d\n", Cin, Cout, ks, H, W,
+            bp.MT, bns, bp.NC, bp.CPD, bp.TPS, bp.SA, bp.SB, bp.Rpad, bp.RB, pl->smem, bp.tmem_cols, bp.total_work);
   *out = pl;
   return cudaSuccess;
 }
@@ -508,6 +636,6 @@ cudaError_t tc_conv_launch(TcConvPlan* pl, int nimg, cudaStream_t st) {
   p.tiles_m = (int)((p.M + 128LL * p.MT - 1) / (128LL * p.MT));
   p.total_work = p.tiles_m * pl->ns;
   const unsigned grid = (unsigned)(p.total_work < pl->num_sms ? p.total_work : pl->num_sms);
-  conv_tc_kernel<<<grid, 192, pl->smem, st>>>(pl->tmA, pl->tmW, p);
+  pl->kernel<<<grid, 192, pl->smem, st>>>(pl->tmA, pl->tmW, pl->tmO, p);
   return cudaGetLastError();
 }

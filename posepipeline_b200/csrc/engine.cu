@@ -272,6 +272,8 @@ struct pe_model {
   size_t ev_used = 0;
   cudaEvent_t ev_fwd0 = nullptr, ev_fwd1 = nullptr;
   double acc_conv_ms = 0, acc_total_ms = 0; int64_t acc_conv_launches = 0;
+  std::vector<double> op_ms;       // per-op accumulated device time while profiling
+  std::vector<int> ev_op;          // op index of each recorded event pair
 };
 
 static float* act_ptr(pe_model* m, int tid) { return m->slots[m->tensors[tid].slot]; }
@@ -383,13 +385,16 @@ static int forward(pe_model* m, int ncrop, int nimg) {
     const pe_op_desc& op = m->ops[i];
     const pe_tensor_desc& to = m->tensors[op.out];
     const bool is_conv = (op.kind == PE_OP_CONV);
-    if (m->profile && is_conv) {
+    const bool timed = m->profile && (is_conv || m->profile > 1);
+    if (timed) {
       if (m->ev_used == m->ev_conv.size()) {
         cudaEvent_t a, b;
         cudaEventCreate(&a); cudaEventCreate(&b);
         m->ev_conv.push_back({a, b});
       }
       cudaEventRecord(m->ev_conv[m->ev_used].first, st);
+      if (m->ev_op.size() <= m->ev_used) m->ev_op.resize(m->ev_used + 1);
+      m->ev_op[m->ev_used] = (int)i;
     }
     switch (op.kind) {
       case PE_OP_STEM:
@@ -423,7 +428,7 @@ static int forward(pe_model* m, int ncrop, int nimg) {
       default:
         return fail(PE_ERR_INVALID, "unknown op kind %d", op.kind);
     }
-    if (m->profile && is_conv) { cudaEventRecord(m->ev_conv[m->ev_used].second, st); ++m->ev_used; }
+    if (timed) { cudaEventRecord(m->ev_conv[m->ev_used].second, st); ++m->ev_used; }
     ++m->launches;
   }
   if (m->profile) cudaEventRecord(m->ev_fwd1, st);
@@ -438,9 +443,10 @@ static int profile_collect(pe_model* m) {
   float ms = 0;
   for (size_t i = 0; i < m->ev_used; ++i) {
     CU(cudaEventElapsedTime(&ms, m->ev_conv[i].first, m->ev_conv[i].second));
-    m->acc_conv_ms += ms;
+    if (m->op_ms.size() < m->ops.size()) m->op_ms.assign(m->ops.size(), 0.0);
+    m->op_ms[m->ev_op[i]] += ms;
+    if (m->ops[m->ev_op[i]].kind == PE_OP_CONV) { m->acc_conv_ms += ms; ++m->acc_conv_launches; }
   }
-  m->acc_conv_launches += (int64_t)m->ev_used;
   CU(cudaEventElapsedTime(&ms, m->ev_fwd0, m->ev_fwd1));
   m->acc_total_ms += ms;
   return PE_OK;
@@ -611,6 +617,7 @@ extern "C" int pe_model_profile(pe_model* m, int32_t enable) {
   if (!m) return fail(PE_ERR_INVALID, "bad argument");
   m->profile = enable;
   m->acc_conv_ms = m->acc_total_ms = 0; m->acc_conv_launches = 0;
+  m->op_ms.assign(m->ops.size(), 0.0);
   return PE_OK;
 }
 
@@ -688,4 +695,10 @@ done:
   cudaStreamSynchronize(st);
   cudaFree(d_in); cudaFree(d_out); cudaFree(d_res); cudaFree(d_dense); cudaFree(d_w); cudaFree(d_wtc); cudaFree(d_b);
   return rc;
+}
+
+extern "C" int pe_model_profile_ops(pe_model* m, double* ms_per_op, int32_t n_ops) {
+  if (!m || !ms_per_op || n_ops != (int32_t)m->ops.size()) return fail(PE_ERR_INVALID, "bad argument to pe_model_profile_ops");
+  for (int i = 0; i < n_ops; ++i) ms_per_op[i] = i < (int)m->op_ms.size() ? m->op_ms[i] : 0.0;
+  return PE_OK;
 }

@@ -276,8 +276,13 @@ class TopDownModel:
         check(self.lib.pe_model_launch_count(self.h, C.byref(v)))
         return v.value
 
-    def profile(self, enable: bool):
+    def profile(self, enable):
         check(self.lib.pe_model_profile(self.h, int(enable)))
+
+    def profile_ops(self) -> np.ndarray:
+        ms = np.zeros(len(self.program.ops), np.float64)
+        check(self.lib.pe_model_profile_ops(self.h, ptr(ms), len(ms)))
+        return ms
 
     def profile_read(self):
         a, b, n = C.c_double(), C.c_double(), C.c_int64()
