@@ -76,6 +76,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
   }
 }
+// same, for waits that are expected to be long (epilogue): back off so the polling does not crowd the LSU
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, uint32_t ns) {
+  uint32_t spins = 0;
+  while (!mbar_try(bar, parity)) {
+    if (ns) __nanosleep(ns);
+    if (++spins > 100000000u) { printf("conv_tc: mbarrier timeout (relaxed)\n"); __trap(); }
+  }
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
@@ -278,7 +286,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t wp8 = (uint32_t)p.Wp * 8u;                         // one image row down, in 16-byte units of the window
     Ring ra, rb;
     uint32_t dg = 0, dgp = 0, tl = 0;       // drain-group buffer / phase, tile counter
-    bool b_ready = false;                   // result of an early poll of the current weight stage
+    bool b_ready = false, a_ready = false, m_ready = false;   // results of early polls (latency hidden behind MMA issue)
     for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++tl) {
       const uint32_t cbuf = tl & 1u;
       mbar_wait(bar_corr_empty + 8 * cbuf, ((tl >> 1) & 1u) ^ 1u);     // epilogue has read this corr buffer
@@ -288,11 +296,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int jj = 0;
       for (int j = 0; j < p.nchunk; ++j) {
         if (jj == 0) {
-          mbar_wait(bar_main_empty + 8 * dg, dgp ^ 1u);               // epilogue has drained this main buffer
-          tc_fence_after();
+          if (!m_ready) mbar_wait(bar_main_empty + 8 * dg, dgp ^ 1u); // epilogue has drained this main buffer
           d_main = tmem_base + dg * GC;
         }
-        mbar_wait(bar_a_full + 8 * ra.idx, ra.phase);
+        if (!a_ready) mbar_wait(bar_a_full + 8 * ra.idx, ra.phase);
         tc_fence_after();
         const uint32_t a_slot = a_lo0 + ra.idx * a_step;
         uint32_t sh8 = 0;                   // window row shift of the group's first tap, in 16-byte units
@@ -335,11 +342,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (no_mma) { if (lane == 0) mbar_arrive(bar_a_empty + 8 * ra.idx); }
         else if (elect_one()) tc_commit(bar_a_empty + 8 * ra.idx);     // activation window free
         ra.advance(p.SA);
+        a_ready = mbar_try(bar_a_full + 8 * ra.idx, ra.phase);         // early polls for the next chunk
         if (++jj == p.CPD || j == p.nchunk - 1) {
           if (no_mma) { if (lane == 0) mbar_arrive(bar_main_full + 8 * dg); }
           else if (elect_one()) tc_commit(bar_main_full + 8 * dg);     // this drain group's partial sums are complete
           jj = 0;
           if (++dg == 2) { dg = 0; dgp ^= 1u; }
+          m_ready = mbar_try(bar_main_empty + 8 * dg, dgp ^ 1u);
         }
         __syncwarp();
       }
@@ -361,7 +370,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int n0 = nsl * NC;
       float acc[NG][16];
       for (int d = 0; d < ndrain; ++d) {
-        mbar_wait(bar_main_full + 8 * dg, dgp);
+        mbar_wait_relaxed(bar_main_full + 8 * dg, dgp, (p.dbg >> 8) & 0xfff);
         tc_fence_after();
         if (!(p.dbg & 16)) {
 #pragma unroll
@@ -382,6 +391,41 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_main_empty + 8 * dg);
         if (++dg == 2) { dg = 0; dgp ^= 1u; }
+        if (d == 0 && p.res && !(p.dbg & 2)) {
+          // Residual add, folded into the accumulators NOW: the loads' HBM/L2 latency hides behind the MMAs of the
+          // remaining channel chunks instead of sitting in the store phase (software-pipelined one group ahead).
+          float4 cur[8], nxt[8];
+          auto fetch = [&](int g, float4 (&dst)[8]) {
+            const int mt = g / gpm, c0 = (g % gpm) * 16;
+            const long long m = m0 + mt * 128 + q * 32 + lane;
+            bool ok = false;
+            if (m < p.M) {
+              const int r = (int)(m % hpwp);
+              const int py = r / p.Wp, px = r - py * p.Wp;
+              ok = py >= 1 && py <= p.H && px >= 1 && px <= p.W;
+            }
+            if (ok) {
+              const float4* rp = reinterpret_cast<const float4*>(p.res + m * rowF + 2 * (n0 + c0));
+#pragma unroll
+              for (int i = 0; i < 8; ++i) dst[i] = __ldg(rp + i);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          };
+          fetch(0, cur);
+#pragma unroll
+          for (int g = 0; g < NG; ++g) {
+            if (g + 1 < NG) fetch(g + 1, nxt);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              acc[g][4 * i + 0] += cur[i].x + cur[4 + i].x; acc[g][4 * i + 1] += cur[i].y + cur[4 + i].y;
+              acc[g][4 * i + 2] += cur[i].z + cur[4 + i].z; acc[g][4 * i + 3] += cur[i].w + cur[4 + i].w;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
+          }
+        }
       }
       // the commit behind the last drain group also covers every hi*lo / lo*hi MMA of this tile
       const uint32_t cbuf = tl & 1u;
@@ -408,7 +452,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int py = r / p.Wp, px = r - py * p.Wp;
           interior = py >= 1 && py <= p.H && px >= 1 && px <= p.W;
         }
-        const float* rrow = p.res ? p.res + m * rowF + 2 * n0 : nullptr;
 #pragma unroll
         for (int gg = 0; gg < gpm; ++gg) {
           const int g = mt * gpm + gg, c0 = gg * 16;
@@ -424,14 +467,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const float4 b4 = __ldg(bp + i);
               v[4 * i + 0] = acc[g][4 * i + 0] + b4.x; v[4 * i + 1] = acc[g][4 * i + 1] + b4.y;
               v[4 * i + 2] = acc[g][4 * i + 2] + b4.z; v[4 * i + 3] = acc[g][4 * i + 3] + b4.w;
-            }
-            if (rrow) {
-              const float4* rp = reinterpret_cast<const float4*>(rrow + 2 * c0);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float4 h = __ldg(rp + i), l = __ldg(rp + 4 + i);
-                v[4 * i + 0] += h.x + l.x; v[4 * i + 1] += h.y + l.y; v[4 * i + 2] += h.z + l.z; v[4 * i + 3] += h.w + l.w;
-              }
             }
             if (p.relu) {
 #pragma unroll
@@ -482,7 +517,7 @@ static TcKernelFn tc_kernel_for(int MT, int NC, int TPS) {
   TCK(1, 16, 1) TCK(1, 16, 3) TCK(1, 32, 1) TCK(1, 32, 3) TCK(2, 32, 1) TCK(2, 32, 3)
   TCK(1, 48, 1) TCK(1, 48, 3) TCK(2, 48, 1) TCK(2, 48, 3)
   TCK(1, 64, 1) TCK(1, 64, 3) TCK(2, 64, 1) TCK(2, 64, 3)
-  TCK(1, 96, 1) TCK(1, 128, 1)
+  TCK(1, 96, 1) TCK(1, 96, 3) TCK(1, 128, 1) TCK(1, 128, 3)
 #undef TCK
   return nullptr;
 }
@@ -557,7 +592,7 @@ cudaError_t tc_conv_plan_create(TcConvPlan** out, const float* in, float* outp, 
     if (NC % 16 || NC > 256) continue;
     if (force_ns && ns != force_ns) continue;
     for (int MT = 4; MT >= 1; --MT) {
-      const int tps = (ntaps == 9 && NC <= 64) ? 3 : 1;
+     for (int tps = (ntaps == 9 ? 3 : 1); tps >= 1; tps -= 2) {
       if (!tc_kernel_for(MT, NC, tps)) continue;
       if (force_mt && MT != force_mt) continue;
       TcParams p{};
@@ -575,7 +610,7 @@ cudaError_t tc_conv_plan_create(TcConvPlan** out, const float* in, float* outp, 
       p.nsub = 1; p.Nsub = NC; p.nboxW = 1; p.NCbox = NC;
       const size_t a_bytes = (size_t)p.Rpad * 128, b_bytes = (size_t)p.TPS * NC * 128;
       int SB = 6;
-      while (SB > 2 && p.SA * a_bytes + SB * b_bytes + 4096 > smem_cap) --SB;
+      while (SB > 3 && p.SA * a_bytes + SB * b_bytes + 4096 > smem_cap) --SB;
       if (p.SA * a_bytes + SB * b_bytes + 4096 > smem_cap) continue;
       p.SB = SB;
       int cols = 32;
@@ -587,13 +622,16 @@ cudaError_t tc_conv_plan_create(TcConvPlan** out, const float* in, float* outp, 
       const double items = (double)((p.total_work + ctas - 1) / ctas);
       // clocks per work item: tf32 MMA at 2048 MAC/clk/SM, but never faster than the operands can be read from
       // shared memory (128 B/clk: A 4 KB + B NC*32 B per MMA) or fetched from L2 (~32 B/clk/SM)
+      // measured (tools/mma_bench.cu): one M=128 SS tcgen05.mma takes max(N/2, 32 + N/4) clocks -- below N=128 the
+      // 4 KB A-operand read from shared memory paces it -- plus ~300 clocks of barrier hand-off per pipeline stage
       const double n_mma = 6.0 * ntaps * nchunk * MT;
-      const double mma = n_mma * std::max(NC / 2.0, (4096.0 + NC * 32.0) / 128.0);
+      const double mma = n_mma * std::max(NC / 2.0, 32.0 + NC / 4.0) + 300.0 * (ntaps / tps) * nchunk;
       const double bytes = (double)nchunk * (a_bytes + (double)ntaps * NC * 128);
       const double epi = (double)MT * (NC / 16) * 260.0 + 1500.0;
       const double item = std::max(std::max(mma, bytes / 32.0), epi);
       const double t = items * item + 4000.0;
       if (t < best) { best = t; bp = p; bsmem = p.SA * a_bytes + p.SB * b_bytes + 32768 + 4096; bns = ns; }
+     }
     }
   }
   if (best >= 1e30) return cudaErrorNotSupported;
