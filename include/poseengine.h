@@ -141,12 +141,13 @@ int pe_model_profile_read(pe_model* m, double* conv_ms, double* other_ms, int64_
 /* per-op accumulated device milliseconds since pe_model_profile(m, 2) (enable=2 times every op, 1 only the convolutions) */
 int pe_model_profile_ops(pe_model* m, double* ms_per_op, int32_t n_ops);
 
-/* one convolution layer on its own (stride 1, k in {1,3}, BN already folded): dense NCHW in/out; the library packs to its
- * HBM layout, runs the SIMT (use_tc=0) or tcgen05 (use_tc=1) kernel, verifies the zero halo and unpacks.
- * w_simt: [k*k][Cin][Cout]; w_tc: [k*k][Cin/16][Cout][hi16|lo16]. */
+/* one convolution layer on its own (k in {1,3}, stride 1, or 3x3 stride 2; BN already folded): dense NCHW in/out; the
+ * library packs to its HBM layout, runs the SIMT (use_tc=0) or tcgen05 (use_tc=1) kernel, verifies the zero halo and
+ * unpacks.  w_simt: [k*k][Cin][Cout]; w_tc: [k*k][Cin/16][Cout][hi16|lo16] (stride 2: the 2x2 space-to-depth form,
+ * [4][4*Cin/16][Cout][32]).  H, W are the input dims; the output is H/stride x W/stride. */
 int pe_conv_test(pe_engine* e, const float* in_nchw, int32_t nimg, int32_t Cin, int32_t H, int32_t W, const float* w_simt,
-                 const float* w_tc, const float* bias, const float* res_nchw, int32_t Cout, int32_t ks, int32_t relu,
-                 int32_t use_tc, float* out_nchw);
+                 const float* w_tc, const float* bias, const float* res_nchw, int32_t Cout, int32_t ks, int32_t stride,
+                 int32_t relu, int32_t use_tc, float* out_nchw);
 
 /* ---- VideoPose3D lifter (wrappers/videopose3d.py:46-85; TemporalModelOptimized1f 243 frames) ---- */
 int pe_lifter_create(pe_engine* e, const float* weights, int64_t n_floats, const int64_t* offsets /*see lifter.py*/,

@@ -33,7 +33,8 @@ struct TcParams {
   long long M;     // rows (padded positions) of this launch
   int H, W, Hp, Wp;
   int nchunk, ntaps, Cout, NC, MT, TPS, SA, SB;
-  int Rpad, RB, nbA, halo;
+  int Rpad, RB, nbA, halo;   // halo = window rows BEFORE the tile's first row
+  int tapw;                  // taps per stencil row: 3 (3x3), 2 (2x2 over the space-to-depth tensor), 1 (1x1)
   int nsub, Nsub, nboxW, NCbox;
   int relu, tmem_cols, bo_mode;
   int tiles_m, total_work, dbuf;   // persistent schedule: work item w -> (tile = w % tiles_m, n-slice = w / tiles_m)
@@ -334,9 +335,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           } else if (no_mma && lane == 0) {
             mbar_arrive(b_empty_bar);
           }
-          // next group's first tap: TPS==3 -> one image row down; TPS==1 -> next tap of the 3x3 stencil
-          if (TPS == 3) sh8 += wp8;
-          else if (p.ntaps == 9) { if (++kx == 3) { kx = 0; sh8 += wp8 - 16; } else sh8 += 8; }
+          // next group's first tap: TPS>1 -> a group is one stencil row, go one image row down; TPS==1 -> next tap
+          if (TPS > 1) sh8 += wp8;
+          else if (p.ntaps > 1) { if (++kx == (uint32_t)p.tapw) { kx = 0; sh8 += wp8 - 8u * (p.tapw - 1); } else sh8 += 8; }
           __syncwarp();
         }
         if (no_mma) { if (lane == 0) mbar_arrive(bar_a_empty + 8 * ra.idx); }
@@ -518,6 +519,7 @@ static TcKernelFn tc_kernel_for(int MT, int NC, int TPS) {
   TCK(1, 48, 1) TCK(1, 48, 3) TCK(2, 48, 1) TCK(2, 48, 3)
   TCK(1, 64, 1) TCK(1, 64, 3) TCK(2, 64, 1) TCK(2, 64, 3)
   TCK(1, 96, 1) TCK(1, 96, 3) TCK(1, 128, 1) TCK(1, 128, 3)
+  TCK(1, 16, 2) TCK(1, 32, 2) TCK(2, 32, 2) TCK(1, 48, 2) TCK(2, 48, 2) TCK(1, 64, 2) TCK(2, 64, 2) TCK(1, 96, 2) TCK(1, 128, 2)
 #undef TCK
   return nullptr;
 }
@@ -569,9 +571,12 @@ static CUresult encode_2d(CUtensorMap* tm, const void* gptr, uint64_t dim0, uint
 cudaError_t tc_conv_plan_create(TcConvPlan** out, const float* in, float* outp, const float* res, const float* wtc,
                                 const float* bias, int Cin, int Cout, int ks, int relu, int H, int W, int max_img) {
   if (env_int("PE_TC_DISABLE", 0)) return cudaErrorNotSupported;
-  if ((ks != 1 && ks != 3) || Cin % 16 || Cout % 16 || Cout > 512) return cudaErrorNotSupported;
+  // ks = 3: 3x3 pad 1;  ks = 1: 1x1;  ks = 2: 2x2 stencil with taps at (+0,+1) rows/cols (no pad) -- the form a
+  // stride-2 3x3 convolution takes over the space-to-depth repack of its input (kernels_simt.cu s2d_kernel)
+  if ((ks != 1 && ks != 2 && ks != 3) || Cin % 16 || Cout % 16 || Cout > 512) return cudaErrorNotSupported;
   const int Hp = H + 2, Wp = W + 2, ntaps = ks * ks, nchunk = Cin / 16;
   const int halo = ks == 3 ? Wp + 1 : 0;
+  const int halo_after = ks == 1 ? 0 : Wp + 1;
   const long long Mmax = (long long)max_img * Hp * Wp;
   if (Mmax + 1024 >= (1LL << 31)) return cudaErrorNotSupported;   // TMA row coordinates are int32
   const size_t smem_cap = 200 * 1024 - 32 * 1024;   // rings; 32 KB more for the epilogue store staging
@@ -592,7 +597,7 @@ cudaError_t tc_conv_plan_create(TcConvPlan** out, const float* in, float* outp, 
     if (NC % 16 || NC > 256) continue;
     if (force_ns && ns != force_ns) continue;
     for (int MT = 4; MT >= 1; --MT) {
-     for (int tps = (ntaps == 9 ? 3 : 1); tps >= 1; tps -= 2) {
+     for (int tps = ks; tps >= 1; tps -= (ks > 1 ? ks - 1 : 1)) {
       if (!tc_kernel_for(MT, NC, tps)) continue;
       if (force_mt && MT != force_mt) continue;
       TcParams p{};
@@ -602,7 +607,8 @@ cudaError_t tc_conv_plan_create(TcConvPlan** out, const float* in, float* outp, 
       const int max_steps = env_int("PE_TC_MAXSTEPS", 18);
       p.CPD = std::max(1, max_steps / (2 * ntaps));
       if (p.CPD > nchunk) p.CPD = nchunk;
-      const int R = 128 * MT + 2 * halo;
+      p.tapw = ks;
+      const int R = 128 * MT + halo + halo_after;
       p.nbA = (R + 255) / 256;
       p.Rpad = ((R + 8 * p.nbA - 1) / (8 * p.nbA)) * (8 * p.nbA);
       p.RB = p.Rpad / p.nbA;

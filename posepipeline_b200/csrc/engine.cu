@@ -255,6 +255,7 @@ struct pe_model {
   std::vector<float*> slots;
   std::vector<TcConvPlan*> tc;   // per op, or nullptr
   float* d_w = nullptr;
+  float* d_s2d = nullptr;        // space-to-depth scratch for stride-2 convolutions on the tensor-core path
   float* d_lut = nullptr;
   int* d_perm = nullptr;
   uint8_t* d_crops = nullptr;
@@ -295,7 +296,7 @@ extern "C" int pe_model_destroy(pe_model* m) {
   cudaStreamSynchronize(m->e->stream);
   for (auto* p : m->tc) if (p) tc_conv_plan_destroy(p);
   for (auto* p : m->slots) if (p) cudaFree(p);
-  cudaFree(m->d_w); cudaFree(m->d_lut); cudaFree(m->d_perm); cudaFree(m->d_crops); cudaFree(m->d_minv);
+  cudaFree(m->d_w); cudaFree(m->d_s2d); cudaFree(m->d_lut); cudaFree(m->d_perm); cudaFree(m->d_crops); cudaFree(m->d_minv);
   cudaFree(m->d_fidx); cudaFree(m->d_cs); cudaFree(m->d_hm); cudaFree(m->d_out);
   cudaFreeHost(m->h_minv); cudaFreeHost(m->h_fidx); cudaFreeHost(m->h_cs); cudaFreeHost(m->h_out);
   for (auto& p : m->ev_conv) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
@@ -353,14 +354,26 @@ extern "C" int pe_model_create(pe_engine* e, const pe_model_desc* desc, const pe
   // tensor-core plans for eligible convolutions
   m->tc.assign(desc->n_ops, nullptr);
   if (desc->use_tensor_cores) {
+    size_t s2d_floats = 0;
     for (int i = 0; i < desc->n_ops; ++i) {
       const pe_op_desc& op = m->ops[i];
-      if (op.kind != PE_OP_CONV || op.stride != 1 || op.wtc_off < 0) continue;
+      if (op.kind == PE_OP_CONV && op.stride == 2 && op.ksize == 3 && op.wtc_off >= 0) {
+        const pe_tensor_desc& to = m->tensors[op.out];
+        s2d_floats = std::max(s2d_floats, (size_t)(to.H + 2) * (to.W + 2) * 8 * op.cin * maximg);
+      }
+    }
+    if (s2d_floats) CUM(cudaMalloc(&m->d_s2d, s2d_floats * sizeof(float)));
+    for (int i = 0; i < desc->n_ops; ++i) {
+      const pe_op_desc& op = m->ops[i];
+      if (op.kind != PE_OP_CONV || op.wtc_off < 0) continue;
+      if (op.stride == 2 && op.ksize != 3) continue;
       const pe_tensor_desc& to = m->tensors[op.out];
       TcConvPlan* plan = nullptr;
-      cudaError_t ce = tc_conv_plan_create(&plan, act_ptr(m, op.in[0]), act_ptr(m, op.out),
+      const bool s2 = op.stride == 2;
+      cudaError_t ce = tc_conv_plan_create(&plan, s2 ? m->d_s2d : act_ptr(m, op.in[0]), act_ptr(m, op.out),
                                            op.residual >= 0 ? act_ptr(m, op.residual) : nullptr, m->d_w + op.wtc_off,
-                                           m->d_w + op.b_off, op.cin, op.cout, op.ksize, op.relu, to.H, to.W, maximg);
+                                           m->d_w + op.b_off, s2 ? 4 * op.cin : op.cin, op.cout, s2 ? 2 : op.ksize, op.relu,
+                                           to.H, to.W, maximg);
       if (ce == cudaSuccess) m->tc[i] = plan;
       else if (ce != cudaErrorNotSupported) {
         int rc = fail(PE_ERR_CUDA, "tensor-core plan for op %d failed: %s", i, cudaGetErrorString(ce));
@@ -404,6 +417,7 @@ static int forward(pe_model* m, int ncrop, int nimg) {
       case PE_OP_CONV: {
         const pe_tensor_desc& ti = m->tensors[op.in[0]];
         if (m->tc[i]) {
+          if (op.stride == 2) { launch_s2d(act_ptr(m, op.in[0]), op.cin, ti.H, ti.W, nimg, m->d_s2d, to.H, to.W, st); ++m->launches; }
           cudaError_t ce = tc_conv_launch(m->tc[i], nimg, st);
           if (ce != cudaSuccess) return fail(PE_ERR_CUDA, "tensor-core conv op %zu: %s", i, cudaGetErrorString(ce));
         } else {
@@ -632,19 +646,24 @@ extern "C" int pe_model_profile_read(pe_model* m, double* conv_ms, double* other
 // ------------------------------------------------------------------------------------------ single-layer parity hook
 extern "C" int pe_conv_test(pe_engine* e, const float* in_nchw, int32_t nimg, int32_t Cin, int32_t H, int32_t W,
                             const float* w_simt, const float* w_tc, const float* bias, const float* res_nchw, int32_t Cout,
-                            int32_t ks, int32_t relu, int32_t use_tc, float* out_nchw) {
+                            int32_t ks, int32_t stride, int32_t relu, int32_t use_tc, float* out_nchw) {
   if (!e || !in_nchw || !w_simt || !bias || !out_nchw || nimg <= 0) return fail(PE_ERR_INVALID, "bad argument to pe_conv_test");
   if (Cin % 16 || Cout % 16) return fail(PE_ERR_INVALID, "pe_conv_test needs channel counts that are multiples of 16");
   CU(cudaSetDevice(e->device));
   cudaStream_t st = e->stream;
+  if (stride != 1 && !(stride == 2 && ks == 3 && H % 2 == 0 && W % 2 == 0)) return fail(PE_ERR_INVALID, "pe_conv_test: stride 2 needs a 3x3 kernel and even H, W");
+  const int Hi = H, Wi = W;                       // input dims; H, W below are the OUTPUT dims
+  H = H / stride; W = W / stride;
+  const size_t rows_in = (size_t)nimg * (Hi + 2) * (Wi + 2);
   const size_t rows = (size_t)nimg * (H + 2) * (W + 2);
   const size_t taps = (size_t)ks * ks;
-  float *d_in = nullptr, *d_out = nullptr, *d_res = nullptr, *d_dense = nullptr, *d_w = nullptr, *d_wtc = nullptr, *d_b = nullptr;
+  float *d_in = nullptr, *d_out = nullptr, *d_res = nullptr, *d_dense = nullptr, *d_w = nullptr, *d_wtc = nullptr, *d_b = nullptr, *d_s = nullptr;
   int rc = PE_OK;
   TcConvPlan* plan = nullptr;
-  const size_t dense_in = (size_t)nimg * Cin * H * W, dense_out = (size_t)nimg * Cout * H * W;
+  const size_t dense_in = (size_t)nimg * Cin * Hi * Wi, dense_out = (size_t)nimg * Cout * H * W;
+  const size_t wtc_floats = (stride == 2 ? (size_t)4 * 4 * Cin : taps * Cin) * Cout * 2;
 #define CT(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { rc = fail(PE_ERR_CUDA, "%s: %s", #x, cudaGetErrorString(_e)); goto done; } } while (0)
-  CT(cudaMalloc(&d_in, rows * 2 * Cin * sizeof(float)));
+  CT(cudaMalloc(&d_in, rows_in * 2 * Cin * sizeof(float)));
   CT(cudaMalloc(&d_out, rows * 2 * Cout * sizeof(float)));
   CT(cudaMalloc(&d_dense, std::max(dense_in, dense_out) * sizeof(float)));
   CT(cudaMalloc(&d_w, taps * Cin * Cout * sizeof(float)));
@@ -658,16 +677,21 @@ extern "C" int pe_conv_test(pe_engine* e, const float* in_nchw, int32_t nimg, in
     launch_chw_to_ps(d_dense, Cout, H, W, nimg, d_res, st);
   }
   CT(cudaMemcpyAsync(d_dense, in_nchw, dense_in * sizeof(float), cudaMemcpyHostToDevice, st));
-  launch_chw_to_ps(d_dense, Cin, H, W, nimg, d_in, st);
+  launch_chw_to_ps(d_dense, Cin, Hi, Wi, nimg, d_in, st);
   if (use_tc) {
     if (!w_tc) { rc = fail(PE_ERR_INVALID, "w_tc is NULL"); goto done; }
-    CT(cudaMalloc(&d_wtc, taps * Cin * Cout * 2 * sizeof(float)));
-    CT(cudaMemcpyAsync(d_wtc, w_tc, taps * Cin * Cout * 2 * sizeof(float), cudaMemcpyHostToDevice, st));
-    cudaError_t ce = tc_conv_plan_create(&plan, d_in, d_out, d_res, d_wtc, d_b, Cin, Cout, ks, relu, H, W, nimg);
+    CT(cudaMalloc(&d_wtc, wtc_floats * sizeof(float)));
+    CT(cudaMemcpyAsync(d_wtc, w_tc, wtc_floats * sizeof(float), cudaMemcpyHostToDevice, st));
+    if (stride == 2) {
+      CT(cudaMalloc(&d_s, rows * 8 * Cin * sizeof(float)));
+      launch_s2d(d_in, Cin, Hi, Wi, nimg, d_s, H, W, st);
+    }
+    cudaError_t ce = tc_conv_plan_create(&plan, stride == 2 ? d_s : d_in, d_out, d_res, d_wtc, d_b, stride == 2 ? 4 * Cin : Cin, Cout,
+                                         stride == 2 ? 2 : ks, relu, H, W, nimg);
     if (ce != cudaSuccess) { rc = fail(PE_ERR_CUDA, "tc_conv_plan_create: %s", cudaGetErrorString(ce)); goto done; }
     CT(tc_conv_launch(plan, nimg, st));
   } else {
-    launch_conv_simt(d_in, d_out, d_res, d_w, d_b, Cin, Cout, ks, 1, relu, H, W, H, W, nimg, st);
+    launch_conv_simt(d_in, d_out, d_res, d_w, d_b, Cin, Cout, ks, stride, relu, Hi, Wi, H, W, nimg, st);
   }
   CT(cudaGetLastError());
   {
@@ -693,7 +717,7 @@ extern "C" int pe_conv_test(pe_engine* e, const float* in_nchw, int32_t nimg, in
 done:
   if (plan) tc_conv_plan_destroy(plan);
   cudaStreamSynchronize(st);
-  cudaFree(d_in); cudaFree(d_out); cudaFree(d_res); cudaFree(d_dense); cudaFree(d_w); cudaFree(d_wtc); cudaFree(d_b);
+  cudaFree(d_in); cudaFree(d_out); cudaFree(d_res); cudaFree(d_dense); cudaFree(d_w); cudaFree(d_wtc); cudaFree(d_b); cudaFree(d_s);
   return rc;
 }
 

@@ -19,6 +19,7 @@ void launch_head(const float* in, int Cin, int H, int W, int nimg, const float* 
                  cudaStream_t st);
 void launch_ps_to_chw(const float* in, int C, int H, int W, int img, float* out, cudaStream_t st);
 
+void launch_s2d(const float* in, int C, int Hin, int Win, int nimg, float* out, int Hout, int Wout, cudaStream_t st);
 void launch_chw_to_ps(const float* in, int C, int H, int W, int nimg, float* out, cudaStream_t st);
 
 void upload_gauss_kernel(const float* taps, int k);

@@ -440,3 +440,41 @@ void launch_chw_to_ps(const float* in, int C, int H, int W, int nimg, float* out
   long long total = (long long)nimg * (H + 2) * (W + 2) * C;
   chw_to_ps_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, C, H, W, nimg, out);
 }
+
+// =============================================================================================
+// Space-to-depth repack for stride-2 3x3 convolutions (HRNet transitions / fuse downsample paths):
+//   S[a'][b'][(py,px,c)] = in_padded[2(a'-1)+py][2(b'-1)+px][c]   on the OUTPUT's padded grid,
+// so that  out[oy][ox] = sum_{dy,dx in {0,1}} S[oy+1+dy][ox+1+dx] . W'[dy][dx]  with
+// W'[dy][dx][(py,px,c)] = w[2dy+py][2dx+px][c] (zero when the tap index exceeds 2): a 2x2, stride-1, tap-shifted
+// GEMM over 4*C channels that runs on the tensor-core kernel.  Pure data movement: hi/lo pairs are copied.
+// =============================================================================================
+__global__ void __launch_bounds__(256) s2d_kernel(const float* __restrict__ in, int C, int Hin, int Win, int nimg,
+                                                  float* __restrict__ out, int Hout, int Wout) {
+  const int C4 = 4 * C, g4 = C4 >> 2;
+  const int Hp = Hout + 2, Wp = Wout + 2, HpI = Hin + 2, WpI = Win + 2;
+  const long long total = (long long)nimg * Hp * Wp * g4;
+  const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (t >= total) return;
+  const int ce = (int)(t % g4) * 4;            // channel of the 4C-channel tensor
+  const long long m = t / g4;
+  const int img = (int)(m / (Hp * Wp));
+  const int r = (int)(m % (Hp * Wp));
+  const int ap = r / Wp, bp = r % Wp;
+  const int par = ce / C, c = ce % C;
+  const int py = par >> 1, px = par & 1;
+  const int sy = 2 * (ap - 1) + py, sx = 2 * (bp - 1) + px;
+  float4 hi = make_float4(0.f, 0.f, 0.f, 0.f), lo = hi;
+  if (ap >= 1 && bp >= 1 && sy < HpI && sx < WpI) {
+    const float* src = in + (((long long)img * HpI + sy) * WpI + sx) * (2 * C) + ps_chan_off(c);
+    hi = *reinterpret_cast<const float4*>(src);
+    lo = *reinterpret_cast<const float4*>(src + 16);
+  }
+  float* dst = out + m * (2 * C4) + ps_chan_off(ce);
+  *reinterpret_cast<float4*>(dst) = hi;
+  *reinterpret_cast<float4*>(dst + 16) = lo;
+}
+
+void launch_s2d(const float* in, int C, int Hin, int Win, int nimg, float* out, int Hout, int Wout, cudaStream_t st) {
+  long long total = (long long)nimg * (Hout + 2) * (Wout + 2) * C;
+  s2d_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, C, Hin, Win, nimg, out, Hout, Wout);
+}

@@ -77,6 +77,21 @@ class WeightBlob:
         return np.concatenate(self.parts) if self.parts else np.zeros(0, np.float32)
 
 
+def space_to_depth_weights(w: np.ndarray) -> np.ndarray:
+    """3x3 stride-2 weights (Cout,Cin,3,3) -> the equivalent 2x2 stride-1 weights (Cout,4*Cin,2,2) over the
+    space-to-depth repack of the input (csrc/kernels_simt.cu s2d_kernel): W'[o][(py,px,c)][dy][dx] = w[o][c][2dy+py][2dx+px]."""
+    cout, cin = w.shape[:2]
+    out = np.zeros((cout, 4, cin, 2, 2), w.dtype)
+    for py in range(2):
+        for px in range(2):
+            for dy in range(2):
+                for dx in range(2):
+                    ky, kx = 2 * dy + py, 2 * dx + px
+                    if ky < 3 and kx < 3:
+                        out[:, py * 2 + px, :, dy, dx] = w[:, :, ky, kx]
+    return out.reshape(cout, 4 * cin, 2, 2)
+
+
 def pack_tc_weights(w: np.ndarray) -> np.ndarray:
     """(Cout,Cin,k,k) folded fp32 -> tensor-core operand [tap][Cin/16][Cout][hi16|lo16] (see csrc/conv_tc.cu)."""
     cout, cin, k, _ = w.shape
@@ -127,18 +142,18 @@ class PoseEngine:
 
 
 def conv_test(engine: PoseEngine, x: np.ndarray, w: np.ndarray, bias: np.ndarray, res: Optional[np.ndarray] = None,
-              relu: bool = True, use_tc: bool = True) -> np.ndarray:
-    """One stride-1 conv layer through the library (parity hook): x (n,Cin,H,W), w (Cout,Cin,k,k) folded -> (n,Cout,H,W)."""
+              relu: bool = True, use_tc: bool = True, stride: int = 1) -> np.ndarray:
+    """One conv layer through the library (parity hook): x (n,Cin,H,W), w (Cout,Cin,k,k) folded -> (n,Cout,H/s,W/s)."""
     x = np.ascontiguousarray(x, np.float32)
     n, cin, H, W = x.shape
     cout, _, k, _ = w.shape
     ws = np.ascontiguousarray(w.transpose(2, 3, 1, 0).reshape(k * k, cin, cout), np.float32)
-    wt = np.ascontiguousarray(pack_tc_weights(w), np.float32)
+    wt = np.ascontiguousarray(pack_tc_weights(space_to_depth_weights(w) if stride == 2 else w), np.float32)
     b = np.ascontiguousarray(bias, np.float32)
     r = np.ascontiguousarray(res, np.float32) if res is not None else None
-    out = np.empty((n, cout, H, W), np.float32)
+    out = np.empty((n, cout, H // stride, W // stride), np.float32)
     check(engine.lib.pe_conv_test(engine.h, ptr(x), n, cin, H, W, ptr(ws), ptr(wt), ptr(b), ptr(r) if r is not None else None,
-                                  cout, k, int(relu), int(use_tc), ptr(out)))
+                                  cout, k, stride, int(relu), int(use_tc), ptr(out)))
     return out
 
 
@@ -196,8 +211,11 @@ class TopDownModel:
                 else:
                     o.w_off = blob.add(wf.transpose(2, 3, 1, 0).reshape(k * k, op.cin, op.cout))   # [tap][Cin][Cout]
                 o.b_off = blob.add(bf)
-                if use_tensor_cores and op.kind == OP_CONV and op.stride == 1 and op.cin % 16 == 0 and op.cout % 16 == 0:
-                    o.wtc_off = blob.add(pack_tc_weights(wf))
+                if use_tensor_cores and op.kind == OP_CONV and op.cin % 16 == 0 and op.cout % 16 == 0:
+                    if op.stride == 1:
+                        o.wtc_off = blob.add(pack_tc_weights(wf))
+                    elif op.stride == 2 and k == 3:
+                        o.wtc_off = blob.add(pack_tc_weights(space_to_depth_weights(wf)))
         if unique_slots:
             slot_of = list(range(len(prog.tensors)))
             slot_elems = [(t.H + 2) * (t.W + 2) * t.C for t in prog.tensors]

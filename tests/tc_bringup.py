@@ -19,6 +19,11 @@ CASES = [  # (Cin, Cout, ks, H, W, nimg, res, relu)
     (256, 64, 1, 96, 72, 2, False, True),
     (384, 48, 1, 12, 9, 4, False, False),
     (64, 64, 3, 96, 72, 2, False, True),
+    (16, 16, 3, 8, 8, 1, False, False, 2),        # stride 2 (space-to-depth + 2x2 taps)
+    (48, 96, 3, 96, 72, 2, False, True, 2),
+    (64, 64, 3, 192, 144, 1, False, True, 2),
+    (192, 384, 3, 24, 18, 3, False, False, 2),
+    (256, 96, 3, 96, 72, 2, False, True, 2),
 ]
 
 
@@ -26,13 +31,14 @@ def main():
     idx = [int(a) for a in sys.argv[1:]] or range(len(CASES))
     eng = E.PoseEngine(0)
     for i in idx:
-        cin, cout, ks, H, W, n, res, relu = CASES[i]
+        cin, cout, ks, H, W, n, res, relu = CASES[i][:8]
+        stride = CASES[i][8] if len(CASES[i]) > 8 else 1
         rng = np.random.default_rng(i)
         x = rng.standard_normal((n, cin, H, W)).astype(np.float32)
         w = (rng.standard_normal((cout, cin, ks, ks)) / np.sqrt(cin * ks * ks)).astype(np.float32)
         b = rng.standard_normal(cout).astype(np.float32)
-        r = rng.standard_normal((n, cout, H, W)).astype(np.float32) if res else None
-        ref = torch.nn.functional.conv2d(torch.from_numpy(x).double(), torch.from_numpy(w).double(), torch.from_numpy(b).double(), padding=ks // 2)
+        r = rng.standard_normal((n, cout, H // stride, W // stride)).astype(np.float32) if res else None
+        ref = torch.nn.functional.conv2d(torch.from_numpy(x).double(), torch.from_numpy(w).double(), torch.from_numpy(b).double(), padding=ks // 2, stride=stride)
         if res:
             ref = ref + torch.from_numpy(r).double()
         if relu:
@@ -41,7 +47,7 @@ def main():
         out = {}
         for tc in (0, 1):
             t0 = time.time()
-            got = E.conv_test(eng, x, w, b, r, relu, bool(tc))
+            got = E.conv_test(eng, x, w, b, r, relu, bool(tc), stride)
             err = np.abs(got - ref).max() / np.abs(ref).max()
             out[tc] = err
             print(f"case {i} {CASES[i]} {'TC  ' if tc else 'SIMT'} max rel err {err:.3e}  ({time.time()-t0:.2f}s)", flush=True)
