@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q -s 2>&1 | grep -E "worst layers|keypoint \|dx\||passed|failed|Error|error" | cut -c1-700 > gpurun_out/pytest_gpu.log
+timeout 1200 python -m pytest tests -m gpu -q -s 2>&1 | grep -E "worst layers|keypoint \|dx\||passed|failed|Error|error|assert" | cut -c1-700 > gpurun_out/pytest_gpu.log
 cat gpurun_out/pytest_gpu.log
 timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_cur.json 2> gpurun_out/bench_cur.err; python -c "
 import json; d=json.load(open('gpurun_out/bench_cur.json')); print({k:d[k] for k in ('value','ms_per_step','gpu_launches')}, d['e2e']['value'], d['roofline']['achieved'], d['clocks'])"; tail -3 gpurun_out/bench_cur.err
