@@ -38,6 +38,7 @@ struct TcParams {
   int nsub, Nsub, nboxW, NCbox;
   int relu, tmem_cols, bo_mode;
   int tiles_m, total_work, dbuf;   // persistent schedule: work item w -> (tile = w % tiles_m, n-slice = w / tiles_m)
+  long long* prof;                 // optional per-CTA cycle counters of the MMA warp (PE_TC_PROF=1): [wait_b, issue, wait_a, wait_main, total, stages]
   int dbg;                         // PE_TC_DBG experiment bits: 1 = issue no MMAs, 2 = no epilogue global traffic
   int CPD;                         // chunks per drain group (accumulation length bound, see kernel comment)
 };
@@ -193,6 +194,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                const __grid_constant__ CUtensorMap tmO, const TcParams p) {
   constexpr int NC = NG * 16 / MT;                 // output channels per CTA
   constexpr uint32_t GC = NG * 16;                 // columns of one accumulator set (= MT*NC)
+  constexpr uint32_t NMAIN = (NG <= 6) ? 3u : 2u;   // `main` accumulator buffers in flight (TMEM: (NMAIN+2)*GC <= 512 columns)
   constexpr uint32_t b_bytes = (uint32_t)TPS * NC * 128u;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -204,9 +206,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t sBar = sStage + 4u * 2u * 4096u;  // 8-byte barriers
   const uint32_t bar_a_full = sBar, bar_a_empty = sBar + 8 * p.SA;
   const uint32_t bar_b_full = bar_a_empty + 8 * p.SA, bar_b_empty = bar_b_full + 8 * p.SB;
-  const uint32_t bar_main_full = bar_b_empty + 8 * p.SB;    // [2]
-  const uint32_t bar_main_empty = bar_main_full + 16;       // [2]
-  const uint32_t bar_corr_empty = bar_main_empty + 16;      // [2]
+  const uint32_t bar_main_full = bar_b_empty + 8 * p.SB;    // [NMAIN] (room for 4)
+  const uint32_t bar_main_empty = bar_main_full + 32;       // [NMAIN]
+  const uint32_t bar_corr_empty = bar_main_empty + 32;      // [2]
   const uint32_t s_tmem = bar_corr_empty + 16;
   uint8_t* gen = smem_raw + (base - raw);
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen + (s_tmem - base));
@@ -216,9 +218,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.SA; ++i) { mbar_init(bar_a_full + 8 * i, 1); mbar_init(bar_a_empty + 8 * i, 1); }
     for (int i = 0; i < p.SB; ++i) { mbar_init(bar_b_full + 8 * i, 1); mbar_init(bar_b_empty + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(bar_main_full + 8 * i, 1); mbar_init(bar_main_empty + 8 * i, 4); mbar_init(bar_corr_empty + 8 * i, 4);
-    }
+    for (int i = 0; i < (int)NMAIN; ++i) { mbar_init(bar_main_full + 8 * i, 1); mbar_init(bar_main_empty + 8 * i, 4); }
+    for (int i = 0; i < 2; ++i) mbar_init(bar_corr_empty + 8 * i, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -288,26 +289,36 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     Ring ra, rb;
     uint32_t dg = 0, dgp = 0, tl = 0;       // drain-group buffer / phase, tile counter
     bool b_ready = false, a_ready = false, m_ready = false;   // results of early polls (latency hidden behind MMA issue)
+    long long c_wb = 0, c_is = 0, c_wa = 0, c_wm = 0, c_st = 0, c_wc = 0;
+    const bool prof = p.prof != nullptr;
+    const long long c_t0 = prof ? clock64() : 0;
     for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++tl) {
       const uint32_t cbuf = tl & 1u;
-      mbar_wait(bar_corr_empty + 8 * cbuf, ((tl >> 1) & 1u) ^ 1u);     // epilogue has read this corr buffer
+      { const long long cc = prof ? clock64() : 0;
+        mbar_wait(bar_corr_empty + 8 * cbuf, ((tl >> 1) & 1u) ^ 1u);   // epilogue has read this corr buffer
+        if (prof) c_wc += clock64() - cc; }
       tc_fence_after();
-      const uint32_t d_corr = tmem_base + (2u + cbuf) * GC;
+      const uint32_t d_corr = tmem_base + (NMAIN + cbuf) * GC;
       uint32_t d_main = tmem_base;
       int jj = 0;
       for (int j = 0; j < p.nchunk; ++j) {
+        long long c0 = prof ? clock64() : 0;
         if (jj == 0) {
           if (!m_ready) mbar_wait(bar_main_empty + 8 * dg, dgp ^ 1u); // epilogue has drained this main buffer
           d_main = tmem_base + dg * GC;
         }
+        if (prof) { const long long c1 = clock64(); c_wm += c1 - c0; c0 = c1; }
         if (!a_ready) mbar_wait(bar_a_full + 8 * ra.idx, ra.phase);
         tc_fence_after();
+        if (prof) c_wa += clock64() - c0;
         const uint32_t a_slot = a_lo0 + ra.idx * a_step;
         uint32_t sh8 = 0;                   // window row shift of the group's first tap, in 16-byte units
         uint32_t kx = 0;
         for (int g = 0; g < ngroups; ++g) {
+          long long c2 = prof ? clock64() : 0;
           if (!b_ready) mbar_wait(bar_b_full + 8 * rb.idx, rb.phase);
           tc_fence_after();
+          if (prof) { const long long c3 = clock64(); c_wb += c3 - c2; c2 = c3; ++c_st; }
           const uint32_t b_slot = b_lo0 + rb.idx * (b_bytes >> 4);
           const uint32_t b_empty_bar = bar_b_empty + 8 * rb.idx;
           rb.advance(p.SB);
@@ -335,6 +346,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           } else if (no_mma && lane == 0) {
             mbar_arrive(b_empty_bar);
           }
+          if (prof) c_is += clock64() - c2;
           // next group's first tap: TPS>1 -> a group is one stencil row, go one image row down; TPS==1 -> next tap
           if (TPS > 1) sh8 += wp8;
           else if (p.ntaps > 1) { if (++kx == (uint32_t)p.tapw) { kx = 0; sh8 += wp8 - 8u * (p.tapw - 1); } else sh8 += 8; }
@@ -348,11 +360,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (no_mma) { if (lane == 0) mbar_arrive(bar_main_full + 8 * dg); }
           else if (elect_one()) tc_commit(bar_main_full + 8 * dg);     // this drain group's partial sums are complete
           jj = 0;
-          if (++dg == 2) { dg = 0; dgp ^= 1u; }
+          if (++dg == NMAIN) { dg = 0; dgp ^= 1u; }
           m_ready = mbar_try(bar_main_empty + 8 * dg, dgp ^ 1u);
         }
         __syncwarp();
       }
+    }
+    if (prof && lane == 0) {
+      long long* o = p.prof + (size_t)blockIdx.x * 8;
+      o[0] = c_wb; o[1] = c_is; o[2] = c_wa; o[3] = c_wm; o[4] = clock64() - c_t0; o[5] = c_st; o[6] = c_wc;
     }
   } else {
     // ===================== epilogue (warps 2..5; TMEM lane quarter = warp % 4) =====================
@@ -370,6 +386,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const long long m0 = (long long)tile * 128 * MT;
       const int n0 = nsl * NC;
       float acc[NG][16];
+      if (p.res && !(p.dbg & 2)) {
+        // pull this tile's residual rows towards L2 while the first chunk's MMAs run
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+          const long long m = m0 + (g / gpm) * 128 + q * 32 + lane;
+          if (m < p.M) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.res + m * rowF + 2 * (n0 + (g % gpm) * 16)));
+        }
+      }
       for (int d = 0; d < ndrain; ++d) {
         mbar_wait_relaxed(bar_main_full + 8 * dg, dgp, (p.dbg >> 8) & 0xfff);
         tc_fence_after();
@@ -391,7 +415,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_main_empty + 8 * dg);
-        if (++dg == 2) { dg = 0; dgp ^= 1u; }
+        if (++dg == NMAIN) { dg = 0; dgp ^= 1u; }
         if (d == 0 && p.res && !(p.dbg & 2)) {
           // Residual add, folded into the accumulators NOW: the loads' HBM/L2 latency hides behind the MMAs of the
           // remaining channel chunks instead of sitting in the store phase (software-pipelined one group ahead).
@@ -434,7 +458,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int g = 0; g < NG; ++g) {
           uint32_t r[16];
-          tc_ld16(t_lane + (2u + cbuf) * GC + g * 16, r);
+          tc_ld16(t_lane + (NMAIN + cbuf) * GC + g * 16, r);
 #pragma unroll
           for (int i = 0; i < 16; ++i) acc[g][i] += __uint_as_float(r[i]);
         }
@@ -620,7 +644,7 @@ cudaError_t tc_conv_plan_create(TcConvPlan** out, const float* in, float* outp, 
       if (p.SA * a_bytes + SB * b_bytes + 4096 > smem_cap) continue;
       p.SB = SB;
       int cols = 32;
-      while (cols < 4 * MT * NC) cols <<= 1;
+      while (cols < ((MT * NC / 16 <= 6) ? 5 : 4) * MT * NC) cols <<= 1;
       p.tmem_cols = cols;
       p.tiles_m = (int)((Mmax + 128LL * MT - 1) / (128LL * MT));
       p.total_work = p.tiles_m * ns;
@@ -647,6 +671,8 @@ cudaError_t tc_conv_plan_create(TcConvPlan** out, const float* in, float* outp, 
   pl->p.H = H; pl->p.W = W; pl->p.Hp = Hp; pl->p.Wp = Wp; pl->p.relu = relu;
   pl->p.bo_mode = env_int("PE_TC_BO_MODE", 1);
   pl->p.dbg = env_int("PE_TC_DBG", 0);
+  pl->p.prof = nullptr;
+  if (env_int("PE_TC_PROF", 0)) { cudaMalloc(&pl->p.prof, 148 * 8 * sizeof(long long)); cudaMemset(pl->p.prof, 0, 148 * 8 * sizeof(long long)); }
   pl->rows_per_img = Hp * Wp;
   pl->smem = bsmem;
   pl->ns = bns;
@@ -672,7 +698,7 @@ cudaError_t tc_conv_plan_create(TcConvPlan** out, const float* in, float* outp, 
   return cudaSuccess;
 }
 
-void tc_conv_plan_destroy(TcConvPlan* plan) { delete plan; }
+void tc_conv_plan_destroy(TcConvPlan* plan) { if (plan && plan->p.prof) cudaFree(plan->p.prof); delete plan; }
 
 cudaError_t tc_conv_launch(TcConvPlan* pl, int nimg, cudaStream_t st) {
   TcParams p = pl->p;
@@ -681,5 +707,14 @@ cudaError_t tc_conv_launch(TcConvPlan* pl, int nimg, cudaStream_t st) {
   p.total_work = p.tiles_m * pl->ns;
   const unsigned grid = (unsigned)(p.total_work < pl->num_sms ? p.total_work : pl->num_sms);
   pl->kernel<<<grid, 192, pl->smem, st>>>(pl->tmA, pl->tmW, pl->tmO, p);
+  if (p.prof) {
+    long long h[148 * 8];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, p.prof, sizeof h, cudaMemcpyDeviceToHost);
+    double a[7] = {0, 0, 0, 0, 0, 0, 0};
+    for (unsigned b = 0; b < grid; ++b) for (int k = 0; k < 7; ++k) a[k] += (double)h[b * 8 + k] / grid;
+    fprintf(stderr, "conv_tc prof (NC=%d MT=%d TPS=%d nchunk=%d ntaps=%d work=%d grid=%u): per-CTA cycles total %.0f | wait_b %.0f issue %.0f wait_a %.0f wait_main %.0f wait_corr %.0f res=%d | stages %.0f -> per stage: wait_b %.0f issue %.0f\n",
+            p.NC, p.MT, p.TPS, p.nchunk, p.ntaps, p.total_work, grid, a[4], a[0], a[1], a[2], a[3], a[6], p.res ? 1 : 0, a[5], a[0] / a[5], a[1] / a[5]);
+  }
   return cudaGetLastError();
 }
