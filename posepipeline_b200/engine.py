@@ -41,9 +41,81 @@ class TopDownSpec:
     checkpoint: Optional[str] = None               # path under MODEL_DATA_DIR (reference wrappers/mmpose.py:33-52)
 
 
+# Halpe-136 left/right pairs, derived from the `swap` fields of the reference's dataset_info
+# (3rdparty/mmpose/config/_base_/halpe.py, passed to the model at halpe/hrnet_w48_halpe_384x288_dark_plus.py:152)
+HALPE_FLIP_PAIRS = [[1, 2],
+                    [3, 4],
+                    [5, 6],
+                    [7, 8],
+                    [9, 10],
+                    [11, 12],
+                    [13, 14],
+                    [15, 16],
+                    [20, 21],
+                    [22, 23],
+                    [24, 25],
+                    [26, 42],
+                    [27, 41],
+                    [28, 40],
+                    [29, 39],
+                    [30, 38],
+                    [31, 37],
+                    [32, 36],
+                    [33, 35],
+                    [43, 52],
+                    [44, 51],
+                    [45, 50],
+                    [46, 49],
+                    [47, 48],
+                    [57, 61],
+                    [58, 60],
+                    [62, 71],
+                    [63, 70],
+                    [64, 69],
+                    [65, 68],
+                    [66, 73],
+                    [67, 72],
+                    [74, 80],
+                    [75, 79],
+                    [76, 78],
+                    [81, 85],
+                    [82, 84],
+                    [86, 90],
+                    [87, 89],
+                    [91, 93],
+                    [94, 115],
+                    [95, 116],
+                    [96, 117],
+                    [97, 118],
+                    [98, 119],
+                    [99, 120],
+                    [100, 121],
+                    [101, 122],
+                    [102, 123],
+                    [103, 124],
+                    [104, 125],
+                    [105, 126],
+                    [106, 127],
+                    [107, 128],
+                    [108, 129],
+                    [109, 130],
+                    [110, 131],
+                    [111, 132],
+                    [112, 133],
+                    [113, 134],
+                    [114, 135]]
+
+
 METHODS: Dict[str, TopDownSpec] = {
     # reference wrappers/mmpose.py:33-36
     "HRNet_W48_COCO": TopDownSpec(checkpoint="mmpose/checkpoints/hrnet_w48_coco_384x288_dark-e881a4b6_20210203.pth"),
+    # reference wrappers/mmpose.py:41-44; old-style config without dataset_info => mmpose falls back to the COCO-17 body
+    # pairs when flipping all 133 channels -- reproduced
+    "HRNet_W48_COCOWholeBody": TopDownSpec(num_joints=133,
+                                           checkpoint="mmpose/checkpoints/hrnet_w48_coco_wholebody_384x288_dark-f5726563_20200918.pth"),
+    # reference wrappers/mmpose.py:49-52 (PosePipe's production default, scripts/process_h36m.py:15)
+    "HRNet_W48_HALPE": TopDownSpec(num_joints=136, flip_pairs=[list(p) for p in HALPE_FLIP_PAIRS],
+                                   checkpoint="mmpose/checkpoints/hrnet_w48_halpe_384x288_dark_plus-d13c2588_20211021.pth"),
     # BASELINE config 1 (upstream hrnet_w32_coco_256x192.py; not configured in the reference)
     "HRNet_W32_COCO": TopDownSpec(variant="w32", image_size=(192, 256), heatmap_size=(48, 64), post_process="default",
                                   modulate_kernel=11, checkpoint="mmpose/checkpoints/hrnet_w32_coco_256x192-c78dce93_20200708.pth"),

@@ -41,7 +41,7 @@ mmpose_joint_dictionary = {
 
 # tags the reference accepts (:33-52) that this build does not implement yet (HRFormer / TCFormer are
 # different backbones and out of the hot-path scope)
-_REFERENCE_ONLY = {"HRFormer_COCO": 17, "HRNet_W48_COCOWholeBody": 133, "HRNet_TCFormer_COCOWholeBody": 133, "HRNet_W48_HALPE": 136}
+_REFERENCE_ONLY = {"HRFormer_COCO": 17, "HRNet_TCFormer_COCOWholeBody": 133}
 
 FRAME_BLOCK = int(os.environ.get("PE_FRAME_BLOCK", "32"))
 _models: Dict[str, "E.TopDownModel"] = {}
@@ -85,7 +85,7 @@ def mmpose_top_down_person(key, method='HRNet_W48_COCO'):
     from pose_pipeline import Video, PersonBbox      # the reference's own tables (pipeline.py:24, :648)
 
     if method in _REFERENCE_ONLY:
-        raise NotImplementedError(f"top-down method {method} is not built in this engine yet (HRNet_W48_COCO, HRNet_W32_COCO are)")
+        raise NotImplementedError(f"top-down method {method} is not built in this engine yet (HRNet_W48_COCO / _COCOWholeBody / _HALPE and HRNet_W32_COCO are)")
     if method not in E.METHODS:
         # the reference falls through its if/elif chain and dies on an unbound `pose_cfg`
         raise UnboundLocalError(f"cannot access local variable 'pose_cfg': unknown top-down method {method!r}")

@@ -52,14 +52,16 @@ def calibrate(variant, in_h, in_w, K, seed, cfg, n_crops=10, q=0.97):
     name = f"backbone.stage4.{nm - 1}.fuse_layers.0.1.1.bias"
     fuse_bias = sd[name] - thr.numpy()
     feat = F.relu(pre - thr[None, :, None, None])
-    rng = np.random.default_rng(seed + 17)
+    rng = np.random.default_rng(seed + K)
     hw = np.zeros((K, C), np.float32)
     for k in range(K):
         ch = rng.choice(C, 8, replace=False)
         hw[k, ch] = rng.uniform(0.5, 1.0, 8)
     hm = torch.einsum("kc,bchw->bkhw", torch.from_numpy(hw), feat)
-    mx = hm.flatten(2).max(dim=2).values.median(dim=0).values.numpy()
-    assert (mx > 0).all(), mx
+    per_crop = hm.flatten(2).max(dim=2).values
+    mx = per_crop.median(dim=0).values.numpy()
+    mx = np.where(mx > 0, mx, per_crop.max(dim=0).values.numpy())      # joints whose channels are silent in most crops
+    mx = np.where(mx > 0, mx, 1.0)
     hw = hw * (0.85 / mx)[:, None]
     hb = np.full((K,), 0.002, np.float32)
     return {"fuse_bias": fuse_bias.astype(np.float32), "head_weight": hw.reshape(K, C, 1, 1).astype(np.float32),
@@ -69,6 +71,8 @@ def calibrate(variant, in_h, in_w, K, seed, cfg, n_crops=10, q=0.97):
 if __name__ == "__main__":
     out = {}
     for variant, h, w, K, seed, cfg in [("w48", 384, 288, 17, 0, T.HRNET_W48_COCO),
+                                        ("w48", 384, 288, 133, 0, T.HRNET_W48_COCO),
+                                        ("w48", 384, 288, 136, 0, T.HRNET_W48_COCO),
                                         ("w32", 256, 192, 17, 0, T.HRNET_W32_COCO)]:
         r = calibrate(variant, h, w, K, seed, cfg)
         for k, v in r.items():

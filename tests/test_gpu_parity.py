@@ -255,3 +255,26 @@ def test_lifter_matches_oracle(eng):
         assert np.abs(got - ref).max() <= 1e-3, np.abs(got - ref).max()
         assert np.abs(got - ref).max() <= 5e-5 * np.abs(ref).max()
     lf.close()
+
+
+def test_topdown_halpe136_and_wholebody133(eng):
+    """§8(f) f3: same backbone, K=136 (Halpe flip pairs from the reference's dataset_info) / K=133 (COCO-17 pairs only, quirk Q3)."""
+    import dataclasses
+    frames = helpers.frames(3)
+    eng.stage_frames(frames)
+    bbs = synthetic_bboxes(3, 91)
+    fidx = np.array([0, 1, 2])
+    for method in ("HRNet_W48_HALPE", "HRNet_W48_COCOWholeBody"):
+        spec = E.METHODS[method]
+        m = E.TopDownModel(eng, helpers.state_dict(method), spec, max_crops=2, use_tensor_cores=USE_TC)
+        got = m.topdown(fidx, bbs)
+        cfg = dataclasses.replace(OT.HRNET_W48_COCO, num_joints=spec.num_joints, flip_pairs=[list(p) for p in spec.flip_pairs])
+        helpers.ORACLE_CFG[method] = cfg
+        ref32 = helpers.oracle_keypoints(method, frames, fidx, bbs, "float32")
+        ref64 = helpers.oracle_keypoints(method, frames, fidx, bbs, "float64")
+        assert got.shape == (3, spec.num_joints, 3)
+        cond = np.abs(ref32[..., :2] - ref64[..., :2]).max(-1)
+        good = cond <= 2e-4
+        d = np.abs(got[..., :2] - ref32[..., :2]).max(-1)
+        assert good.mean() > 0.7 and d[good].max() <= 1e-3, (method, d[good].max(), good.mean())
+        m.close()

@@ -72,7 +72,7 @@ def test_top_down_wrapper_reference_behaviour(tmp_path, monkeypatch):
         W.mmpose_top_down_person(key)
     assert set(os.listdir(tempfile.gettempdir())) == before
     with pytest.raises(NotImplementedError):
-        W.mmpose_top_down_person(key, "HRNet_W48_HALPE")
+        W.mmpose_top_down_person(key, "HRFormer_COCO")
     assert W.mmpose_joint_dictionary["MMPose"][0] == "Nose" and len(W.mmpose_joint_dictionary["MMPoseHalpe"]) == 26
 
 
