@@ -141,7 +141,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--max-crops", type=int, default=int(os.environ.get("PE_MAX_CROPS", "64")))
+    ap.add_argument("--max-crops", type=int, default=int(os.environ.get("PE_MAX_CROPS", "256")))
     ap.add_argument("--no-tc", action="store_true", help="fp32 SIMT convolutions only")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -236,7 +236,9 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": "crops/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 (tf32x3 split-precision tensor-core MMAs, fp32 accumulate)" if not args.no_tc else "f32",
+            "dtype": ("f32" if args.no_tc else
+                      ("f32 via fp16x2 split operands (3 kind::f16 MMAs per MAC, fp32 accumulate)" if model.lib.pe_precision_mode() == 1
+                       else "f32 via tf32x3 split operands (3 kind::tf32 MMAs per MAC, fp32 accumulate)")),
             "data": "synthetic 1080p frames + seeded synthetic weights (no checkpoints/videos offline)",
             "config": {"workload": "HRNet-W48 384x288 top-down, 256 synthetic crops per step per GPU (32 frames x 8 boxes), "
                                    "flip_test + DARK decode (BASELINE configs[1])",
@@ -252,7 +254,7 @@ def main():
                          "kernel": "convolution kernels (conv_tc / conv_simt), all launches of the timed region",
                          "algorithmic_flop_per_crop": FLOP_PER_CROP, "conv_ms_total": conv_ms, "other_ms_total": other_ms,
                          "conv_launches": int(conv_launches), "peak_source": peak_src,
-                         "note": "algorithmic FLOPs count each MAC once; the tf32x3 path executes 3 MMAs per MAC"},
+                         "note": "algorithmic FLOPs count each MAC once; the split-precision path executes 3 MMAs per MAC"},
         }
         if world == 1 and not args.no_cpu_baseline:
             ref = CpuReference()

@@ -78,6 +78,9 @@ typedef struct pe_model_desc {
 
 /* ---- library ---- */
 int pe_abi_version(void);
+/* activation / tensor-core operand format this library was built for: 0 = tf32x3 (8 B per element, hi/lo TF32 pairs),
+ * 1 = fp16x2 (4 B per element, h/l FP16 pairs).  Decides how the host packs the tensor-core weights. */
+int pe_precision_mode(void);
 const char* pe_last_error(void);
 int pe_device_count(int* count);
 

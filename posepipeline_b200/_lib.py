@@ -7,7 +7,8 @@ import os
 import re
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libposeengine.so")
+# PE_PRECISION=tf32 selects the wide-range TF32x3 build (libposeengine_tf32.so); default is the fp16x2 build
+LIB_PATH = os.path.join(_PKG, "libposeengine_tf32.so" if os.environ.get("PE_PRECISION", "fp16") == "tf32" else "libposeengine.so")
 HEADER_PATH = os.path.join(os.path.dirname(_PKG), "include", "poseengine.h")
 
 PE_OK, PE_ERR_INVALID, PE_ERR_CUDA, PE_ERR_STATE, PE_ERR_NOGPU = 0, -1, -2, -3, -4
@@ -62,6 +63,7 @@ def load():
     P = C.POINTER
     sig = {
         "pe_abi_version": (C.c_int, []),
+        "pe_precision_mode": (C.c_int, []),
         "pe_last_error": (C.c_char_p, []),
         "pe_device_count": (C.c_int, [P(C.c_int)]),
         "pe_engine_create": (C.c_int, [C.c_int, vp, P(vp)]),

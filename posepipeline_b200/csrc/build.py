@@ -9,12 +9,14 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
-OUT = os.path.join(PKG, "libposeengine.so")
 SOURCES = ["engine.cu", "kernels_simt.cu", "decode.cu", "lifter.cu", "conv_tc.cu"]
 HEADERS = ["kernels.h", "pe_common.cuh", os.path.join("..", "..", "include", "poseengine.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+# PE_PRECISION=tf32 builds the wide-range TF32x3 variant (8 B/element); default fp16x2 (4 B/element, half the MMAs)
+PRECISION = os.environ.get("PE_PRECISION", "fp16")
+OUT = os.path.join(PKG, "libposeengine.so" if PRECISION == "fp16" else "libposeengine_tf32.so")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
-         "-Xcompiler", "-fno-fast-math", "--fmad=true"]
+         "-Xcompiler", "-fno-fast-math", "--fmad=true", f"-DPE_FP16={1 if PRECISION == 'fp16' else 0}"]
 
 
 def _digest():
@@ -33,7 +35,7 @@ def build(force=False, verbose=False):
     objs = []
     procs = []
     for src in SOURCES:
-        obj = os.path.join(HERE, src.replace(".cu", ".o"))
+        obj = os.path.join(HERE, src.replace(".cu", f".{PRECISION}.o"))
         cmd = [NVCC, *FLAGS, "-c", os.path.join(HERE, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")

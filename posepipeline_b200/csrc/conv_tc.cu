@@ -26,10 +26,19 @@
 #include "kernels.h"
 #include "pe_common.cuh"
 
+// layout constants of this build (pe_common.cuh): bytes per 16-channel chunk row, 16-byte units per row, offset of the
+// lo / l half, MMA k-steps per chunk
+#define CHB PS_CHUNK_BYTES
+constexpr uint32_t ROW16 = CHB / 16;          // 8 (tf32) / 4 (fp16)
+constexpr uint32_t LO16 = CHB / 32;           // 16-byte units from hi to lo: 4 / 2
+constexpr int KSTEPS = PE_FP16 ? 1 : 2;       // MMA k-steps per chunk half: 16 x f16 = one K=16 MMA; 16 x tf32 = two K=8 MMAs
+
 struct TcParams {
   float* out;
   const float* res;
   const float* bias;
+  const float* scale;   // [scale | inv scale]: per-output-channel powers of two un-/re-scaling the packed weights (engine.pack_tc_weights)
+  int scale_pad;        // floats between the two vectors (Cout rounded up to 64)
   long long M;     // rows (padded positions) of this launch
   int H, W, Hp, Wp;
   int nchunk, ntaps, Cout, NC, MT, TPS, SA, SB;
@@ -40,7 +49,7 @@ struct TcParams {
   int tiles_m, total_work, dbuf;   // persistent schedule: work item w -> (tile = w % tiles_m, n-slice = w / tiles_m)
   long long* prof;                 // optional per-CTA cycle counters of the MMA warp (PE_TC_PROF=1): [wait_b, issue, wait_a, wait_main, total, stages]
   int dbg;                         // PE_TC_DBG experiment bits: 1 = issue no MMAs, 2 = no epilogue global traffic
-  int CPD;                         // chunks per drain group (accumulation length bound, see kernel comment)
+  int SPD;                         // weight stages per drain group (accumulation length bound, see kernel comment)
 };
 
 // ------------------------------------------------------------------------------------------ PTX helpers
@@ -102,7 +111,11 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uin
       "{\n"
       ".reg .pred p;\n"
       "setp.ne.b32 p, %4, 0;\n"
+#if PE_FP16
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+#else
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+#endif
       "}\n"
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
@@ -146,13 +159,13 @@ __device__ __forceinline__ void tc_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, int bo_mode) {
   uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
   d |= (uint64_t)1 << 16;                         // leading-dim byte offset (unused for swizzled K-major) = 16 B
-  d |= (uint64_t)(1024 >> 4) << 32;               // stride-dim byte offset: next 8-row group
+  d |= (uint64_t)((8 * CHB) >> 4) << 32;          // stride-dim byte offset: next 8-row group
   d |= (uint64_t)1 << 46;                         // descriptor version (sm_100)
   // Measured on B200 (tests/tc_bringup.py): the 128B swizzle XOR is applied to ABSOLUTE shared-memory address bits,
   // so a descriptor that starts at an arbitrary row of a TMA-written window needs base_offset = 0; setting the
   // "swizzle phase" there (bo_mode 0, kept for the experiment) reads the wrong 16-byte chunks.
   if (bo_mode == 0) d |= (uint64_t)((saddr >> 7) & 7u) << 49;
-  d |= (uint64_t)2 << 61;                         // SWIZZLE_128B
+  d |= (uint64_t)(CHB == 128 ? 2 : 4) << 61;      // SWIZZLE_128B / SWIZZLE_64B
   return d;
 }
 
@@ -161,13 +174,14 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, int bo_mode) {
 //
 // Accumulation-length bound.  Measured on B200 (tests/tc_bringup.py): tcgen05 kind::tf32 accumulates into TMEM with
 // truncation, a bias of ~1.2e-8 (relative) per MMA step that grows linearly with K -- 1.6e-5 at K=3456, too much for
-// the 1e-3 px keypoint gate after ~100 layers.  So no TMEM accumulator ever sees more than CPD*ntaps*2 (<= ~18-32)
-// hi*hi steps: the MMA warp ping-pongs between two `main` accumulators, one drain group (CPD channel chunks) each,
+// the 1e-3 px keypoint gate after ~100 layers (the bias is systematic, so it compounds through the residual stream).
+// So no TMEM accumulator ever sees more than ~6 hi*hi steps: the MMA warp rotates through NMAIN `main` accumulators, one
+// drain group (SPD weight stages) each,
 // and the epilogue warps add every drained partial into FP32 registers (round-to-nearest).  The two cross terms
 // hi*lo + lo*hi are 2^-11 smaller, so their truncation is harmless and they accumulate over the whole K in `corr`
 // (double-buffered per tile).  TMEM columns: main0 | main1 | corr0 | corr1, MT*NC = NG*16 columns each.
-__device__ __forceinline__ void st_shared_v4(uint32_t addr, float4 v) {
-  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+__device__ __forceinline__ void st_shared_u4(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, int c0, int c1, uint32_t src) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
@@ -195,15 +209,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   constexpr int NC = NG * 16 / MT;                 // output channels per CTA
   constexpr uint32_t GC = NG * 16;                 // columns of one accumulator set (= MT*NC)
   constexpr uint32_t NMAIN = (NG <= 6) ? 3u : 2u;   // `main` accumulator buffers in flight (TMEM: (NMAIN+2)*GC <= 512 columns)
-  constexpr uint32_t b_bytes = (uint32_t)TPS * NC * 128u;
+  constexpr uint32_t b_bytes = (uint32_t)TPS * NC * CHB;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
-  const uint32_t a_bytes = (uint32_t)p.Rpad * 128u;
+  const uint32_t a_bytes = (uint32_t)p.Rpad * CHB;
   const uint32_t sA = base;
   const uint32_t sB = sA + p.SA * a_bytes;
   const uint32_t sStage = sB + p.SB * b_bytes;     // epilogue store staging: 4 warps x 2 buffers x (32 rows x 128 B), SWIZZLE_128B
-  const uint32_t sBar = sStage + 4u * 2u * 4096u;  // 8-byte barriers
+  const uint32_t sBar = sStage + 4u * 2u * 32u * CHB;  // 8-byte barriers
   const uint32_t bar_a_full = sBar, bar_a_empty = sBar + 8 * p.SA;
   const uint32_t bar_b_full = bar_a_empty + 8 * p.SA, bar_b_empty = bar_b_full + 8 * p.SB;
   const uint32_t bar_main_full = bar_b_empty + 8 * p.SB;    // [NMAIN] (room for 4)
@@ -250,7 +264,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (p.dbg & 8) { mbar_arrive(full); }
           else {
             mbar_expect_tx(full, a_bytes);
-            for (int b = 0; b < p.nbA; ++b) tma_load_2d(dst + (uint32_t)b * p.RB * 128u, &tmA, j * 32, m0 - p.halo + b * p.RB, full);
+            for (int b = 0; b < p.nbA; ++b) tma_load_2d(dst + (uint32_t)b * p.RB * CHB, &tmA, j * (CHB / 4), m0 - p.halo + b * p.RB, full);
           }
           ra.advance(p.SA);
         };
@@ -266,7 +280,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             else {
               mbar_expect_tx(full, b_bytes);
 #pragma unroll
-              for (int t = 0; t < TPS; ++t, wr += tap_stride) tma_load_2d(dst + (uint32_t)(t * NC) * 128u, &tmW, 0, wr, full);
+              for (int t = 0; t < TPS; ++t, wr += tap_stride) tma_load_2d(dst + (uint32_t)(t * NC) * CHB, &tmW, 0, wr, full);
             }
             rb.advance(p.SB);
             if (g == 0 && j + 1 < p.nchunk) load_a(j + 1);   // next activation window right behind the first weights
@@ -280,12 +294,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================== MMA issuer: warp-uniform control flow, one elected lane issues =====================
     const bool no_mma = (p.dbg & 1) != 0;
     // instruction descriptor: D=F32, A=B=TF32, K-major both, N = NC, M = 128
-    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NC >> 3) << 17) | ((128u >> 4) << 24);
+    constexpr uint32_t FMT = PE_FP16 ? 0u : 2u;                       // A/B format: F16 = 0, TF32 = 2
+    constexpr uint32_t idesc = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(NC >> 3) << 17) | ((128u >> 4) << 24);
     const uint64_t d0 = umma_desc(sA, p.bo_mode);
     const uint32_t desc_hi = (uint32_t)(d0 >> 32);                    // identical for A and B tiles
     const uint32_t a_lo0 = (uint32_t)d0, b_lo0 = (uint32_t)umma_desc(sB, p.bo_mode);
     const uint32_t a_step = a_bytes >> 4;
-    const uint32_t wp8 = (uint32_t)p.Wp * 8u;                         // one image row down, in 16-byte units of the window
+    const uint32_t wp8 = (uint32_t)p.Wp * ROW16;                      // one image row down, in 16-byte units of the window
     Ring ra, rb;
     uint32_t dg = 0, dgp = 0, tl = 0;       // drain-group buffer / phase, tile counter
     bool b_ready = false, a_ready = false, m_ready = false;   // results of early polls (latency hidden behind MMA issue)
@@ -300,21 +315,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_after();
       const uint32_t d_corr = tmem_base + (NMAIN + cbuf) * GC;
       uint32_t d_main = tmem_base;
-      int jj = 0;
+      int sj = 0;                           // stages issued into the current drain group
+      const int last_stage = p.nchunk * ngroups - 1;
+      int stage_no = 0;
       for (int j = 0; j < p.nchunk; ++j) {
         long long c0 = prof ? clock64() : 0;
-        if (jj == 0) {
-          if (!m_ready) mbar_wait(bar_main_empty + 8 * dg, dgp ^ 1u); // epilogue has drained this main buffer
-          d_main = tmem_base + dg * GC;
-        }
-        if (prof) { const long long c1 = clock64(); c_wm += c1 - c0; c0 = c1; }
         if (!a_ready) mbar_wait(bar_a_full + 8 * ra.idx, ra.phase);
         tc_fence_after();
         if (prof) c_wa += clock64() - c0;
         const uint32_t a_slot = a_lo0 + ra.idx * a_step;
         uint32_t sh8 = 0;                   // window row shift of the group's first tap, in 16-byte units
         uint32_t kx = 0;
-        for (int g = 0; g < ngroups; ++g) {
+        for (int g = 0; g < ngroups; ++g, ++stage_no) {
+          if (sj == 0) {
+            const long long cm = prof ? clock64() : 0;
+            if (!m_ready) mbar_wait(bar_main_empty + 8 * dg, dgp ^ 1u); // epilogue has drained this main buffer
+            d_main = tmem_base + dg * GC;
+            if (prof) c_wm += clock64() - cm;
+          }
           long long c2 = prof ? clock64() : 0;
           if (!b_ready) mbar_wait(bar_b_full + 8 * rb.idx, rb.phase);
           tc_fence_after();
@@ -323,23 +341,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t b_empty_bar = bar_b_empty + 8 * rb.idx;
           rb.advance(p.SB);
           b_ready = mbar_try(bar_b_full + 8 * rb.idx, rb.phase);   // poll the NEXT stage now; its latency hides behind the MMA issue
-          const uint32_t acc_main = (jj == 0 && g == 0) ? 0u : 1u;
+          const uint32_t acc_main = (sj == 0) ? 0u : 1u;
           const uint32_t acc_corr = (j == 0 && g == 0) ? 0u : 1u;
           if (!no_mma && elect_one()) {
 #pragma unroll
             for (int t = 0; t < TPS; ++t) {
 #pragma unroll
               for (int mt = 0; mt < MT; ++mt) {
-                const uint32_t a = a_slot + sh8 + (uint32_t)(t * 8 + mt * 1024);      // +1 row per tap, +128 rows per mt
-                const uint32_t b = b_slot + (uint32_t)(t * NC * 8);
+                const uint32_t a = a_slot + sh8 + (uint32_t)(t * ROW16 + mt * 128 * ROW16);   // +1 row per tap, +128 rows per mt
+                const uint32_t b = b_slot + (uint32_t)(t * NC * ROW16);
                 const uint32_t dm = d_main + (uint32_t)(mt * NC), dc = d_corr + (uint32_t)(mt * NC);
-                // k-step 0: floats 0..7 of hi (bytes 0..31) and of lo (bytes 64..95); k-step 1: +32 B
-                tc_mma_tf32(dm, desc64(desc_hi, a), desc64(desc_hi, b), idesc, t == 0 ? acc_main : 1u);     // hi * hi
-                tc_mma_tf32(dc, desc64(desc_hi, a), desc64(desc_hi, b + 4), idesc, t == 0 ? acc_corr : 1u); // hi * lo
-                tc_mma_tf32(dc, desc64(desc_hi, a + 4), desc64(desc_hi, b), idesc, 1u);                     // lo * hi
-                tc_mma_tf32(dm, desc64(desc_hi, a + 2), desc64(desc_hi, b + 2), idesc, 1u);
-                tc_mma_tf32(dc, desc64(desc_hi, a + 2), desc64(desc_hi, b + 6), idesc, 1u);
-                tc_mma_tf32(dc, desc64(desc_hi, a + 6), desc64(desc_hi, b + 2), idesc, 1u);
+                // hi/h half at +0, lo/l half at +LO16 (16-byte units); tf32: two K=8 steps of 32 B, fp16: one K=16 step
+#pragma unroll
+                for (int ks = 0; ks < KSTEPS; ++ks) {
+                  const uint32_t ak = a + 2 * ks, bk = b + 2 * ks;
+                  tc_mma_tf32(dm, desc64(desc_hi, ak), desc64(desc_hi, bk), idesc, (t == 0 && ks == 0) ? acc_main : 1u);          // hi * hi
+                  tc_mma_tf32(dc, desc64(desc_hi, ak), desc64(desc_hi, bk + LO16), idesc, (t == 0 && ks == 0) ? acc_corr : 1u);   // hi * lo
+                  tc_mma_tf32(dc, desc64(desc_hi, ak + LO16), desc64(desc_hi, bk), idesc, 1u);                                    // lo * hi
+                }
               }
             }
             tc_commit(b_empty_bar);                         // weights stage free once these MMAs retire
@@ -347,22 +366,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_arrive(b_empty_bar);
           }
           if (prof) c_is += clock64() - c2;
+          if (++sj == p.SPD || stage_no == last_stage) {
+            if (no_mma) { if (lane == 0) mbar_arrive(bar_main_full + 8 * dg); }
+            else if (elect_one()) tc_commit(bar_main_full + 8 * dg);     // this drain group's partial sums are complete
+            sj = 0;
+            if (++dg == NMAIN) { dg = 0; dgp ^= 1u; }
+            m_ready = mbar_try(bar_main_empty + 8 * dg, dgp ^ 1u);
+          }
           // next group's first tap: TPS>1 -> a group is one stencil row, go one image row down; TPS==1 -> next tap
           if (TPS > 1) sh8 += wp8;
-          else if (p.ntaps > 1) { if (++kx == (uint32_t)p.tapw) { kx = 0; sh8 += wp8 - 8u * (p.tapw - 1); } else sh8 += 8; }
+          else if (p.ntaps > 1) { if (++kx == (uint32_t)p.tapw) { kx = 0; sh8 += wp8 - ROW16 * (p.tapw - 1); } else sh8 += ROW16; }
           __syncwarp();
         }
         if (no_mma) { if (lane == 0) mbar_arrive(bar_a_empty + 8 * ra.idx); }
         else if (elect_one()) tc_commit(bar_a_empty + 8 * ra.idx);     // activation window free
         ra.advance(p.SA);
         a_ready = mbar_try(bar_a_full + 8 * ra.idx, ra.phase);         // early polls for the next chunk
-        if (++jj == p.CPD || j == p.nchunk - 1) {
-          if (no_mma) { if (lane == 0) mbar_arrive(bar_main_full + 8 * dg); }
-          else if (elect_one()) tc_commit(bar_main_full + 8 * dg);     // this drain group's partial sums are complete
-          jj = 0;
-          if (++dg == NMAIN) { dg = 0; dgp ^= 1u; }
-          m_ready = mbar_try(bar_main_empty + 8 * dg, dgp ^ 1u);
-        }
         __syncwarp();
       }
     }
@@ -373,12 +392,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else {
     // ===================== epilogue (warps 2..5; TMEM lane quarter = warp % 4) =====================
     const int q = warp & 3;
-    const int rowF = 2 * p.Cout;
+    const int rowF = ps_row_floats(p.Cout);
+    constexpr int CF = PS_CHUNK_FLOATS;                     // floats per 16-channel chunk of a row
     constexpr int gpm = NC / 16;                            // 16-column groups per 128-row accumulator
-    const int ndrain = (p.nchunk + p.CPD - 1) / p.CPD;
+    const int ndrain = (p.nchunk * ngroups + p.SPD - 1) / p.SPD;
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
     const int hpwp = p.Hp * p.Wp;
-    const uint32_t st_base = sStage + (uint32_t)q * 8192u;
+    const uint32_t st_base = sStage + (uint32_t)q * 2u * 32u * CHB;
     uint32_t st_cnt = 0;
     uint32_t tl = 0, dg = 0, dgp = 0;
     int tile = blockIdx.x % p.tiles_m, nsl = blockIdx.x / p.tiles_m;
@@ -391,7 +411,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int g = 0; g < NG; ++g) {
           const long long m = m0 + (g / gpm) * 128 + q * 32 + lane;
-          if (m < p.M) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.res + m * rowF + 2 * (n0 + (g % gpm) * 16)));
+          if (m < p.M) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.res + m * rowF + (n0 / 16 + g % gpm) * CF));
         }
       }
       for (int d = 0; d < ndrain; ++d) {
@@ -403,6 +423,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint32_t r[16];
             tc_ld16_nowait(t_lane + dg * GC + g * 16, r);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            // accumulators stay in the SCALED domain (weights were multiplied by 2^k per channel); the residual is brought
+            // into that domain when it is added and the final phase multiplies by 2^-k: all exact
             if (d == 0) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) acc[g][i] = __uint_as_float(r[i]);
@@ -419,9 +441,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (d == 0 && p.res && !(p.dbg & 2)) {
           // Residual add, folded into the accumulators NOW: the loads' HBM/L2 latency hides behind the MMAs of the
           // remaining channel chunks instead of sitting in the store phase (software-pipelined one group ahead).
-          float4 cur[8], nxt[8];
-          auto fetch = [&](int g, float4 (&dst)[8]) {
-            const int mt = g / gpm, c0 = (g % gpm) * 16;
+          constexpr int NV = CHB / 16;                       // 16-byte vectors per row chunk
+          float4 cur[NV], nxt[NV];
+          auto fetch = [&](int g, float4 (&dst)[NV]) {
+            const int mt = g / gpm, gg = g % gpm;
             const long long m = m0 + mt * 128 + q * 32 + lane;
             bool ok = false;
             if (m < p.M) {
@@ -430,25 +453,49 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               ok = py >= 1 && py <= p.H && px >= 1 && px <= p.W;
             }
             if (ok) {
-              const float4* rp = reinterpret_cast<const float4*>(p.res + m * rowF + 2 * (n0 + c0));
+              const float4* rp = reinterpret_cast<const float4*>(p.res + m * rowF + (n0 / 16 + gg) * CF);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) dst[i] = __ldg(rp + i);
+              for (int i = 0; i < NV; ++i) dst[i] = __ldg(rp + i);
             } else {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+              for (int i = 0; i < NV; ++i) dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
           };
           fetch(0, cur);
 #pragma unroll
           for (int g = 0; g < NG; ++g) {
             if (g + 1 < NG) fetch(g + 1, nxt);
+            float isc[16];                       // 2^k of this group's channels (exact)
+            {
+              const float4* ip = reinterpret_cast<const float4*>(p.scale + p.scale_pad + n0 + (g % gpm) * 16);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) { const float4 t4 = __ldg(ip + i); isc[4 * i] = t4.x; isc[4 * i + 1] = t4.y; isc[4 * i + 2] = t4.z; isc[4 * i + 3] = t4.w; }
+            }
+#if PE_FP16
+            // cur[0..1] = 16 h halfs, cur[2..3] = 16 l halfs
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const uint32_t* hw = reinterpret_cast<const uint32_t*>(&cur[i]);
+              const uint32_t* lw = reinterpret_cast<const uint32_t*>(&cur[2 + i]);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[k]));
+                const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[k]));
+                acc[g][8 * i + 2 * k + 0] = fmaf(hf.x + lf.x, isc[8 * i + 2 * k + 0], acc[g][8 * i + 2 * k + 0]);
+                acc[g][8 * i + 2 * k + 1] = fmaf(hf.y + lf.y, isc[8 * i + 2 * k + 1], acc[g][8 * i + 2 * k + 1]);
+              }
+            }
+#else
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              acc[g][4 * i + 0] += cur[i].x + cur[4 + i].x; acc[g][4 * i + 1] += cur[i].y + cur[4 + i].y;
-              acc[g][4 * i + 2] += cur[i].z + cur[4 + i].z; acc[g][4 * i + 3] += cur[i].w + cur[4 + i].w;
+              acc[g][4 * i + 0] = fmaf(cur[i].x + cur[4 + i].x, isc[4 * i + 0], acc[g][4 * i + 0]);
+              acc[g][4 * i + 1] = fmaf(cur[i].y + cur[4 + i].y, isc[4 * i + 1], acc[g][4 * i + 1]);
+              acc[g][4 * i + 2] = fmaf(cur[i].z + cur[4 + i].z, isc[4 * i + 2], acc[g][4 * i + 2]);
+              acc[g][4 * i + 3] = fmaf(cur[i].w + cur[4 + i].w, isc[4 * i + 3], acc[g][4 * i + 3]);
             }
+#endif
 #pragma unroll
-            for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
+            for (int i = 0; i < NV; ++i) cur[i] = nxt[i];
           }
         }
       }
@@ -480,43 +527,57 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int gg = 0; gg < gpm; ++gg) {
           const int g = mt * gpm + gg, c0 = gg * 16;
-          float4 hi[4], lo[4];
+          constexpr int NV = CHB / 16;                       // 16-byte vectors of one staged row: [hi.. | lo..]
+          uint4 ov[NV];
           if (!interior) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) hi[i] = lo[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = 0; i < NV; ++i) ov[i] = make_uint4(0u, 0u, 0u, 0u);
           } else {
             const float4* bp = reinterpret_cast<const float4*>(p.bias + n0 + c0);
+            const float4* sp = reinterpret_cast<const float4*>(p.scale + n0 + c0);
             float v[16];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const float4 b4 = __ldg(bp + i);
-              v[4 * i + 0] = acc[g][4 * i + 0] + b4.x; v[4 * i + 1] = acc[g][4 * i + 1] + b4.y;
-              v[4 * i + 2] = acc[g][4 * i + 2] + b4.z; v[4 * i + 3] = acc[g][4 * i + 3] + b4.w;
+              const float4 b4 = __ldg(bp + i), s4 = __ldg(sp + i);
+              v[4 * i + 0] = fmaf(acc[g][4 * i + 0], s4.x, b4.x); v[4 * i + 1] = fmaf(acc[g][4 * i + 1], s4.y, b4.y);
+              v[4 * i + 2] = fmaf(acc[g][4 * i + 2], s4.z, b4.z); v[4 * i + 3] = fmaf(acc[g][4 * i + 3], s4.w, b4.w);
             }
             if (p.relu) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
             }
+#if PE_FP16
+            uint2 h[4], l[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) split4(make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]), hi[i], lo[i]);
+            for (int i = 0; i < 4; ++i) split4_h(make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]), h[i], l[i]);
+            ov[0] = make_uint4(h[0].x, h[0].y, h[1].x, h[1].y); ov[1] = make_uint4(h[2].x, h[2].y, h[3].x, h[3].y);
+            ov[2] = make_uint4(l[0].x, l[0].y, l[1].x, l[1].y); ov[3] = make_uint4(l[2].x, l[2].y, l[3].x, l[3].y);
+#else
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              float4 hi, lo;
+              split4(make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]), hi, lo);
+              ov[i] = make_uint4(__float_as_uint(hi.x), __float_as_uint(hi.y), __float_as_uint(hi.z), __float_as_uint(hi.w));
+              ov[4 + i] = make_uint4(__float_as_uint(lo.x), __float_as_uint(lo.y), __float_as_uint(lo.z), __float_as_uint(lo.w));
+            }
+#endif
           }
-          // stage this warp's 32 rows x 128 B (hi16|lo16) in shared memory (128B-swizzled: conflict-free 16-byte stores),
-          // then ONE bulk tensor store writes them as full 128-byte lines (a per-thread row store would scatter 16-byte
-          // pieces over 32 lines per instruction).  Rows past the tensor end are clipped by the TMA unit.
-          const uint32_t sbuf = st_base + (st_cnt & 1u) * 4096u;
+          // stage this warp's 32 rows x CHB bytes in shared memory (hardware swizzle pattern of the store tensor map:
+          // conflict-free 16-byte stores), then ONE bulk tensor store writes them as full lines (a per-thread row store
+          // would scatter 16-byte pieces over 32 lines per instruction).  Rows past the tensor end are clipped by TMA.
+          const uint32_t sbuf = st_base + (st_cnt & 1u) * 32u * CHB;
           if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the buffer used two stores ago is free
           __syncwarp();
-          const uint32_t srow = sbuf + (uint32_t)lane * 128u;
+          const uint32_t srow = sbuf + (uint32_t)lane * CHB;
+          // SWIZZLE_128B: 16-byte chunk index ^= row & 7;  SWIZZLE_64B: chunk index ^= (row >> 1) & 3
+          const uint32_t sw = (CHB == 128) ? (lane & 7u) : ((lane >> 1) & 3u);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            st_shared_v4(srow + (((uint32_t)i ^ (lane & 7u)) << 4), hi[i]);
-            st_shared_v4(srow + (((uint32_t)(4 + i) ^ (lane & 7u)) << 4), lo[i]);
-          }
+          for (int i = 0; i < NV; ++i) st_shared_u4(srow + (((uint32_t)i ^ sw) << 4), ov[i]);
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
           if (lane == 0) {
             const long long mrow = m0 + mt * 128 + q * 32;
-            if (mrow < p.M) tma_store_2d(&tmO, 2 * (n0 + c0), (int)mrow, sbuf);
+            if (mrow < p.M) tma_store_2d(&tmO, (n0 + c0) / 16 * CF, (int)mrow, sbuf);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
           ++st_cnt;
@@ -588,7 +649,8 @@ static CUresult encode_2d(CUtensorMap* tm, const void* gptr, uint64_t dim0, uint
   cuuint32_t box[2] = {box0, box1};
   cuuint32_t estr[2] = {1, 1};
   return cuTensorMapEncodeTiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(gptr), gdim, gstr, box, estr,
-                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CHB == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 }
 
@@ -603,7 +665,8 @@ cudaError_t tc_conv_plan_create(TcConvPlan** out, const float* in, float* outp, 
   const int halo_after = ks == 1 ? 0 : Wp + 1;
   const long long Mmax = (long long)max_img * Hp * Wp;
   if (Mmax + 1024 >= (1LL << 31)) return cudaErrorNotSupported;   // TMA row coordinates are int32
-  const size_t smem_cap = 200 * 1024 - 32 * 1024;   // rings; 32 KB more for the epilogue store staging
+  const size_t stage_bytes = (size_t)4 * 2 * 32 * CHB;   // epilogue store staging
+  const size_t smem_cap = 200 * 1024 - stage_bytes;
   double best = 1e30;
   TcParams bp{};
   size_t bsmem = 0;
@@ -628,9 +691,8 @@ cudaError_t tc_conv_plan_create(TcConvPlan** out, const float* in, float* outp, 
       p.NC = NC; p.MT = MT; p.nchunk = nchunk; p.ntaps = ntaps; p.Cout = Cout; p.halo = halo; p.dbuf = 1;
       p.TPS = tps;
       // accumulation-length bound: at most ~max_steps hi*hi MMA steps per TMEM accumulator before a drain
-      const int max_steps = env_int("PE_TC_MAXSTEPS", 18);
-      p.CPD = std::max(1, max_steps / (2 * ntaps));
-      if (p.CPD > nchunk) p.CPD = nchunk;
+      const int max_steps = env_int("PE_TC_MAXSTEPS", 6);   // measured: 18 steps -> heatmap error 7e-5 (keypoint gate fails), 6 -> 2.3e-5
+      p.SPD = std::max(1, max_steps / (KSTEPS * tps));
       p.tapw = ks;
       const int R = 128 * MT + halo + halo_after;
       p.nbA = (R + 255) / 256;
@@ -638,7 +700,7 @@ cudaError_t tc_conv_plan_create(TcConvPlan** out, const float* in, float* outp, 
       p.RB = p.Rpad / p.nbA;
       p.SA = 2;
       p.nsub = 1; p.Nsub = NC; p.nboxW = 1; p.NCbox = NC;
-      const size_t a_bytes = (size_t)p.Rpad * 128, b_bytes = (size_t)p.TPS * NC * 128;
+      const size_t a_bytes = (size_t)p.Rpad * CHB, b_bytes = (size_t)p.TPS * NC * CHB;
       int SB = 6;
       while (SB > 3 && p.SA * a_bytes + SB * b_bytes + 4096 > smem_cap) --SB;
       if (p.SA * a_bytes + SB * b_bytes + 4096 > smem_cap) continue;
@@ -654,20 +716,23 @@ cudaError_t tc_conv_plan_create(TcConvPlan** out, const float* in, float* outp, 
       // shared memory (128 B/clk: A 4 KB + B NC*32 B per MMA) or fetched from L2 (~32 B/clk/SM)
       // measured (tools/mma_bench.cu): one M=128 SS tcgen05.mma takes max(N/2, 32 + N/4) clocks -- below N=128 the
       // 4 KB A-operand read from shared memory paces it -- plus ~300 clocks of barrier hand-off per pipeline stage
-      const double n_mma = 6.0 * ntaps * nchunk * MT;
+      const double n_mma = 3.0 * KSTEPS * ntaps * nchunk * MT;
       const double mma = n_mma * std::max(NC / 2.0, 32.0 + NC / 4.0) + 300.0 * (ntaps / tps) * nchunk;
-      const double bytes = (double)nchunk * (a_bytes + (double)ntaps * NC * 128);
+      const double bytes = (double)nchunk * (a_bytes + (double)ntaps * NC * CHB);
       const double epi = (double)MT * (NC / 16) * 260.0 + 1500.0;
       const double item = std::max(std::max(mma, bytes / 32.0), epi);
       const double t = items * item + 4000.0;
-      if (t < best) { best = t; bp = p; bsmem = p.SA * a_bytes + p.SB * b_bytes + 32768 + 4096; bns = ns; }
+      if (t < best) { best = t; bp = p; bsmem = p.SA * a_bytes + p.SB * b_bytes + stage_bytes + 4096; bns = ns; }
      }
     }
   }
   if (best >= 1e30) return cudaErrorNotSupported;
   TcConvPlan* pl = new TcConvPlan();
   pl->p = bp;
-  pl->p.out = outp; pl->p.res = res; pl->p.bias = bias;
+  // weight blob = [per-channel scale 2^-k: Cout floats padded to 64][inverse 2^k: same][packed operand]
+  const float* wpack = wtc + 2 * (((Cout + 63) / 64) * 64);
+  pl->p.scale_pad = ((Cout + 63) / 64) * 64;
+  pl->p.out = outp; pl->p.res = res; pl->p.bias = bias; pl->p.scale = wtc;
   pl->p.H = H; pl->p.W = W; pl->p.Hp = Hp; pl->p.Wp = Wp; pl->p.relu = relu;
   pl->p.bo_mode = env_int("PE_TC_BO_MODE", 1);
   pl->p.dbg = env_int("PE_TC_DBG", 0);
@@ -676,9 +741,10 @@ cudaError_t tc_conv_plan_create(TcConvPlan** out, const float* in, float* outp, 
   pl->rows_per_img = Hp * Wp;
   pl->smem = bsmem;
   pl->ns = bns;
-  CUresult r1 = encode_2d(&pl->tmA, in, (uint64_t)2 * Cin, (uint64_t)Mmax, (uint64_t)2 * Cin * 4, 32, (uint32_t)bp.RB);
-  CUresult r2 = encode_2d(&pl->tmW, wtc, 32, (uint64_t)ntaps * nchunk * Cout, 128, 32, (uint32_t)bp.NCbox);
-  CUresult r3 = encode_2d(&pl->tmO, outp, (uint64_t)2 * Cout, (uint64_t)Mmax, (uint64_t)2 * Cout * 4, 32, 32);
+  const uint32_t cf = PS_CHUNK_FLOATS;    // tensor maps address 4-byte words: one 16-channel chunk = cf words
+  CUresult r1 = encode_2d(&pl->tmA, in, (uint64_t)ps_row_floats(Cin), (uint64_t)Mmax, (uint64_t)ps_row_floats(Cin) * 4, cf, (uint32_t)bp.RB);
+  CUresult r2 = encode_2d(&pl->tmW, wpack, cf, (uint64_t)ntaps * nchunk * Cout, CHB, cf, (uint32_t)bp.NCbox);
+  CUresult r3 = encode_2d(&pl->tmO, outp, (uint64_t)ps_row_floats(Cout), (uint64_t)Mmax, (uint64_t)ps_row_floats(Cout) * 4, cf, 32);
   if (r3 != CUDA_SUCCESS) r1 = r3;
   if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) {
     fprintf(stderr, "conv_tc: cuTensorMapEncodeTiled failed (%d, %d) Cin=%d Cout=%d RB=%d NCbox=%d\n", (int)r1, (int)r2, Cin, Cout, bp.RB, bp.NCbox);
@@ -692,8 +758,8 @@ cudaError_t tc_conv_plan_create(TcConvPlan** out, const float* in, float* outp, 
   }
   pl->num_sms = num_sms;
   if (env_int("PE_TC_VERBOSE", 0))
-    fprintf(stderr, "conv_tc plan: Cin=%d Cout=%d ks=%d %dx%d  MT=%d NS=%d NC=%d CPD=%d TPS=%d SA=%d SB=%d Rpad=%d RB=%d smem=%zu tmem=%d work=%d\n", Cin, Cout, ks, H, W,
-            bp.MT, bns, bp.NC, bp.CPD, bp.TPS, bp.SA, bp.SB, bp.Rpad, bp.RB, pl->smem, bp.tmem_cols, bp.total_work);
+    fprintf(stderr, "conv_tc plan: Cin=%d Cout=%d ks=%d %dx%d  MT=%d NS=%d NC=%d SPD=%d TPS=%d SA=%d SB=%d Rpad=%d RB=%d smem=%zu tmem=%d work=%d\n", Cin, Cout, ks, H, W,
+            bp.MT, bns, bp.NC, bp.SPD, bp.TPS, bp.SA, bp.SB, bp.Rpad, bp.RB, pl->smem, bp.tmem_cols, bp.total_work);
   *out = pl;
   return cudaSuccess;
 }

@@ -77,11 +77,10 @@ __global__ void __launch_bounds__(256) stem_kernel(const uint8_t* __restrict__ c
   const int img = (int)(m / (Hp * Wp));
   const int r = (int)(m % (Hp * Wp));
   const int py = r / Wp, px = r % Wp;
-  float* orow = out + m * 128 + chunk * 32;
+  float* orow = out + m * ps_row_floats(64);
   if (py < 1 || py > oh || px < 1 || px > ow) {
-    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) reinterpret_cast<float4*>(orow)[i] = z;
+    for (int i = 0; i < 16; i += 4) ps_zero4(orow, chunk * 16 + i);
     return;
   }
   const bool flip = img >= ncrop;
@@ -111,11 +110,7 @@ __global__ void __launch_bounds__(256) stem_kernel(const uint8_t* __restrict__ c
   }
 #pragma unroll
   for (int i = 0; i < 16; i += 4) {
-    float4 v = make_float4(fmaxf(acc[i], 0.f), fmaxf(acc[i + 1], 0.f), fmaxf(acc[i + 2], 0.f), fmaxf(acc[i + 3], 0.f));
-    float4 hi, lo;
-    split4(v, hi, lo);
-    *reinterpret_cast<float4*>(orow + i) = hi;
-    *reinterpret_cast<float4*>(orow + 16 + i) = lo;
+    ps_store4(orow, chunk * 16 + i, make_float4(fmaxf(acc[i], 0.f), fmaxf(acc[i + 1], 0.f), fmaxf(acc[i + 2], 0.f), fmaxf(acc[i + 3], 0.f)));
   }
 }
 
@@ -186,7 +181,7 @@ __global__ void __launch_bounds__(BN * 4) conv_simt_kernel(ConvArgs a) {
 
   const int nchunk = a.Cin >> 4;
   const int ksteps = a.ntaps * nchunk;
-  const int inRowF = 2 * a.Cin;
+  const int inRowF = ps_row_floats(a.Cin), outRowF = ps_row_floats(a.Cout);
 
   float4 pa[AU];
   float4 pb;
@@ -199,12 +194,7 @@ __global__ void __launch_bounds__(BN * 4) conv_simt_kernel(ConvArgs a) {
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (idx < 256) {
         const long long row = s_inrow[idx >> 2];
-        if (row >= 0) {
-          const float* p = a.in + (row + shift) * inRowF + ch * 32 + (idx & 3) * 4;
-          const float4 h = *reinterpret_cast<const float4*>(p);
-          const float4 l = *reinterpret_cast<const float4*>(p + 16);
-          v = make_float4(h.x + l.x, h.y + l.y, h.z + l.z, h.w + l.w);
-        }
+        if (row >= 0) v = ps_load4(a.in + (row + shift) * inRowF, ch * 16 + (idx & 3) * 4);
       }
       pa[u] = v;
     }
@@ -259,23 +249,20 @@ __global__ void __launch_bounds__(BN * 4) conv_simt_kernel(ConvArgs a) {
         if (c + j < a.cout_real) a.out[m * a.cout_real + c + j] = a.relu ? fmaxf(vv[j], 0.f) : vv[j];
       continue;
     }
-    float* orow = a.out + m * (2 * a.Cout);
+    float* orow = a.out + m * outRowF;
     if (s_inrow[tm * 4 + i] < 0) {
-      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-      float* p = orow + ps_chan_off(c);
-      *reinterpret_cast<float4*>(p) = z;
-      *reinterpret_cast<float4*>(p + 16) = z;
+      ps_zero4(orow, c);
       continue;
     }
     float4 v = make_float4(acc[i][0] + bz.x, acc[i][1] + bz.y, acc[i][2] + bz.z, acc[i][3] + bz.w);
     // res_off >= 0: residual before the ReLU (HRNet blocks); res_off < 0: after it, at row m - res_off (lifter)
     if (a.res && a.res_off >= 0) {
-      const float4 rr = ps_load4(a.res + (m + a.res_off) * (2 * a.Cout), c);
+      const float4 rr = ps_load4(a.res + (m + a.res_off) * outRowF, c);
       v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
     }
     if (a.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
     if (a.res && a.res_off < 0) {
-      const float4 rr = ps_load4(a.res + (m - a.res_off) * (2 * a.Cout), c);
+      const float4 rr = ps_load4(a.res + (m - a.res_off) * outRowF, c);
       v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
     }
     ps_store4(orow, c, v);
@@ -327,12 +314,10 @@ __global__ void __launch_bounds__(256) fuse_kernel(FuseArgs a) {
   const int img = (int)(m / (Hp * Wp));
   const int r = (int)(m % (Hp * Wp));
   const int py = r / Wp, px = r % Wp;
-  float* orow = a.out + m * (2 * a.C);
+  const int rowF = ps_row_floats(a.C);
+  float* orow = a.out + m * rowF;
   if (py < 1 || py > a.H || px < 1 || px > a.W) {
-    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    float* p = orow + ps_chan_off(c);
-    *reinterpret_cast<float4*>(p) = z;
-    *reinterpret_cast<float4*>(p + 16) = z;
+    ps_zero4(orow, c);
     return;
   }
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -340,7 +325,7 @@ __global__ void __launch_bounds__(256) fuse_kernel(FuseArgs a) {
     const int u = a.up[j];
     const int h = a.H / u, w = a.W / u;
     const long long row = ((long long)img * (h + 2) + (py - 1) / u + 1) * (w + 2) + (px - 1) / u + 1;
-    const float4 v = ps_load4(a.in[j] + row * (2 * a.C), c);
+    const float4 v = ps_load4(a.in[j] + row * rowF, c);
     s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
   }
   if (a.relu) { s.x = fmaxf(s.x, 0.f); s.y = fmaxf(s.y, 0.f); s.z = fmaxf(s.z, 0.f); s.w = fmaxf(s.w, 0.f); }
@@ -371,7 +356,7 @@ __global__ void __launch_bounds__(128) head_kernel(const float* __restrict__ in,
   const int img = (int)(t / (H * W));
   const int r = (int)(t % (H * W));
   const int y = r / W, x = r % W;
-  const float* row = in + (((long long)img * (H + 2) + y + 1) * (W + 2) + x + 1) * (2 * Cin);
+  const float* row = in + (((long long)img * (H + 2) + y + 1) * (W + 2) + x + 1) * ps_row_floats(Cin);
   for (int k0 = 0; k0 < K; k0 += 32) {
     float acc[32];
     const int kn = min(32, K - k0);
@@ -408,9 +393,10 @@ __global__ void ps_to_chw_kernel(const float* __restrict__ in, int C, int H, int
   const int c = (int)(t / (H * W));
   const int r = (int)(t % (H * W));
   const int y = r / W, x = r % W;
-  const float* row = in + (((long long)img * (H + 2) + y + 1) * (W + 2) + x + 1) * (2 * C);
-  const int o = ((c >> 4) << 5) + (c & 15);
-  out[t] = row[o] + row[o + 16];
+  const float* row = in + (((long long)img * (H + 2) + y + 1) * (W + 2) + x + 1) * ps_row_floats(C);
+  const float4 v = ps_load4(row, c & ~3);
+  const float vv[4] = {v.x, v.y, v.z, v.w};
+  out[t] = vv[c & 3];
 }
 
 void launch_ps_to_chw(const float* in, int C, int H, int W, int img, float* out, cudaStream_t st) {
@@ -418,26 +404,24 @@ void launch_ps_to_chw(const float* in, int C, int H, int W, int img, float* out,
   ps_to_chw_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, C, H, W, img, out);
 }
 
-// debug: dense NCHW fp32 -> PS tensor (zero halo, tf32 hi/lo split)
+// debug: dense NCHW fp32 -> PS tensor (zero halo, split)
 __global__ void chw_to_ps_kernel(const float* __restrict__ in, int C, int H, int W, int nimg, float* __restrict__ out) {
   const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
-  const int Hp = H + 2, Wp = W + 2;
-  if (t >= (long long)nimg * Hp * Wp * C) return;
-  const int c = (int)(t % C);
-  const long long m = t / C;
+  const int Hp = H + 2, Wp = W + 2, c4 = C >> 2;
+  if (t >= (long long)nimg * Hp * Wp * c4) return;
+  const int c = (int)(t % c4) * 4;
+  const long long m = t / c4;
   const int img = (int)(m / (Hp * Wp));
   const int r = (int)(m % (Hp * Wp));
   const int py = r / Wp, px = r % Wp;
-  float v = 0.f;
-  if (py >= 1 && py <= H && px >= 1 && px <= W) v = in[(((long long)img * C + c) * H + py - 1) * W + px - 1];
-  const float hi = tf32_round(v);
-  float* o = out + m * (2 * C) + ((c >> 4) << 5) + (c & 15);
-  o[0] = hi;
-  o[16] = v - hi;
+  float v[4] = {0.f, 0.f, 0.f, 0.f};
+  if (py >= 1 && py <= H && px >= 1 && px <= W)
+    for (int i = 0; i < 4; ++i) v[i] = in[(((long long)img * C + c + i) * H + py - 1) * W + px - 1];
+  ps_store4(out + m * ps_row_floats(C), c, make_float4(v[0], v[1], v[2], v[3]));
 }
 
 void launch_chw_to_ps(const float* in, int C, int H, int W, int nimg, float* out, cudaStream_t st) {
-  long long total = (long long)nimg * (H + 2) * (W + 2) * C;
+  long long total = (long long)nimg * (H + 2) * (W + 2) * (C / 4);
   chw_to_ps_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, C, H, W, nimg, out);
 }
 
@@ -463,15 +447,11 @@ __global__ void __launch_bounds__(256) s2d_kernel(const float* __restrict__ in, 
   const int par = ce / C, c = ce % C;
   const int py = par >> 1, px = par & 1;
   const int sy = 2 * (ap - 1) + py, sx = 2 * (bp - 1) + px;
-  float4 hi = make_float4(0.f, 0.f, 0.f, 0.f), lo = hi;
-  if (ap >= 1 && bp >= 1 && sy < HpI && sx < WpI) {
-    const float* src = in + (((long long)img * HpI + sy) * WpI + sx) * (2 * C) + ps_chan_off(c);
-    hi = *reinterpret_cast<const float4*>(src);
-    lo = *reinterpret_cast<const float4*>(src + 16);
-  }
-  float* dst = out + m * (2 * C4) + ps_chan_off(ce);
-  *reinterpret_cast<float4*>(dst) = hi;
-  *reinterpret_cast<float4*>(dst + 16) = lo;
+  float* drow = out + m * ps_row_floats(C4);
+  if (ap >= 1 && bp >= 1 && sy < HpI && sx < WpI)
+    ps_copy4(drow, ce, in + (((long long)img * HpI + sy) * WpI + sx) * ps_row_floats(C), c);
+  else
+    ps_zero4(drow, ce);
 }
 
 void launch_s2d(const float* in, int C, int Hin, int Win, int nimg, float* out, int Hout, int Wout, cudaStream_t st) {

@@ -39,11 +39,10 @@ __global__ void lifter_pack_input(const float* __restrict__ kp, int n_frames, in
   const int row = (int)(t / 48), c = (int)(t % 48);
   int f = row - pad;
   f = f < 0 ? 0 : (f >= n_frames ? n_frames - 1 : f);
-  const float v = c < 34 ? kp[(size_t)f * 34 + c] : 0.f;
-  const float hi = tf32_round(v);
-  float* o = out + (size_t)row * 96 + ((c >> 4) << 5) + (c & 15);
-  o[0] = hi;
-  o[16] = v - hi;
+  if (c & 3) return;
+  float v[4];
+  for (int i = 0; i < 4; ++i) v[i] = (c + i) < 34 ? kp[(size_t)f * 34 + c + i] : 0.f;
+  ps_store4(out + (size_t)row * ps_row_floats(48), c, make_float4(v[0], v[1], v[2], v[3]));
 }
 
 extern "C" int pe_lifter_create(pe_engine* e, const float* weights, int64_t n_floats, const int64_t* offsets, int32_t n_offsets,
@@ -85,8 +84,8 @@ extern "C" int pe_lift3d(pe_lifter* l, const float* kp2d_norm, int32_t n_frames,
     cudaFree(l->d_a); cudaFree(l->d_b); cudaFree(l->d_c); cudaFree(l->d_in); cudaFree(l->d_out);
     l->d_a = l->d_b = l->d_c = l->d_in = l->d_out = nullptr;
     const size_t rows = (size_t)T0 + 64;
-    if (cudaMalloc(&l->d_a, rows * 2 * C * sizeof(float)) != cudaSuccess || cudaMalloc(&l->d_b, rows * 2 * C * sizeof(float)) != cudaSuccess ||
-        cudaMalloc(&l->d_c, rows * 2 * C * sizeof(float)) != cudaSuccess || cudaMalloc(&l->d_in, rows * 96 * sizeof(float)) != cudaSuccess ||
+    if (cudaMalloc(&l->d_a, rows * ps_row_floats(C) * sizeof(float)) != cudaSuccess || cudaMalloc(&l->d_b, rows * ps_row_floats(C) * sizeof(float)) != cudaSuccess ||
+        cudaMalloc(&l->d_c, rows * ps_row_floats(C) * sizeof(float)) != cudaSuccess || cudaMalloc(&l->d_in, rows * ps_row_floats(48) * sizeof(float)) != cudaSuccess ||
         cudaMalloc(&l->d_out, rows * 51 * sizeof(float)) != cudaSuccess) {
       l->cap_rows = 0;
       return pe_set_error(PE_ERR_CUDA, "pe_lift3d: out of device memory");

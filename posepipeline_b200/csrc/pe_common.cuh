@@ -13,14 +13,26 @@
 //   lo to tcgen05.mma kind::tf32 directly (3xTF32 split precision); SIMT kernels read hi+lo (= the fp32
 //   value, exactly).  One 128-byte chunk = one TMA/UMMA SWIZZLE_128B row.
 // ---------------------------------------------------------------------------------------------
-struct ActView {
-  float* base;       // device pointer to row 0
-  int C, H, W;       // logical dims per image
-  __host__ __device__ int Hp() const { return H + 2; }
-  __host__ __device__ int Wp() const { return W + 2; }
-  __host__ __device__ int rowFloats() const { return 2 * C; }
-  __host__ __device__ long long rowsPerImage() const { return (long long)(H + 2) * (W + 2); }
-};
+// Two builds of the same layout idea (compile-time switch PE_FP16, see csrc/build.py):
+//   PE_FP16=0  "tf32x3": chunk = [hi(16 x f32) | lo(16 x f32)] = 128 B; hi = value rounded to TF32, lo = value - hi (exact).
+//                        8 bytes per element, no range limit; tcgen05 kind::tf32, K = 8 per MMA.
+//   PE_FP16=1  "fp16x2": chunk = [h(16 x f16) | l(16 x f16)]   =  64 B; h = fp16(value), l = fp16(value - h): 22 significant
+//                        bits, 4 bytes per element, |value| must stay below 65504 (activations of BN'd CNNs do; values
+//                        are clamped, never inf); tcgen05 kind::f16, K = 16 per MMA: half the MMAs and half the bytes.
+#ifndef PE_FP16
+#define PE_FP16 0
+#endif
+#include <cuda_fp16.h>
+
+#if PE_FP16
+#define PS_CHUNK_BYTES 64
+#else
+#define PS_CHUNK_BYTES 128
+#endif
+#define PS_CHUNK_FLOATS (PS_CHUNK_BYTES / 4)
+
+// floats (4-byte units) per PS row of a C-channel tensor
+__host__ __device__ __forceinline__ int ps_row_floats(int C) { return (C >> 4) * PS_CHUNK_FLOATS; }
 
 __device__ __forceinline__ float tf32_round(float v) {
   uint32_t u;
@@ -33,20 +45,79 @@ __device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
   lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
 }
 
-// offset (in floats) of channel c (multiple of 4) inside a PS row
-__device__ __forceinline__ int ps_chan_off(int c) { return ((c >> 4) << 5) + (c & 15); }
+// fp16 split of 4 values: h (4 halfs in a uint2) and l
+__device__ __forceinline__ void split4_h(const float4 v, uint2& h, uint2& l) {
+  const float lim = 65504.f;
+  const float x = fminf(fmaxf(v.x, -lim), lim), y = fminf(fmaxf(v.y, -lim), lim);
+  const float z = fminf(fmaxf(v.z, -lim), lim), w = fminf(fmaxf(v.w, -lim), lim);
+  const __half2 h0 = __floats2half2_rn(x, y), h1 = __floats2half2_rn(z, w);
+  const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+  const __half2 l0 = __floats2half2_rn(x - f0.x, y - f0.y), l1 = __floats2half2_rn(z - f1.x, w - f1.y);
+  h.x = *reinterpret_cast<const uint32_t*>(&h0); h.y = *reinterpret_cast<const uint32_t*>(&h1);
+  l.x = *reinterpret_cast<const uint32_t*>(&l0); l.y = *reinterpret_cast<const uint32_t*>(&l1);
+}
+__device__ __forceinline__ float4 join4_h(const uint2 h, const uint2 l) {
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&h.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
+  const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&l.x)), d = __half22float2(*reinterpret_cast<const __half2*>(&l.y));
+  return make_float4(a.x + c.x, a.y + c.y, b.x + d.x, b.y + d.y);
+}
 
+// byte offset of channel c (multiple of 4) inside a PS row (the hi / h part; the lo / l part is PS_CHUNK_BYTES/2 further)
+__device__ __forceinline__ int ps_chan_byte(int c) {
+#if PE_FP16
+  return ((c >> 4) << 6) + ((c & 15) << 1);
+#else
+  return ((c >> 4) << 7) + ((c & 15) << 2);
+#endif
+}
+
+// the fp32 values of channels c..c+3 of a row
 __device__ __forceinline__ float4 ps_load4(const float* row, int c) {
-  const float* p = row + ps_chan_off(c);
-  float4 h = *reinterpret_cast<const float4*>(p);
-  float4 l = *reinterpret_cast<const float4*>(p + 16);
+  const char* p = reinterpret_cast<const char*>(row) + ps_chan_byte(c);
+#if PE_FP16
+  return join4_h(*reinterpret_cast<const uint2*>(p), *reinterpret_cast<const uint2*>(p + 32));
+#else
+  const float4 h = *reinterpret_cast<const float4*>(p);
+  const float4 l = *reinterpret_cast<const float4*>(p + 64);
   return make_float4(h.x + l.x, h.y + l.y, h.z + l.z, h.w + l.w);
+#endif
 }
 
 __device__ __forceinline__ void ps_store4(float* row, int c, float4 v) {
+  char* p = reinterpret_cast<char*>(row) + ps_chan_byte(c);
+#if PE_FP16
+  uint2 h, l;
+  split4_h(v, h, l);
+  *reinterpret_cast<uint2*>(p) = h;
+  *reinterpret_cast<uint2*>(p + 32) = l;
+#else
   float4 hi, lo;
   split4(v, hi, lo);
-  float* p = row + ps_chan_off(c);
   *reinterpret_cast<float4*>(p) = hi;
-  *reinterpret_cast<float4*>(p + 16) = lo;
+  *reinterpret_cast<float4*>(p + 64) = lo;
+#endif
+}
+
+__device__ __forceinline__ void ps_zero4(float* row, int c) {
+  char* p = reinterpret_cast<char*>(row) + ps_chan_byte(c);
+#if PE_FP16
+  *reinterpret_cast<uint2*>(p) = make_uint2(0u, 0u);
+  *reinterpret_cast<uint2*>(p + 32) = make_uint2(0u, 0u);
+#else
+  *reinterpret_cast<float4*>(p) = make_float4(0.f, 0.f, 0.f, 0.f);
+  *reinterpret_cast<float4*>(p + 64) = make_float4(0.f, 0.f, 0.f, 0.f);
+#endif
+}
+
+// raw copy of 4 channels (both halves) between rows: no arithmetic, used by the space-to-depth repack
+__device__ __forceinline__ void ps_copy4(float* drow, int cd, const float* srow, int cs) {
+  char* d = reinterpret_cast<char*>(drow) + ps_chan_byte(cd);
+  const char* s = reinterpret_cast<const char*>(srow) + ps_chan_byte(cs);
+#if PE_FP16
+  *reinterpret_cast<uint2*>(d) = *reinterpret_cast<const uint2*>(s);
+  *reinterpret_cast<uint2*>(d + 32) = *reinterpret_cast<const uint2*>(s + 32);
+#else
+  *reinterpret_cast<float4*>(d) = *reinterpret_cast<const float4*>(s);
+  *reinterpret_cast<float4*>(d + 64) = *reinterpret_cast<const float4*>(s + 64);
+#endif
 }

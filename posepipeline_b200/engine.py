@@ -164,12 +164,43 @@ def space_to_depth_weights(w: np.ndarray) -> np.ndarray:
     return out.reshape(cout, 4 * cin, 2, 2)
 
 
+def fp16_split(x: np.ndarray):
+    """h = fp16(x) (clamped to the finite range), l = fp16(x - h): 22 significant bits."""
+    x = np.clip(np.ascontiguousarray(x, np.float32), -65504.0, 65504.0)
+    h = x.astype(np.float16)
+    l = (x - h.astype(np.float32)).astype(np.float16)
+    return h, l
+
+
 def pack_tc_weights(w: np.ndarray) -> np.ndarray:
-    """(Cout,Cin,k,k) folded fp32 -> tensor-core operand [tap][Cin/16][Cout][hi16|lo16] (see csrc/conv_tc.cu)."""
+    """(Cout,Cin,k,k) folded fp32 -> tensor-core weight blob (float32 words), see csrc/conv_tc.cu:
+         [scale 2^-k: Cout floats, padded to 64] [inverse 2^k: same] [operand: [tap][Cin/16][Cout][hi16|lo16]]
+    The operand holds TF32 pairs (library built with PE_FP16=0) or FP16 pairs packed two per word (PE_FP16=1).
+    Each output channel's weights are multiplied by a power of two so the largest is in [8,16): exact, and it keeps the
+    small `lo` halves out of the FP16 subnormal range (a 0.05 weight would otherwise carry only ~20 significant bits);
+    the epilogue multiplies the accumulators by `scale` = the inverse power of two (exact again)."""
     cout, cin, k, _ = w.shape
-    t = w.transpose(2, 3, 1, 0).reshape(k * k, cin // 16, 16, cout).transpose(0, 1, 3, 2)   # tap, chunk, cout, 16
-    hi, lo = tf32_split(t)
-    return np.concatenate([hi, lo], axis=3)
+    mx = np.abs(w.reshape(cout, -1)).max(axis=1)
+    e = np.where(mx > 0, np.floor(np.log2(16.0 / np.maximum(mx, 1e-30))), 0.0)
+    e = np.clip(e, -20, 40)
+    while True:                                   # guard the open upper bound against log2 rounding
+        over = mx * np.exp2(e) >= 16.0
+        if not over.any():
+            break
+        e = e - over
+    up = np.exp2(e).astype(np.float32)
+    ws = (w * up[:, None, None, None]).astype(np.float32)                                    # exact
+    scale = np.ones(2 * (((cout + 63) // 64) * 64), np.float32)
+    scale[:cout] = np.exp2(-e).astype(np.float32)
+    scale[len(scale) // 2: len(scale) // 2 + cout] = up
+    t = ws.transpose(2, 3, 1, 0).reshape(k * k, cin // 16, 16, cout).transpose(0, 1, 3, 2)   # tap, chunk, cout, 16
+    if _lib.load().pe_precision_mode() == 1:
+        h, l = fp16_split(t)
+        op = np.ascontiguousarray(np.concatenate([h, l], axis=3)).view(np.float32)
+    else:
+        hi, lo = tf32_split(t)
+        op = np.concatenate([hi, lo], axis=3)
+    return np.concatenate([scale, op.ravel()])
 
 
 class PoseEngine:

@@ -187,14 +187,18 @@ def test_every_layer_matches_oracle(eng):
 
 
 # ------------------------------------------------------------------ end to end
-def _check_keypoints(got, ref32, ref64, tol=1e-3):
-    """<= tol px wherever the oracle itself is well conditioned (its fp32 and fp64 runs agree to 2e-4 px)."""
+def _check_keypoints(got, ref32, ref64, tol=1e-3, cond_thr=1e-4, min_good=0.9):
+    """The gate: |dx| <= tol px wherever the oracle itself is well conditioned, i.e. its own fp32 and fp64 runs agree to
+    cond_thr px (DARK's Taylor step divides by the local Hessian: on a flat or ridge-like peak the oracle's fp32 rounding
+    alone moves the keypoint by more than that).  Elsewhere the error must stay proportional to the oracle's own."""
     assert got.shape == ref32.shape
     cond = np.abs(ref32[..., :2] - ref64[..., :2]).max(-1)
-    good = cond <= 2e-4
-    assert good.mean() > 0.9, good.mean()
+    good = cond <= cond_thr
     d = np.abs(got[..., :2] - ref32[..., :2]).max(-1)
-    print("keypoint |dx| px: max over well-conditioned", d[good].max(), "p99", np.quantile(d, 0.99), "oracle fp32-vs-fp64 max", cond.max())
+    worst = np.argsort(d.ravel())[::-1][:3]
+    print("keypoint |dx| px: max over well-conditioned", d[good].max(), "p99", np.quantile(d, 0.99), "well-conditioned", good.mean(),
+          "worst (d, oracle self-error):", [(float(d.ravel()[i]), float(cond.ravel()[i])) for i in worst])
+    assert good.mean() > min_good, good.mean()
     assert d[good].max() <= tol, (d[good].max(), np.argwhere(d > tol))
     assert np.all(d[~good] <= 50 * cond[~good] + tol), (d[~good], cond[~good])
     sc = np.abs(got[..., 2] - ref32[..., 2])
@@ -273,8 +277,5 @@ def test_topdown_halpe136_and_wholebody133(eng):
         ref32 = helpers.oracle_keypoints(method, frames, fidx, bbs, "float32")
         ref64 = helpers.oracle_keypoints(method, frames, fidx, bbs, "float64")
         assert got.shape == (3, spec.num_joints, 3)
-        cond = np.abs(ref32[..., :2] - ref64[..., :2]).max(-1)
-        good = cond <= 2e-4
-        d = np.abs(got[..., :2] - ref32[..., :2]).max(-1)
-        assert good.mean() > 0.7 and d[good].max() <= 1e-3, (method, d[good].max(), good.mean())
+        _check_keypoints(got, ref32, ref64, min_good=0.7)
         m.close()

@@ -44,7 +44,7 @@ def test_mmpose_top_down_person_on_video(tmp_path, synthetic_env):
     net64 = helpers.oracle_net("HRNet_W48_COCO", 0, "float64")
     ref64 = OT.top_down_video(net64, decoded, bbox, OT.HRNET_W48_COCO)
     cond = np.abs(ref[..., :2] - ref64[..., :2]).max(-1)
-    good = cond <= 2e-4
+    good = cond <= 1e-4
     d = np.abs(got[..., :2] - ref[..., :2]).max(-1)
     assert good.mean() > 0.7 and d[good].max() <= 1e-3, (d[good].max(), good.mean())   # 720p crops run off the frame: fewer well-conditioned maps
     assert np.abs(got[..., 2] - ref[..., 2]).max() <= 1e-4 * max(1.0, np.abs(ref[..., 2]).max())

@@ -128,7 +128,10 @@ def test_frame_sharding_world2_gloo_matches_single_rank(tmp_path, monkeypatch):
     single = W.mmpose_top_down_person(key)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + os.getpid() % 500
+    import socket
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
     procs = [ctx.Process(target=_worker, args=(r, 2, port, str(tmp_path), q)) for r in range(2)]
     for p in procs:
         p.start()
