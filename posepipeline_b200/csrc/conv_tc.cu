@@ -31,7 +31,11 @@
 #define CHB PS_CHUNK_BYTES
 constexpr uint32_t ROW16 = CHB / 16;          // 8 (tf32) / 4 (fp16)
 constexpr uint32_t LO16 = CHB / 32;           // 16-byte units from hi to lo: 4 / 2
-constexpr int KSTEPS = PE_FP16 ? 1 : 2;       // MMA k-steps per chunk half: 16 x f16 = one K=16 MMA; 16 x tf32 = two K=8 MMAs
+constexpr int KSTEPS = PE_FP16 ? 1 : 2;
+// warp roles: 0 = activation-window TMA producer, 1 = MMA issuer, 2..9 = epilogue (TMEM lane quarter = warp & 3, two warps per
+// quarter splitting the 16-column groups), 10 = weight TMA producer, 11 = second MMA issuer (cross terms)
+constexpr int TC_THREADS = 384;
+constexpr int EPI_WARPS = 8;       // MMA k-steps per chunk half: 16 x f16 = one K=16 MMA; 16 x tf32 = two K=8 MMAs
 
 struct TcParams {
   float* out;
@@ -203,7 +207,7 @@ __device__ __forceinline__ uint64_t desc64(uint32_t hi, uint32_t lo) {
 }
 
 template <int NG, int MT, int TPS>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ CUtensorMap tmO, const TcParams p) {
   constexpr int NC = NG * 16 / MT;                 // output channels per CTA
@@ -216,24 +220,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t a_bytes = (uint32_t)p.Rpad * CHB;
   const uint32_t sA = base;
   const uint32_t sB = sA + p.SA * a_bytes;
-  const uint32_t sStage = sB + p.SB * b_bytes;     // epilogue store staging: 4 warps x 2 buffers x (32 rows x 128 B), SWIZZLE_128B
-  const uint32_t sBar = sStage + 4u * 2u * 32u * CHB;  // 8-byte barriers
+  const uint32_t sStage = sB + p.SB * b_bytes;     // epilogue store staging: 8 warps x 2 buffers x (32 rows x CHB), hardware swizzle
+  const uint32_t sBar = sStage + (uint32_t)EPI_WARPS * 2u * 32u * CHB;  // 8-byte barriers
   const uint32_t bar_a_full = sBar, bar_a_empty = sBar + 8 * p.SA;
   const uint32_t bar_b_full = bar_a_empty + 8 * p.SA, bar_b_empty = bar_b_full + 8 * p.SB;
   const uint32_t bar_main_full = bar_b_empty + 8 * p.SB;    // [NMAIN] (room for 4)
   const uint32_t bar_main_empty = bar_main_full + 32;       // [NMAIN]
   const uint32_t bar_corr_empty = bar_main_empty + 32;      // [2]
-  const uint32_t s_tmem = bar_corr_empty + 16;
+  const uint32_t bar_corr_full = bar_corr_empty + 16;       // [2]
+  const uint32_t s_tmem = bar_corr_full + 16;
   uint8_t* gen = smem_raw + (base - raw);
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen + (s_tmem - base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < p.SA; ++i) { mbar_init(bar_a_full + 8 * i, 1); mbar_init(bar_a_empty + 8 * i, 1); }
-    for (int i = 0; i < p.SB; ++i) { mbar_init(bar_b_full + 8 * i, 1); mbar_init(bar_b_empty + 8 * i, 1); }
-    for (int i = 0; i < (int)NMAIN; ++i) { mbar_init(bar_main_full + 8 * i, 1); mbar_init(bar_main_empty + 8 * i, 4); }
-    for (int i = 0; i < 2; ++i) mbar_init(bar_corr_empty + 8 * i, 4);
+    for (int i = 0; i < p.SA; ++i) { mbar_init(bar_a_full + 8 * i, 1); mbar_init(bar_a_empty + 8 * i, 2); }   // empty: both MMA warps
+    for (int i = 0; i < p.SB; ++i) { mbar_init(bar_b_full + 8 * i, 1); mbar_init(bar_b_empty + 8 * i, 2); }
+    for (int i = 0; i < (int)NMAIN; ++i) { mbar_init(bar_main_full + 8 * i, 1); mbar_init(bar_main_empty + 8 * i, EPI_WARPS); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_corr_empty + 8 * i, EPI_WARPS); mbar_init(bar_corr_full + 8 * i, 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -249,16 +254,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int ngroups = p.ntaps / TPS;
 
   if (warp == 0) {
-    // ===================== TMA producer (one lane) =====================
+    // ===================== activation-window TMA producer (one lane) =====================
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmW) : "memory");
-      Ring ra, rb;
-      int tile = blockIdx.x % p.tiles_m, nsl = blockIdx.x / p.tiles_m;
+      Ring ra;
+      int tile = blockIdx.x % p.tiles_m;
       for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
         const int m0 = tile * 128 * MT;            // row index fits 31 bits (asserted on the host)
-        const int n0 = nsl * NC;
-        auto load_a = [&](int j) {
+        for (int j = 0; j < p.nchunk; ++j) {
           mbar_wait(bar_a_empty + 8 * ra.idx, ra.phase ^ 1u);
           const uint32_t full = bar_a_full + 8 * ra.idx, dst = sA + ra.idx * a_bytes;
           if (p.dbg & 8) { mbar_arrive(full); }
@@ -267,10 +270,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int b = 0; b < p.nbA; ++b) tma_load_2d(dst + (uint32_t)b * p.RB * CHB, &tmA, j * (CHB / 4), m0 - p.halo + b * p.RB, full);
           }
           ra.advance(p.SA);
-        };
-        load_a(0);
-        int wrow = n0;                              // row of W tile (tap 0, chunk j): (tap*nchunk + j)*Cout + n0
-        const int tap_stride = p.nchunk * p.Cout;
+        }
+        tile += gridDim.x;
+        while (tile >= p.tiles_m) tile -= p.tiles_m;
+      }
+    }
+  } else if (warp == 2 + EPI_WARPS) {
+    // ===================== weight TMA producer (one lane): its own warp, so a full activation ring never delays weights
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmW) : "memory");
+      Ring rb;
+      int tile = blockIdx.x % p.tiles_m, nsl = blockIdx.x / p.tiles_m;
+      const int tap_stride = p.nchunk * p.Cout;
+      for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+        int wrow = nsl * NC;                        // row of W tile (tap 0, chunk j): (tap*nchunk + j)*Cout + n0
         for (int j = 0; j < p.nchunk; ++j, wrow += p.Cout) {
           int wr = wrow;
           for (int g = 0; g < ngroups; ++g) {
@@ -283,15 +296,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               for (int t = 0; t < TPS; ++t, wr += tap_stride) tma_load_2d(dst + (uint32_t)(t * NC) * CHB, &tmW, 0, wr, full);
             }
             rb.advance(p.SB);
-            if (g == 0 && j + 1 < p.nchunk) load_a(j + 1);   // next activation window right behind the first weights
           }
         }
         tile += gridDim.x;
         while (tile >= p.tiles_m) { tile -= p.tiles_m; ++nsl; }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer: warp-uniform control flow, one elected lane issues =====================
+  } else if (warp == 1 || warp == 3 + EPI_WARPS) {
+    // ===================== MMA issuers: warp-uniform control flow, one elected lane issues =====================
+    // Measured on B200 (tools/issue_bench.cu): for N <= 128 a tcgen05.mma blocks its issuing thread for the whole shared-
+    // memory operand fetch (~51 clk at N = 48), so NOTHING the issuing warp does besides issuing -- barrier polls, commits,
+    // address arithmetic -- overlaps with tensor work.  Two issuing warps interleave in the tensor pipe (44 clk per N = 48
+    // MMA, each warp's non-MMA time hidden behind the other's MMAs), so the work is split by accumulator:
+    //   warp X (1):  hi*hi  -> `main` accumulators, owns the drain-group protocol with the epilogue
+    //   warp Y (11): hi*lo + lo*hi -> `corr` accumulator of the tile, commits corr_full at the end of a tile
+    // Both wait on the same a_full / b_full barriers; a stage is free once BOTH have committed (a_empty / b_empty count 2).
+    const bool roleX = (warp == 1);
     const bool no_mma = (p.dbg & 1) != 0;
     // instruction descriptor: D=F32, A=B=TF32, K-major both, N = NC, M = 128
     constexpr uint32_t FMT = PE_FP16 ? 0u : 2u;                       // A/B format: F16 = 0, TF32 = 2
@@ -309,10 +329,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const long long c_t0 = prof ? clock64() : 0;
     for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++tl) {
       const uint32_t cbuf = tl & 1u;
-      { const long long cc = prof ? clock64() : 0;
+      if (!roleX) {
+        const long long cc = prof ? clock64() : 0;
         mbar_wait(bar_corr_empty + 8 * cbuf, ((tl >> 1) & 1u) ^ 1u);   // epilogue has read this corr buffer
-        if (prof) c_wc += clock64() - cc; }
-      tc_fence_after();
+        if (prof) c_wc += clock64() - cc;
+        tc_fence_after();
+      }
       const uint32_t d_corr = tmem_base + (NMAIN + cbuf) * GC;
       uint32_t d_main = tmem_base;
       int sj = 0;                           // stages issued into the current drain group
@@ -327,9 +349,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint32_t sh8 = 0;                   // window row shift of the group's first tap, in 16-byte units
         uint32_t kx = 0;
         for (int g = 0; g < ngroups; ++g, ++stage_no) {
-          if (sj == 0) {
+          if (roleX && sj == 0) {
             const long long cm = prof ? clock64() : 0;
             if (!m_ready) mbar_wait(bar_main_empty + 8 * dg, dgp ^ 1u); // epilogue has drained this main buffer
+            tc_fence_after();
             d_main = tmem_base + dg * GC;
             if (prof) c_wm += clock64() - cm;
           }
@@ -343,30 +366,47 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           b_ready = mbar_try(bar_b_full + 8 * rb.idx, rb.phase);   // poll the NEXT stage now; its latency hides behind the MMA issue
           const uint32_t acc_main = (sj == 0) ? 0u : 1u;
           const uint32_t acc_corr = (j == 0 && g == 0) ? 0u : 1u;
-          if (!no_mma && elect_one()) {
+          if (no_mma) {
+            if (lane == 0) mbar_arrive(b_empty_bar);
+          } else if (roleX) {
+            if (elect_one()) {
 #pragma unroll
-            for (int t = 0; t < TPS; ++t) {
+              for (int t = 0; t < TPS; ++t) {
 #pragma unroll
-              for (int mt = 0; mt < MT; ++mt) {
-                const uint32_t a = a_slot + sh8 + (uint32_t)(t * ROW16 + mt * 128 * ROW16);   // +1 row per tap, +128 rows per mt
-                const uint32_t b = b_slot + (uint32_t)(t * NC * ROW16);
-                const uint32_t dm = d_main + (uint32_t)(mt * NC), dc = d_corr + (uint32_t)(mt * NC);
-                // hi/h half at +0, lo/l half at +LO16 (16-byte units); tf32: two K=8 steps of 32 B, fp16: one K=16 step
+                for (int mt = 0; mt < MT; ++mt) {
+                  const uint32_t a = a_slot + sh8 + (uint32_t)(t * ROW16 + mt * 128 * ROW16);   // +1 row per tap, +128 rows per mt
+                  const uint32_t b = b_slot + (uint32_t)(t * NC * ROW16);
+                  const uint32_t dm = d_main + (uint32_t)(mt * NC);
 #pragma unroll
-                for (int ks = 0; ks < KSTEPS; ++ks) {
-                  const uint32_t ak = a + 2 * ks, bk = b + 2 * ks;
-                  tc_mma_tf32(dm, desc64(desc_hi, ak), desc64(desc_hi, bk), idesc, (t == 0 && ks == 0) ? acc_main : 1u);          // hi * hi
-                  tc_mma_tf32(dc, desc64(desc_hi, ak), desc64(desc_hi, bk + LO16), idesc, (t == 0 && ks == 0) ? acc_corr : 1u);   // hi * lo
-                  tc_mma_tf32(dc, desc64(desc_hi, ak + LO16), desc64(desc_hi, bk), idesc, 1u);                                    // lo * hi
+                  for (int ks = 0; ks < KSTEPS; ++ks)
+                    tc_mma_tf32(dm, desc64(desc_hi, a + 2 * ks), desc64(desc_hi, b + 2 * ks), idesc, (t == 0 && ks == 0) ? acc_main : 1u);   // hi * hi
                 }
               }
+              tc_commit(b_empty_bar);                         // weights stage free once these MMAs (and warp Y's) retire
             }
-            tc_commit(b_empty_bar);                         // weights stage free once these MMAs retire
-          } else if (no_mma && lane == 0) {
-            mbar_arrive(b_empty_bar);
+          } else {
+            if (elect_one()) {
+#pragma unroll
+              for (int t = 0; t < TPS; ++t) {
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                  const uint32_t a = a_slot + sh8 + (uint32_t)(t * ROW16 + mt * 128 * ROW16);
+                  const uint32_t b = b_slot + (uint32_t)(t * NC * ROW16);
+                  const uint32_t dc = d_corr + (uint32_t)(mt * NC);
+                  // hi/h half at +0, lo/l half at +LO16 (16-byte units); tf32: two K=8 steps of 32 B, fp16: one K=16 step
+#pragma unroll
+                  for (int ks = 0; ks < KSTEPS; ++ks) {
+                    const uint32_t ak = a + 2 * ks, bk = b + 2 * ks;
+                    tc_mma_tf32(dc, desc64(desc_hi, ak), desc64(desc_hi, bk + LO16), idesc, (t == 0 && ks == 0) ? acc_corr : 1u);   // hi * lo
+                    tc_mma_tf32(dc, desc64(desc_hi, ak + LO16), desc64(desc_hi, bk), idesc, 1u);                                    // lo * hi
+                  }
+                }
+              }
+              tc_commit(b_empty_bar);
+            }
           }
           if (prof) c_is += clock64() - c2;
-          if (++sj == p.SPD || stage_no == last_stage) {
+          if (roleX && (++sj == p.SPD || stage_no == last_stage)) {
             if (no_mma) { if (lane == 0) mbar_arrive(bar_main_full + 8 * dg); }
             else if (elect_one()) tc_commit(bar_main_full + 8 * dg);     // this drain group's partial sums are complete
             sj = 0;
@@ -379,58 +419,88 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           __syncwarp();
         }
         if (no_mma) { if (lane == 0) mbar_arrive(bar_a_empty + 8 * ra.idx); }
-        else if (elect_one()) tc_commit(bar_a_empty + 8 * ra.idx);     // activation window free
+        else if (elect_one()) tc_commit(bar_a_empty + 8 * ra.idx);     // activation window free (once both issuers committed)
         ra.advance(p.SA);
         a_ready = mbar_try(bar_a_full + 8 * ra.idx, ra.phase);         // early polls for the next chunk
         __syncwarp();
       }
+      if (!roleX) {
+        if (no_mma) { if (lane == 0) mbar_arrive(bar_corr_full + 8 * cbuf); }
+        else if (elect_one()) tc_commit(bar_corr_full + 8 * cbuf);     // every cross-term MMA of this tile has retired
+        __syncwarp();
+      }
     }
     if (prof && lane == 0) {
-      long long* o = p.prof + (size_t)blockIdx.x * 8;
+      long long* o = p.prof + (size_t)blockIdx.x * 16 + (roleX ? 0 : 8);
       o[0] = c_wb; o[1] = c_is; o[2] = c_wa; o[3] = c_wm; o[4] = clock64() - c_t0; o[5] = c_st; o[6] = c_wc;
     }
   } else {
-    // ===================== epilogue (warps 2..5; TMEM lane quarter = warp % 4) =====================
+    // ===================== epilogue (warps 2..9; TMEM lane quarter = warp & 3; the two warps of a quarter take the even / odd
+    // 16-column groups, so TMEM drains, residual loads, the fp16 split and the stores of one tile run on 8 warps) ==========
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    constexpr int NGH = (NG + 1) / 2;                       // groups per warp (the odd warp of an odd NG has one fewer)
     const int rowF = ps_row_floats(p.Cout);
     constexpr int CF = PS_CHUNK_FLOATS;                     // floats per 16-channel chunk of a row
     constexpr int gpm = NC / 16;                            // 16-column groups per 128-row accumulator
     const int ndrain = (p.nchunk * ngroups + p.SPD - 1) / p.SPD;
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
     const int hpwp = p.Hp * p.Wp;
-    const uint32_t st_base = sStage + (uint32_t)q * 2u * 32u * CHB;
+    const uint32_t st_base = sStage + (uint32_t)(warp - 2) * 2u * 32u * CHB;
     uint32_t st_cnt = 0;
     uint32_t tl = 0, dg = 0, dgp = 0;
     int tile = blockIdx.x % p.tiles_m, nsl = blockIdx.x / p.tiles_m;
     for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++tl) {
       const long long m0 = (long long)tile * 128 * MT;
       const int n0 = nsl * NC;
-      float acc[NG][16];
+      float acc[NGH][16];
+      // interior test of this lane's row in each of the MT 128-row accumulators (bit mt)
+      uint32_t interior = 0;
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        const long long m = m0 + mt * 128 + q * 32 + lane;
+        if (m < p.M) {
+          const int r = (int)(m % hpwp);
+          const int py = r / p.Wp, px = r - py * p.Wp;
+          if (py >= 1 && py <= p.H && px >= 1 && px <= p.W) interior |= 1u << mt;
+        }
+      }
       if (p.res && !(p.dbg & 2)) {
         // pull this tile's residual rows towards L2 while the first chunk's MMAs run
 #pragma unroll
-        for (int g = 0; g < NG; ++g) {
-          const long long m = m0 + (g / gpm) * 128 + q * 32 + lane;
-          if (m < p.M) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.res + m * rowF + (n0 / 16 + g % gpm) * CF));
+        for (int gi = 0; gi < NGH; ++gi) {
+          const int g = 2 * gi + half;
+          if (g < NG && ((interior >> (g / gpm)) & 1u)) {
+            const long long m = m0 + (g / gpm) * 128 + q * 32 + lane;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.res + m * rowF + (n0 / 16 + g % gpm) * CF));
+          }
         }
       }
       for (int d = 0; d < ndrain; ++d) {
         mbar_wait_relaxed(bar_main_full + 8 * dg, dgp, (p.dbg >> 8) & 0xfff);
         tc_fence_after();
         if (!(p.dbg & 16)) {
+          // two 16-column groups per TMEM wait (32 live registers)
 #pragma unroll
-          for (int g = 0; g < NG; ++g) {
-            uint32_t r[16];
-            tc_ld16_nowait(t_lane + dg * GC + g * 16, r);
+          for (int g2 = 0; g2 < NGH; g2 += 2) {
+            uint32_t r[2][16];
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+              if (g2 + u < NGH && 2 * (g2 + u) + half < NG) tc_ld16_nowait(t_lane + dg * GC + (2 * (g2 + u) + half) * 16, r[u]);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             // accumulators stay in the SCALED domain (weights were multiplied by 2^k per channel); the residual is brought
             // into that domain when it is added and the final phase multiplies by 2^-k: all exact
-            if (d == 0) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) acc[g][i] = __uint_as_float(r[i]);
-            } else {
+            for (int u = 0; u < 2; ++u) {
+              const int gi = g2 + u;
+              if (gi >= NGH || 2 * gi + half >= NG) continue;
+              if (d == 0) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) acc[g][i] += __uint_as_float(r[i]);
+                for (int i = 0; i < 16; ++i) acc[gi][i] = __uint_as_float(r[u][i]);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) acc[gi][i] += __uint_as_float(r[u][i]);
+              }
             }
           }
         }
@@ -440,148 +510,146 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (++dg == NMAIN) { dg = 0; dgp ^= 1u; }
         if (d == 0 && p.res && !(p.dbg & 2)) {
           // Residual add, folded into the accumulators NOW: the loads' HBM/L2 latency hides behind the MMAs of the
-          // remaining channel chunks instead of sitting in the store phase (software-pipelined one group ahead).
+          // remaining channel chunks instead of sitting in the store phase.  All loads are issued before the first use.
           constexpr int NV = CHB / 16;                       // 16-byte vectors per row chunk
-          float4 cur[NV], nxt[NV];
-          auto fetch = [&](int g, float4 (&dst)[NV]) {
-            const int mt = g / gpm, gg = g % gpm;
-            const long long m = m0 + mt * 128 + q * 32 + lane;
-            bool ok = false;
-            if (m < p.M) {
-              const int r = (int)(m % hpwp);
-              const int py = r / p.Wp, px = r - py * p.Wp;
-              ok = py >= 1 && py <= p.H && px >= 1 && px <= p.W;
-            }
-            if (ok) {
-              const float4* rp = reinterpret_cast<const float4*>(p.res + m * rowF + (n0 / 16 + gg) * CF);
 #pragma unroll
-              for (int i = 0; i < NV; ++i) dst[i] = __ldg(rp + i);
-            } else {
+          for (int g2 = 0; g2 < NGH; g2 += 2) {
+            float4 rv[2][NV];
 #pragma unroll
-              for (int i = 0; i < NV; ++i) dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-          };
-          fetch(0, cur);
+            for (int u = 0; u < 2; ++u) {
+              const int g = 2 * (g2 + u) + half;
+              const bool ok = g2 + u < NGH && g < NG && ((interior >> (g / gpm)) & 1u);
+              if (ok) {
+                const long long m = m0 + (g / gpm) * 128 + q * 32 + lane;
+                const float4* rp = reinterpret_cast<const float4*>(p.res + m * rowF + (n0 / 16 + g % gpm) * CF);
 #pragma unroll
-          for (int g = 0; g < NG; ++g) {
-            if (g + 1 < NG) fetch(g + 1, nxt);
-            float isc[16];                       // 2^k of this group's channels (exact)
-            {
-              const float4* ip = reinterpret_cast<const float4*>(p.scale + p.scale_pad + n0 + (g % gpm) * 16);
+                for (int i = 0; i < NV; ++i) rv[u][i] = __ldg(rp + i);
+              } else {
 #pragma unroll
-              for (int i = 0; i < 4; ++i) { const float4 t4 = __ldg(ip + i); isc[4 * i] = t4.x; isc[4 * i + 1] = t4.y; isc[4 * i + 2] = t4.z; isc[4 * i + 3] = t4.w; }
-            }
-#if PE_FP16
-            // cur[0..1] = 16 h halfs, cur[2..3] = 16 l halfs
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              const uint32_t* hw = reinterpret_cast<const uint32_t*>(&cur[i]);
-              const uint32_t* lw = reinterpret_cast<const uint32_t*>(&cur[2 + i]);
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[k]));
-                const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[k]));
-                acc[g][8 * i + 2 * k + 0] = fmaf(hf.x + lf.x, isc[8 * i + 2 * k + 0], acc[g][8 * i + 2 * k + 0]);
-                acc[g][8 * i + 2 * k + 1] = fmaf(hf.y + lf.y, isc[8 * i + 2 * k + 1], acc[g][8 * i + 2 * k + 1]);
+                for (int i = 0; i < NV; ++i) rv[u][i] = make_float4(0.f, 0.f, 0.f, 0.f);
               }
             }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int gi = g2 + u, g = 2 * gi + half;
+              if (gi >= NGH || g >= NG) continue;
+              float isc[16];                       // 2^k of this group's channels (exact)
+              {
+                const float4* ip = reinterpret_cast<const float4*>(p.scale + p.scale_pad + n0 + (g % gpm) * 16);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { const float4 t4 = __ldg(ip + i); isc[4 * i] = t4.x; isc[4 * i + 1] = t4.y; isc[4 * i + 2] = t4.z; isc[4 * i + 3] = t4.w; }
+              }
+#if PE_FP16
+              // rv[0..1] = 16 h halfs, rv[2..3] = 16 l halfs
+#pragma unroll
+              for (int i = 0; i < 2; ++i) {
+                const uint32_t* hw = reinterpret_cast<const uint32_t*>(&rv[u][i]);
+                const uint32_t* lw = reinterpret_cast<const uint32_t*>(&rv[u][2 + i]);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[k]));
+                  const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[k]));
+                  acc[gi][8 * i + 2 * k + 0] = fmaf(hf.x + lf.x, isc[8 * i + 2 * k + 0], acc[gi][8 * i + 2 * k + 0]);
+                  acc[gi][8 * i + 2 * k + 1] = fmaf(hf.y + lf.y, isc[8 * i + 2 * k + 1], acc[gi][8 * i + 2 * k + 1]);
+                }
+              }
 #else
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              acc[g][4 * i + 0] = fmaf(cur[i].x + cur[4 + i].x, isc[4 * i + 0], acc[g][4 * i + 0]);
-              acc[g][4 * i + 1] = fmaf(cur[i].y + cur[4 + i].y, isc[4 * i + 1], acc[g][4 * i + 1]);
-              acc[g][4 * i + 2] = fmaf(cur[i].z + cur[4 + i].z, isc[4 * i + 2], acc[g][4 * i + 2]);
-              acc[g][4 * i + 3] = fmaf(cur[i].w + cur[4 + i].w, isc[4 * i + 3], acc[g][4 * i + 3]);
-            }
+              for (int i = 0; i < 4; ++i) {
+                acc[gi][4 * i + 0] = fmaf(rv[u][i].x + rv[u][4 + i].x, isc[4 * i + 0], acc[gi][4 * i + 0]);
+                acc[gi][4 * i + 1] = fmaf(rv[u][i].y + rv[u][4 + i].y, isc[4 * i + 1], acc[gi][4 * i + 1]);
+                acc[gi][4 * i + 2] = fmaf(rv[u][i].z + rv[u][4 + i].z, isc[4 * i + 2], acc[gi][4 * i + 2]);
+                acc[gi][4 * i + 3] = fmaf(rv[u][i].w + rv[u][4 + i].w, isc[4 * i + 3], acc[gi][4 * i + 3]);
+              }
 #endif
-#pragma unroll
-            for (int i = 0; i < NV; ++i) cur[i] = nxt[i];
+            }
           }
         }
       }
-      // the commit behind the last drain group also covers every hi*lo / lo*hi MMA of this tile
+      // cross terms: committed by the second MMA warp at the end of the tile
       const uint32_t cbuf = tl & 1u;
+      mbar_wait_relaxed(bar_corr_full + 8 * cbuf, (tl >> 1) & 1u, 0);
+      tc_fence_after();
       if (!(p.dbg & 16)) {
 #pragma unroll
-        for (int g = 0; g < NG; ++g) {
-          uint32_t r[16];
-          tc_ld16(t_lane + (NMAIN + cbuf) * GC + g * 16, r);
+        for (int g2 = 0; g2 < NGH; g2 += 2) {
+          uint32_t r[2][16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) acc[g][i] += __uint_as_float(r[i]);
+          for (int u = 0; u < 2; ++u)
+            if (g2 + u < NGH && 2 * (g2 + u) + half < NG) tc_ld16_nowait(t_lane + (NMAIN + cbuf) * GC + (2 * (g2 + u) + half) * 16, r[u]);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int gi = g2 + u;
+            if (gi >= NGH || 2 * gi + half >= NG) continue;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[gi][i] += __uint_as_float(r[u][i]);
+          }
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_corr_empty + 8 * cbuf);
-      // ---- bias / residual / ReLU / tf32 split / store (the MMA warp is already on the next tile)
+      // ---- bias / ReLU / split / store (the MMA warp is already on the next tile)
 #pragma unroll
-      for (int mt = 0; mt < MT; ++mt) {
-        const long long m = m0 + mt * 128 + q * 32 + lane;
-        if (p.dbg & 2) continue;
-        bool interior = false;
-        if (m < p.M) {
-          const int r = (int)(m % hpwp);
-          const int py = r / p.Wp, px = r - py * p.Wp;
-          interior = py >= 1 && py <= p.H && px >= 1 && px <= p.W;
-        }
+      for (int gi = 0; gi < NGH; ++gi) {
+        const int g = 2 * gi + half;
+        if (g >= NG || (p.dbg & 2)) continue;
+        const int mt = g / gpm, c0 = (g % gpm) * 16;
+        constexpr int NV = CHB / 16;                       // 16-byte vectors of one staged row: [hi.. | lo..]
+        uint4 ov[NV];
+        if (!((interior >> mt) & 1u)) {
 #pragma unroll
-        for (int gg = 0; gg < gpm; ++gg) {
-          const int g = mt * gpm + gg, c0 = gg * 16;
-          constexpr int NV = CHB / 16;                       // 16-byte vectors of one staged row: [hi.. | lo..]
-          uint4 ov[NV];
-          if (!interior) {
+          for (int i = 0; i < NV; ++i) ov[i] = make_uint4(0u, 0u, 0u, 0u);
+        } else {
+          const float4* bp = reinterpret_cast<const float4*>(p.bias + n0 + c0);
+          const float4* sp = reinterpret_cast<const float4*>(p.scale + n0 + c0);
+          float v[16];
 #pragma unroll
-            for (int i = 0; i < NV; ++i) ov[i] = make_uint4(0u, 0u, 0u, 0u);
-          } else {
-            const float4* bp = reinterpret_cast<const float4*>(p.bias + n0 + c0);
-            const float4* sp = reinterpret_cast<const float4*>(p.scale + n0 + c0);
-            float v[16];
+          for (int i = 0; i < 4; ++i) {
+            const float4 b4 = __ldg(bp + i), s4 = __ldg(sp + i);
+            v[4 * i + 0] = fmaf(acc[gi][4 * i + 0], s4.x, b4.x); v[4 * i + 1] = fmaf(acc[gi][4 * i + 1], s4.y, b4.y);
+            v[4 * i + 2] = fmaf(acc[gi][4 * i + 2], s4.z, b4.z); v[4 * i + 3] = fmaf(acc[gi][4 * i + 3], s4.w, b4.w);
+          }
+          if (p.relu) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float4 b4 = __ldg(bp + i), s4 = __ldg(sp + i);
-              v[4 * i + 0] = fmaf(acc[g][4 * i + 0], s4.x, b4.x); v[4 * i + 1] = fmaf(acc[g][4 * i + 1], s4.y, b4.y);
-              v[4 * i + 2] = fmaf(acc[g][4 * i + 2], s4.z, b4.z); v[4 * i + 3] = fmaf(acc[g][4 * i + 3], s4.w, b4.w);
-            }
-            if (p.relu) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
-            }
+            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+          }
 #if PE_FP16
-            uint2 h[4], l[4];
+          uint2 h[4], l[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) split4_h(make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]), h[i], l[i]);
-            ov[0] = make_uint4(h[0].x, h[0].y, h[1].x, h[1].y); ov[1] = make_uint4(h[2].x, h[2].y, h[3].x, h[3].y);
-            ov[2] = make_uint4(l[0].x, l[0].y, l[1].x, l[1].y); ov[3] = make_uint4(l[2].x, l[2].y, l[3].x, l[3].y);
+          for (int i = 0; i < 4; ++i) split4_h(make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]), h[i], l[i]);
+          ov[0] = make_uint4(h[0].x, h[0].y, h[1].x, h[1].y); ov[1] = make_uint4(h[2].x, h[2].y, h[3].x, h[3].y);
+          ov[2] = make_uint4(l[0].x, l[0].y, l[1].x, l[1].y); ov[3] = make_uint4(l[2].x, l[2].y, l[3].x, l[3].y);
 #else
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              float4 hi, lo;
-              split4(make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]), hi, lo);
-              ov[i] = make_uint4(__float_as_uint(hi.x), __float_as_uint(hi.y), __float_as_uint(hi.z), __float_as_uint(hi.w));
-              ov[4 + i] = make_uint4(__float_as_uint(lo.x), __float_as_uint(lo.y), __float_as_uint(lo.z), __float_as_uint(lo.w));
-            }
+          for (int i = 0; i < 4; ++i) {
+            float4 hi, lo;
+            split4(make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]), hi, lo);
+            ov[i] = make_uint4(__float_as_uint(hi.x), __float_as_uint(hi.y), __float_as_uint(hi.z), __float_as_uint(hi.w));
+            ov[4 + i] = make_uint4(__float_as_uint(lo.x), __float_as_uint(lo.y), __float_as_uint(lo.z), __float_as_uint(lo.w));
+          }
 #endif
-          }
-          // stage this warp's 32 rows x CHB bytes in shared memory (hardware swizzle pattern of the store tensor map:
-          // conflict-free 16-byte stores), then ONE bulk tensor store writes them as full lines (a per-thread row store
-          // would scatter 16-byte pieces over 32 lines per instruction).  Rows past the tensor end are clipped by TMA.
-          const uint32_t sbuf = st_base + (st_cnt & 1u) * 32u * CHB;
-          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the buffer used two stores ago is free
-          __syncwarp();
-          const uint32_t srow = sbuf + (uint32_t)lane * CHB;
-          // SWIZZLE_128B: 16-byte chunk index ^= row & 7;  SWIZZLE_64B: chunk index ^= (row >> 1) & 3
-          const uint32_t sw = (CHB == 128) ? (lane & 7u) : ((lane >> 1) & 3u);
-#pragma unroll
-          for (int i = 0; i < NV; ++i) st_shared_u4(srow + (((uint32_t)i ^ sw) << 4), ov[i]);
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          __syncwarp();
-          if (lane == 0) {
-            const long long mrow = m0 + mt * 128 + q * 32;
-            if (mrow < p.M) tma_store_2d(&tmO, (n0 + c0) / 16 * CF, (int)mrow, sbuf);
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          }
-          ++st_cnt;
         }
+        // stage this warp's 32 rows x CHB bytes in shared memory (hardware swizzle pattern of the store tensor map:
+        // conflict-free 16-byte stores), then ONE bulk tensor store writes them as full lines (a per-thread row store
+        // would scatter 16-byte pieces over 32 lines per instruction).  Rows past the tensor end are clipped by TMA.
+        const uint32_t sbuf = st_base + (st_cnt & 1u) * 32u * CHB;
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the buffer used two stores ago is free
+        __syncwarp();
+        const uint32_t srow = sbuf + (uint32_t)lane * CHB;
+        // SWIZZLE_128B: 16-byte chunk index ^= row & 7;  SWIZZLE_64B: chunk index ^= (row >> 1) & 3
+        const uint32_t sw = (CHB == 128) ? (lane & 7u) : ((lane >> 1) & 3u);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) st_shared_u4(srow + (((uint32_t)i ^ sw) << 4), ov[i]);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          const long long mrow = m0 + mt * 128 + q * 32;
+          if (mrow < p.M) tma_store_2d(&tmO, (n0 + c0) / 16 * CF, (int)mrow, sbuf);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        ++st_cnt;
       }
       tile += gridDim.x;
       while (tile >= p.tiles_m) { tile -= p.tiles_m; ++nsl; }
@@ -665,8 +733,8 @@ cudaError_t tc_conv_plan_create(TcConvPlan** out, const float* in, float* outp, 
   const int halo_after = ks == 1 ? 0 : Wp + 1;
   const long long Mmax = (long long)max_img * Hp * Wp;
   if (Mmax + 1024 >= (1LL << 31)) return cudaErrorNotSupported;   // TMA row coordinates are int32
-  const size_t stage_bytes = (size_t)4 * 2 * 32 * CHB;   // epilogue store staging
-  const size_t smem_cap = 200 * 1024 - stage_bytes;
+  const size_t stage_bytes = (size_t)EPI_WARPS * 2 * 32 * CHB;   // epilogue store staging
+  const size_t smem_cap = 220 * 1024 - stage_bytes;
   double best = 1e30;
   TcParams bp{};
   size_t bsmem = 0;
@@ -698,12 +766,18 @@ cudaError_t tc_conv_plan_create(TcConvPlan** out, const float* in, float* outp, 
       p.nbA = (R + 255) / 256;
       p.Rpad = ((R + 8 * p.nbA - 1) / (8 * p.nbA)) * (8 * p.nbA);
       p.RB = p.Rpad / p.nbA;
-      p.SA = 2;
       p.nsub = 1; p.Nsub = NC; p.nboxW = 1; p.NCbox = NC;
       const size_t a_bytes = (size_t)p.Rpad * CHB, b_bytes = (size_t)p.TPS * NC * CHB;
+      // ring depths: three activation windows in flight when they fit next to >= 4 weight stages (the window loads come from
+      // HBM: 2 stages left the load path latency-bound, measured), else two
       int SB = 6;
-      while (SB > 3 && p.SA * a_bytes + SB * b_bytes + 4096 > smem_cap) --SB;
-      if (p.SA * a_bytes + SB * b_bytes + 4096 > smem_cap) continue;
+      p.SA = env_int("PE_TC_SA", 3);
+      while (SB > 4 && p.SA * a_bytes + SB * b_bytes + 4096 > smem_cap) --SB;
+      if (p.SA * a_bytes + SB * b_bytes + 4096 > smem_cap) {
+        p.SA = 2; SB = 6;
+        while (SB > 3 && p.SA * a_bytes + SB * b_bytes + 4096 > smem_cap) --SB;
+        if (p.SA * a_bytes + SB * b_bytes + 4096 > smem_cap) continue;
+      }
       p.SB = SB;
       int cols = 32;
       while (cols < ((MT * NC / 16 <= 6) ? 5 : 4) * MT * NC) cols <<= 1;
@@ -737,7 +811,7 @@ cudaError_t tc_conv_plan_create(TcConvPlan** out, const float* in, float* outp, 
   pl->p.bo_mode = env_int("PE_TC_BO_MODE", 1);
   pl->p.dbg = env_int("PE_TC_DBG", 0);
   pl->p.prof = nullptr;
-  if (env_int("PE_TC_PROF", 0)) { cudaMalloc(&pl->p.prof, 148 * 8 * sizeof(long long)); cudaMemset(pl->p.prof, 0, 148 * 8 * sizeof(long long)); }
+  if (env_int("PE_TC_PROF", 0)) { cudaMalloc(&pl->p.prof, 148 * 16 * sizeof(long long)); cudaMemset(pl->p.prof, 0, 148 * 16 * sizeof(long long)); }
   pl->rows_per_img = Hp * Wp;
   pl->smem = bsmem;
   pl->ns = bns;
@@ -753,7 +827,7 @@ cudaError_t tc_conv_plan_create(TcConvPlan** out, const float* in, float* outp, 
   }
   pl->kernel = tc_kernel_for(bp.MT, bp.NC, bp.TPS);
   {
-    cudaError_t e = cudaFuncSetAttribute(pl->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(210 * 1024));
+    cudaError_t e = cudaFuncSetAttribute(pl->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
     if (e != cudaSuccess) { delete pl; return e; }
   }
   pl->num_sms = num_sms;
@@ -772,15 +846,17 @@ cudaError_t tc_conv_launch(TcConvPlan* pl, int nimg, cudaStream_t st) {
   p.tiles_m = (int)((p.M + 128LL * p.MT - 1) / (128LL * p.MT));
   p.total_work = p.tiles_m * pl->ns;
   const unsigned grid = (unsigned)(p.total_work < pl->num_sms ? p.total_work : pl->num_sms);
-  pl->kernel<<<grid, 192, pl->smem, st>>>(pl->tmA, pl->tmW, pl->tmO, p);
+  pl->kernel<<<grid, TC_THREADS, pl->smem, st>>>(pl->tmA, pl->tmW, pl->tmO, p);
   if (p.prof) {
-    long long h[148 * 8];
+    long long h[148 * 16];
     cudaStreamSynchronize(st);
     cudaMemcpy(h, p.prof, sizeof h, cudaMemcpyDeviceToHost);
-    double a[7] = {0, 0, 0, 0, 0, 0, 0};
-    for (unsigned b = 0; b < grid; ++b) for (int k = 0; k < 7; ++k) a[k] += (double)h[b * 8 + k] / grid;
-    fprintf(stderr, "conv_tc prof (NC=%d MT=%d TPS=%d nchunk=%d ntaps=%d work=%d grid=%u): per-CTA cycles total %.0f | wait_b %.0f issue %.0f wait_a %.0f wait_main %.0f wait_corr %.0f res=%d | stages %.0f -> per stage: wait_b %.0f issue %.0f\n",
-            p.NC, p.MT, p.TPS, p.nchunk, p.ntaps, p.total_work, grid, a[4], a[0], a[1], a[2], a[3], a[6], p.res ? 1 : 0, a[5], a[0] / a[5], a[1] / a[5]);
+    for (int role = 0; role < 2; ++role) {
+      double a[7] = {0, 0, 0, 0, 0, 0, 0};
+      for (unsigned b = 0; b < grid; ++b) for (int k = 0; k < 7; ++k) a[k] += (double)h[b * 16 + role * 8 + k] / grid;
+      fprintf(stderr, "conv_tc prof %s (NC=%d MT=%d TPS=%d nchunk=%d ntaps=%d work=%d grid=%u): per-CTA cycles total %.0f | wait_b %.0f issue %.0f wait_a %.0f wait_main %.0f wait_corr %.0f res=%d | stages %.0f -> per stage: total %.0f wait_b %.0f issue %.0f\n",
+              role ? "Y" : "X", p.NC, p.MT, p.TPS, p.nchunk, p.ntaps, p.total_work, grid, a[4], a[0], a[1], a[2], a[3], a[6], p.res ? 1 : 0, a[5], a[4] / a[5], a[0] / a[5], a[1] / a[5]);
+    }
   }
   return cudaGetLastError();
 }
