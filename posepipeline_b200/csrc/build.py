@@ -17,6 +17,7 @@ PRECISION = os.environ.get("PE_PRECISION", "fp16")
 OUT = os.path.join(PKG, "libposeengine.so" if PRECISION == "fp16" else "libposeengine_tf32.so")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "-Xcompiler", "-fno-fast-math", "--fmad=true", f"-DPE_FP16={1 if PRECISION == 'fp16' else 0}"]
+FLAGS += os.environ.get("PE_EXTRA_NVCC_FLAGS", "").split()      # e.g. -DPE_TC_PROFILE=1 (cycle counters in conv_tc)
 
 
 def _digest():
