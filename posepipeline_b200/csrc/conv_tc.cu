@@ -726,47 +726,32 @@ static CUresult encode_nd(CUtensorMap* tm, const void* gptr, int rank, const uin
                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 }
 
-cudaError_t tc_conv_plan_create(TcConvPlan** out, const float* in, float* outp, const float* res, const float* wtc,
-                                const float* bias, int Cin, int Cout, int ks, int relu, int H, int W, int max_img) {
-  if (env_int("PE_TC_DISABLE", 0)) return cudaErrorNotSupported;
-  // ks = 3: 3x3 pad 1;  ks = 1: 1x1;  ks = 2: 2x2 stencil with taps at (+0,+1) rows/cols (no pad) -- the form a
-  // stride-2 3x3 convolution takes over the space-to-depth repack of its input (kernels_simt.cu s2d_kernel)
-  if ((ks != 1 && ks != 2 && ks != 3) || Cin % 16 || Cout % 16 || Cout > 512) return cudaErrorNotSupported;
+cudaError_t tc_conv_launch(TcConvPlan* pl, int nimg, cudaStream_t st);
+
+// One feasible tiling of a layer: N-split, accumulators per CTA, chunks per stage, ring depth.
+struct TcCand {
+  TcParams p;
+  int ns, MT, NC, KC;
+  size_t smem;
+  double cost;      // model estimate (clocks per CTA), used to rank and as the choice when auto-tuning is off
+};
+
+static std::vector<TcCand> tc_enumerate(int Cin, int Cout, int ks, bool has_res, int H, int W, int max_img, int num_sms) {
+  std::vector<TcCand> out;
   const int Hp = H + 2, Wp = W + 2, ntaps = ks * ks, nchunk = Cin / 16;
   const int halo = ks == 3 ? Wp + 1 : 0;
   const int halo_after = ks == 1 ? 0 : Wp + 1;
   const long long Mmax = (long long)max_img * Hp * Wp;
-  if (Mmax + 1024 >= (1LL << 31)) return cudaErrorNotSupported;   // TMA row coordinates are int32
   const size_t smem_total = 227 * 1024 - 2048;                    // dynamic shared memory budget minus alignment slack + barriers
-  double best = 1e30;
-  TcParams bp{};
-  size_t bsmem = 0;
-  int bns = 0, bMT = 0, bNC = 0, bKC = 0;
-  const int force_mt = env_int("PE_TC_MT", 0), force_ns = env_int("PE_TC_NS", 0), force_kc = env_int("PE_TC_KC", 0);
-  int num_sms = 148;
-  {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-  }
+  (void)H; (void)W;
   for (int ns = 1; ns <= 8; ns *= 2) {
     if (Cout % ns) continue;
     const int NC = Cout / ns;
     if (NC % 16 || NC > 128) continue;
-    if (force_ns && ns != force_ns) continue;
     for (int MT = 2; MT >= 1; --MT) {
       for (int KC = (ks == 1 ? 4 : 1); KC >= 1; KC >>= 1) {
         if (nchunk % KC) continue;
         if (!tc_kernel_for(MT, NC, ntaps, KC)) continue;
-        if (force_mt && MT != force_mt) continue;
-        if (force_kc && KC != force_kc) continue;
-        // Measured on B200 (tests/layer_perf.py over the HRNet-W48 layer set, forced MT): two 128-row accumulators per CTA
-        // win when one CTA owns all output channels (Cout <= 64: weights amortised over 256 rows, half the per-tile
-        // fixed cost), one accumulator wins when Cout is split over CTAs; the 96-channel residual layers are the exception
-        if (!force_mt) {
-          const bool want2 = (ns == 1 && NC <= 64 && ks != 1) || (res && ks == 3 && Cout == 96 && nchunk <= 6);
-          if ((MT == 2) != want2 && tc_kernel_for(want2 ? 2 : 1, NC, ntaps, KC)) continue;
-        }
         TcParams p{};
         p.nchunk = nchunk; p.Cout = Cout; p.halo = halo;
         p.nstage = nchunk / KC;
@@ -789,7 +774,7 @@ cudaError_t tc_conv_plan_create(TcConvPlan** out, const float* in, float* outp, 
         // warp, so a third when the warp owns three groups).  Shrink the staging before giving up a third stage.
         const int ngh = (MT * NC / 16 + 1) / 2;
         int S = 0, nstg = 2;
-        const int cand[3] = {res ? std::max(2, std::min(ngh, 3)) : 2, 2, 1};
+        const int cand[3] = {has_res ? std::max(2, std::min(ngh, 3)) : 2, 2, 1};
         for (int ci = 0; ci < 3 && S < 3; ++ci) {
           const size_t staging = (size_t)EPI_WARPS * cand[ci] * 32 * CHB;
           if (staging + 2 * (size_t)p.stage_bytes > smem_total) continue;
@@ -814,69 +799,144 @@ cudaError_t tc_conv_plan_create(TcConvPlan** out, const float* in, float* outp, 
         const double bytes = (double)nchunk * (p.a_bytes + (double)b_chunk);
         const double epi = (double)MT * (NC / 16) * 130.0 * (1 + p.ndrain * 0.5) + 1500.0;
         const double item = std::max(std::max(mma, bytes / 40.0), epi) + (S < 3 ? 0.15 * mma : 0.0)
-                            + ((res && MT * NC / 16 > 6) ? 0.5 * epi : 0.0);   // NG = 8 tiles load the residual late (registers)
-        const double t = items * item + 4000.0;
-        if (t < best) {
-          best = t; bp = p; bns = ns; bMT = MT; bNC = NC; bKC = KC;
-          bsmem = (size_t)S * p.stage_bytes + (size_t)EPI_WARPS * nstg * 32 * CHB + 2048;
-        }
+                            + ((has_res && MT * NC / 16 > 6) ? 0.5 * epi : 0.0);
+        TcCand c;
+        c.p = p; c.ns = ns; c.MT = MT; c.NC = NC; c.KC = KC;
+        c.smem = (size_t)S * p.stage_bytes + (size_t)EPI_WARPS * nstg * 32 * CHB + 2048;
+        c.cost = items * item + 4000.0;
+        out.push_back(c);
       }
     }
   }
-  if (best >= 1e30) return cudaErrorNotSupported;
-  TcConvPlan* pl = new TcConvPlan();
-  pl->p = bp;
+  return out;
+}
+
+// tensor maps + kernel attributes of one candidate
+static cudaError_t tc_build(TcConvPlan* pl, const TcCand& c, const float* in, float* outp, const float* res, const float* wtc,
+                            const float* bias, int Cin, int Cout, int ks, int relu, int H, int W, int max_img, int num_sms) {
+  const int Hp = H + 2, Wp = W + 2, ntaps = ks * ks, nchunk = Cin / 16;
+  const long long Mmax = (long long)max_img * Hp * Wp;
+  pl->p = c.p;
   // weight blob = [per-channel scale 2^-k: Cout floats padded to 64][inverse 2^k: same][packed operand]
   const float* wpack = wtc + 2 * (((Cout + 63) / 64) * 64);
   pl->p.scale_pad = ((Cout + 63) / 64) * 64;
   pl->p.res = res; pl->p.bias = bias; pl->p.scale = wtc;
   pl->p.H = H; pl->p.W = W; pl->p.Hp = Hp; pl->p.Wp = Wp; pl->p.relu = relu;
-  pl->p.prof = nullptr;
-#if PE_TC_PROFILE
-  if (env_int("PE_TC_PROF", 0)) { cudaMalloc(&pl->p.prof, 148 * 16 * sizeof(long long)); cudaMemset(pl->p.prof, 0, 148 * 16 * sizeof(long long)); }
-#endif
   pl->rows_per_img = Hp * Wp;
-  pl->smem = bsmem;
-  pl->ns = bns; pl->MT = bMT; pl->NC = bNC; pl->TAPS = ntaps; pl->KC = bKC;
+  pl->smem = c.smem;
+  pl->ns = c.ns; pl->MT = c.MT; pl->NC = c.NC; pl->TAPS = ntaps; pl->KC = c.KC;
+  pl->num_sms = num_sms;
   const uint32_t cf = PS_CHUNK_FLOATS;    // tensor maps address 4-byte words: one 16-channel chunk = cf words
   CUresult r1, r2, r3;
   {
     const uint64_t dims[2] = {(uint64_t)ps_row_floats(Cin), (uint64_t)Mmax}, str[1] = {(uint64_t)ps_row_floats(Cin) * 4};
-    const uint32_t box[2] = {cf, (uint32_t)bp.RB};
+    const uint32_t box[2] = {cf, (uint32_t)c.p.RB};
     r1 = encode_nd(&pl->tmA, in, 2, dims, str, box);
   }
   {
     // weights [tap][chunk*Cout + n][CHB bytes] as a 3-D tensor: one box = all taps of NC channels of one chunk
     const uint64_t dims[3] = {cf, (uint64_t)nchunk * Cout, (uint64_t)ntaps}, str[2] = {CHB, (uint64_t)nchunk * Cout * CHB};
-    const uint32_t box[3] = {cf, (uint32_t)bNC, (uint32_t)ntaps};
+    const uint32_t box[3] = {cf, (uint32_t)c.NC, (uint32_t)ntaps};
     r2 = encode_nd(&pl->tmW, wpack, 3, dims, str, box);
   }
   {
     const uint64_t dims[2] = {(uint64_t)ps_row_floats(Cout), (uint64_t)Mmax}, str[1] = {(uint64_t)ps_row_floats(Cout) * 4};
     const uint32_t box[2] = {cf, 32};
     r3 = encode_nd(&pl->tmO, outp, 2, dims, str, box);
-  }
-  pl->tmR = pl->tmO;
-  if (res) {
-    const uint64_t dims[2] = {(uint64_t)ps_row_floats(Cout), (uint64_t)Mmax}, str[1] = {(uint64_t)ps_row_floats(Cout) * 4};
-    const uint32_t box[2] = {cf, 32};
-    const CUresult r4 = encode_nd(&pl->tmR, res, 2, dims, str, box);
-    if (r4 != CUDA_SUCCESS) r3 = r4;
+    pl->tmR = pl->tmO;
+    if (res) {
+      const CUresult r4 = encode_nd(&pl->tmR, res, 2, dims, str, box);
+      if (r4 != CUDA_SUCCESS) r3 = r4;
+    }
   }
   if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS || r3 != CUDA_SUCCESS) {
-    fprintf(stderr, "conv_tc: cuTensorMapEncodeTiled failed (%d, %d, %d) Cin=%d Cout=%d RB=%d NC=%d\n", (int)r1, (int)r2, (int)r3, Cin, Cout, bp.RB, bNC);
-    delete pl;
+    fprintf(stderr, "conv_tc: cuTensorMapEncodeTiled failed (%d, %d, %d) Cin=%d Cout=%d RB=%d NC=%d\n", (int)r1, (int)r2, (int)r3, Cin, Cout, c.p.RB, c.NC);
     return cudaErrorInvalidValue;
   }
-  pl->kernel = tc_kernel_for(bMT, bNC, ntaps, bKC);
+  pl->kernel = tc_kernel_for(c.MT, c.NC, ntaps, c.KC);
+  return cudaFuncSetAttribute(pl->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+}
+
+// Tiling choice.  The candidates compute bit-identical results (the accumulation order over K does not depend on the
+// N-split, the tile height or the stage size), so the choice is purely a speed matter and it is MEASURED: at model creation
+// every candidate of a not-yet-seen layer shape runs on the layer's own buffers and the fastest is kept (per process cache
+// keyed by shape).  PE_TC_AUTOTUNE=0 falls back to the cost model; PE_TC_MT / PE_TC_NS / PE_TC_KC pin a tiling.
+#include <map>
+#include <tuple>
+#include <algorithm>
+typedef std::tuple<int, int, int, int, int, int, int> TcShapeKey;   // Cin, Cout, ks, H, W, residual, max_img
+static std::map<TcShapeKey, std::tuple<int, int, int>> g_tc_choice;  // -> ns, MT, KC
+
+cudaError_t tc_conv_plan_create(TcConvPlan** out, const float* in, float* outp, const float* res, const float* wtc,
+                                const float* bias, int Cin, int Cout, int ks, int relu, int H, int W, int max_img) {
+  if (env_int("PE_TC_DISABLE", 0)) return cudaErrorNotSupported;
+  // ks = 3: 3x3 pad 1;  ks = 1: 1x1;  ks = 2: 2x2 stencil with taps at (+0,+1) rows/cols (no pad) -- the form a
+  // stride-2 3x3 convolution takes over the space-to-depth repack of its input (kernels_simt.cu s2d_kernel)
+  if ((ks != 1 && ks != 2 && ks != 3) || Cin % 16 || Cout % 16 || Cout > 512) return cudaErrorNotSupported;
+  if ((long long)max_img * (H + 2) * (W + 2) + 1024 >= (1LL << 31)) return cudaErrorNotSupported;   // TMA row coordinates are int32
+  int num_sms = 148;
   {
-    cudaError_t e = cudaFuncSetAttribute(pl->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
-    if (e != cudaSuccess) { delete pl; return e; }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  pl->num_sms = num_sms;
+  std::vector<TcCand> cands = tc_enumerate(Cin, Cout, ks, res != nullptr, H, W, max_img, num_sms);
+  const int force_mt = env_int("PE_TC_MT", 0), force_ns = env_int("PE_TC_NS", 0), force_kc = env_int("PE_TC_KC", 0);
+  cands.erase(std::remove_if(cands.begin(), cands.end(), [&](const TcCand& c) {
+                return (force_mt && c.MT != force_mt) || (force_ns && c.ns != force_ns) || (force_kc && c.KC != force_kc); }),
+              cands.end());
+  if (cands.empty()) return cudaErrorNotSupported;
+  std::sort(cands.begin(), cands.end(), [](const TcCand& a, const TcCand& b) { return a.cost < b.cost; });
+  const TcShapeKey key(Cin, Cout, ks, H, W, res ? 1 : 0, max_img);
+  const bool pinned = force_mt || force_ns || force_kc;
+  size_t pick = 0;
+  auto hit = g_tc_choice.find(key);
+  if (!pinned && hit != g_tc_choice.end()) {
+    for (size_t i = 0; i < cands.size(); ++i)
+      if (std::make_tuple(cands[i].ns, cands[i].MT, cands[i].KC) == hit->second) pick = i;
+  } else if (!pinned && env_int("PE_TC_AUTOTUNE", 1) && cands.size() > 1) {
+    cudaStream_t ts;
+    cudaEvent_t e0, e1;
+    if (cudaStreamCreateWithFlags(&ts, cudaStreamNonBlocking) != cudaSuccess) return cudaGetLastError();
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best_ms = 1e30f;
+    const size_t ntry = std::min<size_t>(cands.size(), 8);
+    for (size_t i = 0; i < ntry; ++i) {
+      TcConvPlan tmp{};
+      if (tc_build(&tmp, cands[i], in, outp, res, wtc, bias, Cin, Cout, ks, relu, H, W, max_img, num_sms) != cudaSuccess) continue;
+      float ms_min = 1e30f;
+      for (int rep = 0; rep < 3; ++rep) {                 // rep 0 warms the instruction cache and L2
+        cudaEventRecord(e0, ts);
+        tc_conv_launch(&tmp, max_img, ts);
+        cudaEventRecord(e1, ts);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { ms_min = 1e30f; break; }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0) ms_min = std::min(ms_min, ms);
+      }
+      if (env_int("PE_TC_VERBOSE", 0) > 1)
+        fprintf(stderr, "conv_tc tune: Cin=%d Cout=%d ks=%d %dx%d res=%d  NS=%d MT=%d KC=%d S=%d -> %.3f ms (model %.0f)\n", Cin, Cout, ks, H, W,
+                res ? 1 : 0, cands[i].ns, cands[i].MT, cands[i].KC, cands[i].p.S, ms_min, cands[i].cost);
+      if (ms_min < best_ms) { best_ms = ms_min; pick = i; }
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaStreamDestroy(ts);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    g_tc_choice[key] = std::make_tuple(cands[pick].ns, cands[pick].MT, cands[pick].KC);
+  }
+  TcConvPlan* pl = new TcConvPlan();
+  cudaError_t e = tc_build(pl, cands[pick], in, outp, res, wtc, bias, Cin, Cout, ks, relu, H, W, max_img, num_sms);
+  if (e != cudaSuccess) { delete pl; return e; }
+  pl->p.prof = nullptr;
+#if PE_TC_PROFILE
+  if (env_int("PE_TC_PROF", 0)) { cudaMalloc(&pl->p.prof, 148 * 16 * sizeof(long long)); cudaMemset(pl->p.prof, 0, 148 * 16 * sizeof(long long)); }
+#endif
+  const TcCand& c = cands[pick];
   if (env_int("PE_TC_VERBOSE", 0))
-    fprintf(stderr, "conv_tc plan: Cin=%d Cout=%d ks=%d %dx%d  MT=%d NS=%d NC=%d KC=%d S=%d nstg=%d rpg=%d ndrain=%d Rpad=%d RB=%d stage=%u smem=%zu tmem=%d work=%d\n",
-            Cin, Cout, ks, H, W, bMT, bns, bNC, bKC, bp.S, bp.nstg, bp.rpg, bp.ndrain, bp.Rpad, bp.RB, bp.stage_bytes, pl->smem, bp.tmem_cols, bp.total_work);
+    fprintf(stderr, "conv_tc plan: Cin=%d Cout=%d ks=%d %dx%d res=%d  MT=%d NS=%d NC=%d KC=%d S=%d nstg=%d rpg=%d ndrain=%d Rpad=%d RB=%d stage=%u smem=%zu tmem=%d work=%d\n",
+            Cin, Cout, ks, H, W, res ? 1 : 0, c.MT, c.ns, c.NC, c.KC, c.p.S, c.p.nstg, c.p.rpg, c.p.ndrain, c.p.Rpad, c.p.RB, c.p.stage_bytes, c.smem, c.p.tmem_cols,
+            c.p.total_work);
   *out = pl;
   return cudaSuccess;
 }

@@ -363,7 +363,8 @@ extern "C" int pe_model_create(pe_engine* e, const pe_model_desc* desc, const pe
         s2d_floats = std::max(s2d_floats, (size_t)(to.H + 2) * (to.W + 2) * ps_row_floats(4 * op.cin) * maximg);
       }
     }
-    if (s2d_floats) CUM(cudaMalloc(&m->d_s2d, s2d_floats * sizeof(float)));
+    if (s2d_floats) { CUM(cudaMalloc(&m->d_s2d, s2d_floats * sizeof(float))); CUM(cudaMemsetAsync(m->d_s2d, 0, s2d_floats * sizeof(float), e->stream)); }
+    CUM(cudaStreamSynchronize(e->stream));   // weights and zeroed slots are in place: plan creation times candidate tilings on them
     for (int i = 0; i < desc->n_ops; ++i) {
       const pe_op_desc& op = m->ops[i];
       if (op.kind != PE_OP_CONV || op.wtc_off < 0) continue;
