@@ -62,6 +62,7 @@ struct TcParams {
   int ndrain;                // drain groups per tile
   int nstg;                  // epilogue store-staging buffers per warp (1 or 2)
   int relu, tmem_cols;
+  int poll_ns;               // back-off between barrier polls of the producer / epilogue warps (spinning warps burn issue slots and power)
   int tiles_m, total_work;   // persistent schedule: work item w -> (tile = w % tiles_m, n-slice = w / tiles_m)
   uint32_t a_bytes, stage_bytes;
   long long* prof;
@@ -277,7 +278,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int n0 = nsl * NC;
         int j = 0;
         for (int st = 0; st < p.nstage; ++st) {
-          mbar_wait(bar_empty + 8 * r.idx, r.phase ^ 1u);
+          mbar_wait_relaxed(bar_empty + 8 * r.idx, r.phase ^ 1u, p.poll_ns);
           const uint32_t full = bar_full + 8 * r.idx, dst = sRing + r.idx * stage_bytes;
           mbar_expect_tx(full, tx);
 #pragma unroll
@@ -525,7 +526,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #endif
       };
       for (int d = 0; d < ndrain; ++d) {
-        mbar_wait_relaxed(bar_main_full + 8 * dg, dgp, 0);
+        mbar_wait_relaxed(bar_main_full + 8 * dg, dgp, p.poll_ns);
         tc_fence_after();
         // one 16-column group per TMEM wait: tcgen05.ld is throughput-bound (64 clk per x16 load, tools/tmem_bench.cu), so
         // batching the waits buys nothing and costs 16 live registers.  Accumulators stay in the SCALED domain (weights
@@ -549,7 +550,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) mbar_arrive(bar_main_empty + 8 * dg);
         if (++dg == NMAIN) { dg = 0; dgp ^= 1u; }
         if (d == 0 && p.res) {
-          mbar_wait_relaxed(res_bar, tl & 1u, 0);
+          mbar_wait_relaxed(res_bar, tl & 1u, p.poll_ns);
           const uint32_t sw = (CHB == 128) ? (lane & 7u) : ((lane >> 1) & 3u);   // swizzle of this lane's staged row
 #pragma unroll
           for (int gi = 0; gi < NGH; ++gi) {
@@ -581,7 +582,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       while (tile_n >= p.tiles_m) { tile_n -= p.tiles_m; ++nsl_n; }
       // cross terms: committed by MMA warp Y at the end of the tile
       const uint32_t cbuf = tl & 1u;
-      mbar_wait_relaxed(bar_corr_full + 8 * cbuf, (tl >> 1) & 1u, 0);
+      mbar_wait_relaxed(bar_corr_full + 8 * cbuf, (tl >> 1) & 1u, p.poll_ns);
       tc_fence_after();
 #pragma unroll
       for (int gi = 0; gi < NGH; ++gi) {
@@ -822,6 +823,7 @@ static cudaError_t tc_build(TcConvPlan* pl, const TcCand& c, const float* in, fl
   pl->p.scale_pad = ((Cout + 63) / 64) * 64;
   pl->p.res = res; pl->p.bias = bias; pl->p.scale = wtc;
   pl->p.H = H; pl->p.W = W; pl->p.Hp = Hp; pl->p.Wp = Wp; pl->p.relu = relu;
+  pl->p.poll_ns = env_int("PE_TC_POLL_NS", 0);
   pl->rows_per_img = Hp * Wp;
   pl->smem = c.smem;
   pl->ns = c.ns; pl->MT = c.MT; pl->NC = c.NC; pl->TAPS = ntaps; pl->KC = c.KC;

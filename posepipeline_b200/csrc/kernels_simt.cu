@@ -57,67 +57,132 @@ void launch_warp_crop(const uint8_t* frames, int fh, int fw, const int32_t* fram
 // LUT (ToTensor + NormalizeTensor, cfg :132-136, fused).  Images [ncrop, 2*ncrop) are the flip-test
 // pass: they read the crop mirrored in x (== img.flip(3)).
 // =============================================================================================
-__global__ void __launch_bounds__(256) stem_kernel(const uint8_t* __restrict__ crops, int ncrop, int nimg, int ih, int iw,
-                                                   const float* __restrict__ lut,   // [3][256]
-                                                   const float* __restrict__ w,     // [27][64]  (tap-major: (ky*3+kx)*3+c)
-                                                   const float* __restrict__ bias,  // [64]
-                                                   float* __restrict__ out, int oh, int ow) {
-  __shared__ float s_w[27 * 64];
-  __shared__ float s_lut[768];
-  __shared__ float s_b[64];
-  for (int i = threadIdx.x; i < 27 * 64; i += 256) s_w[i] = w[i];
-  for (int i = threadIdx.x; i < 768; i += 256) s_lut[i] = lut[i];
-  if (threadIdx.x < 64) s_b[threadIdx.x] = bias[threadIdx.x];
-  __syncthreads();
+// One CTA = a 16x16 tile of the PADDED output grid of one image, one thread per position, all 64 output channels.
+//   1. the 33x33x3 input patch goes through the normalisation LUT into shared memory once (13 byte loads per thread;
+//      the first version re-read 81 bytes per thread and was load/store-unit bound at 6 TFLOP/s),
+//   2. 27 x 64 FMAs per thread, weights broadcast from shared memory as float4 (same order ky,kx,c as the oracle's
+//      accumulation; out-of-image taps contribute fmaf(0, w, acc) = acc, so padding is exact),
+//   3. the 256-byte PS rows are staged in shared memory (XOR-swizzled 16-byte units) and leave as 4 KB contiguous runs.
+constexpr int STEM_T = 16;                                   // tile edge
+constexpr int STEM_P = 2 * STEM_T + 1;                       // input patch edge
+constexpr int STEM_ROWB = 4 * PS_CHUNK_BYTES;                // bytes of a 64-channel PS row
+constexpr int STEM_IN_FLOATS = (3 * STEM_P * (STEM_P + 1) + 3) & ~3;   // padded so the staged rows behind it stay 16-byte aligned
+constexpr size_t STEM_SMEM = sizeof(float) * (27 * 64 + 768 + 64 + STEM_IN_FLOATS) + (size_t)STEM_T * STEM_T * STEM_ROWB;
+
+__global__ void __launch_bounds__(256, 2) stem_kernel(const uint8_t* __restrict__ crops, int ncrop, int nimg, int ih, int iw,
+                                                      const float* __restrict__ lut,   // [3][256]
+                                                      const float* __restrict__ w,     // [27][64]  (tap-major: (ky*3+kx)*3+c)
+                                                      const float* __restrict__ bias,  // [64]
+                                                      float* __restrict__ out, int oh, int ow) {
+  extern __shared__ __align__(16) uint8_t stem_smem[];
+  float* s_w = reinterpret_cast<float*>(stem_smem);           // [27][64]
+  float* s_lut = s_w + 27 * 64;                               // [768]
+  float* s_b = s_lut + 768;                                   // [64]
+  float* s_in = s_b + 64;                                     // [3][STEM_P][STEM_P + 1]
+  uint8_t* s_out = reinterpret_cast<uint8_t*>(s_in + STEM_IN_FLOATS);          // [256 positions][STEM_ROWB], swizzled
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 27 * 64; i += 256) s_w[i] = w[i];
+  for (int i = tid; i < 768; i += 256) s_lut[i] = lut[i];
+  if (tid < 64) s_b[tid] = bias[tid];
   const int Hp = oh + 2, Wp = ow + 2;
-  const long long M = (long long)nimg * Hp * Wp;
-  const long long m = (long long)blockIdx.x * 64 + (threadIdx.x >> 2);
-  if (m >= M) return;
-  const int chunk = threadIdx.x & 3;  // 16 output channels
-  const int img = (int)(m / (Hp * Wp));
-  const int r = (int)(m % (Hp * Wp));
-  const int py = r / Wp, px = r % Wp;
-  float* orow = out + m * ps_row_floats(64);
-  if (py < 1 || py > oh || px < 1 || px > ow) {
-#pragma unroll
-    for (int i = 0; i < 16; i += 4) ps_zero4(orow, chunk * 16 + i);
-    return;
-  }
+  const int img = blockIdx.z;
+  const int ty0 = blockIdx.y * STEM_T, tx0 = blockIdx.x * STEM_T;      // tile origin on the padded grid
   const bool flip = img >= ncrop;
   const uint8_t* c0 = crops + (size_t)(flip ? img - ncrop : img) * ih * iw * 3;
-  float acc[16];
+  __syncthreads();                                                      // LUT ready
+  // input patch: rows iy0 .. iy0 + 32, cols ix0 .. ix0 + 32, where output (py, px) reads input (2(py-1)-1+ky, 2(px-1)-1+kx)
+  const int iy0 = 2 * (ty0 - 1) - 1, ix0 = 2 * (tx0 - 1) - 1;
+  for (int i = tid; i < STEM_P * STEM_P; i += 256) {
+    const int ry = i / STEM_P, rx = i - ry * STEM_P;
+    const int iy = iy0 + ry, ix = ix0 + rx;
+    float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+    if (iy >= 0 && iy < ih && ix >= 0 && ix < iw) {
+      const uint8_t* pix = c0 + ((size_t)iy * iw + (flip ? iw - 1 - ix : ix)) * 3;
+      v0 = s_lut[pix[0]]; v1 = s_lut[256 + pix[1]]; v2 = s_lut[512 + pix[2]];
+    }
+    s_in[(0 * STEM_P + ry) * (STEM_P + 1) + rx] = v0;
+    s_in[(1 * STEM_P + ry) * (STEM_P + 1) + rx] = v1;
+    s_in[(2 * STEM_P + ry) * (STEM_P + 1) + rx] = v2;
+  }
+  __syncthreads();
+  const int ly = tid >> 4, lx = tid & 15;
+  const int py = ty0 + ly, px = tx0 + lx;
+  const bool inside = py < Hp && px < Wp;
+  const bool interior = py >= 1 && py <= oh && px >= 1 && px <= ow;
+  uint4* srow = reinterpret_cast<uint4*>(s_out + (size_t)tid * STEM_ROWB);
+  constexpr int UNITS = STEM_ROWB / 16;                                 // 16-byte units per row
+  if (!interior) {
 #pragma unroll
-  for (int i = 0; i < 16; ++i) acc[i] = s_b[chunk * 16 + i];
-  const int oy = py - 1, ox = px - 1;
+    for (int u = 0; u < UNITS; ++u) srow[u] = make_uint4(0u, 0u, 0u, 0u);
+  } else {
+    float vin[27];
 #pragma unroll
-  for (int ky = 0; ky < 3; ++ky) {
-    const int iy = oy * 2 - 1 + ky;
-    if (iy < 0 || iy >= ih) continue;
+    for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-    for (int kx = 0; kx < 3; ++kx) {
-      const int ix = ox * 2 - 1 + kx;
-      if (ix < 0 || ix >= iw) continue;
-      const int sxx = flip ? iw - 1 - ix : ix;
-      const uint8_t* pix = c0 + ((size_t)iy * iw + sxx) * 3;
+      for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const float v = s_lut[c * 256 + pix[c]];
-        const float* wr = s_w + ((ky * 3 + kx) * 3 + c) * 64 + chunk * 16;
+        for (int c = 0; c < 3; ++c) vin[(ky * 3 + kx) * 3 + c] = s_in[(c * STEM_P + 2 * ly + ky) * (STEM_P + 1) + 2 * lx + kx];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) acc[i] = fmaf(v, wr[i], acc[i]);
+    for (int q = 0; q < 4; ++q) {                                       // 16 output channels = one PS chunk per pass
+      float acc[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc[i] = s_b[q * 16 + i];
+#pragma unroll
+      for (int t = 0; t < 27; ++t) {
+        const float4* wr = reinterpret_cast<const float4*>(s_w + t * 64 + q * 16);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 w4 = wr[i];
+          acc[4 * i + 0] = fmaf(vin[t], w4.x, acc[4 * i + 0]); acc[4 * i + 1] = fmaf(vin[t], w4.y, acc[4 * i + 1]);
+          acc[4 * i + 2] = fmaf(vin[t], w4.z, acc[4 * i + 2]); acc[4 * i + 3] = fmaf(vin[t], w4.w, acc[4 * i + 3]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc[i] = fmaxf(acc[i], 0.f);
+      // chunk q of the row: PS_CHUNK_BYTES / 16 units, stored at unit ^ (tid & 7) inside its group of 8
+      constexpr int UPC = PS_CHUNK_BYTES / 16;
+      uint4 o[UPC];
+#if PE_FP16
+      uint2 h[4], l[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) split4_h(make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]), h[i], l[i]);
+      o[0] = make_uint4(h[0].x, h[0].y, h[1].x, h[1].y); o[1] = make_uint4(h[2].x, h[2].y, h[3].x, h[3].y);
+      o[2] = make_uint4(l[0].x, l[0].y, l[1].x, l[1].y); o[3] = make_uint4(l[2].x, l[2].y, l[3].x, l[3].y);
+#else
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float4 hi, lo;
+        split4(make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]), hi, lo);
+        o[i] = make_uint4(__float_as_uint(hi.x), __float_as_uint(hi.y), __float_as_uint(hi.z), __float_as_uint(hi.w));
+        o[4 + i] = make_uint4(__float_as_uint(lo.x), __float_as_uint(lo.y), __float_as_uint(lo.z), __float_as_uint(lo.w));
+      }
+#endif
+#pragma unroll
+      for (int i = 0; i < UPC; ++i) {
+        const int u = q * UPC + i;
+        srow[(u & ~7) | ((u & 7) ^ (tid & 7))] = o[i];
       }
     }
   }
-#pragma unroll
-  for (int i = 0; i < 16; i += 4) {
-    ps_store4(orow, chunk * 16 + i, make_float4(fmaxf(acc[i], 0.f), fmaxf(acc[i + 1], 0.f), fmaxf(acc[i + 2], 0.f), fmaxf(acc[i + 3], 0.f)));
+  __syncthreads();
+  // copy out: tile row ly' = 16 positions x STEM_ROWB contiguous bytes in global memory
+  const size_t img_row0 = (size_t)img * Hp * Wp;
+  for (int i = tid; i < STEM_T * STEM_T * UNITS; i += 256) {
+    const int pos = i / UNITS, u = i - pos * UNITS;
+    const int y = ty0 + (pos >> 4), x = tx0 + (pos & 15);
+    if (y >= Hp || x >= Wp) continue;
+    const uint4 v = reinterpret_cast<const uint4*>(s_out + (size_t)pos * STEM_ROWB)[(u & ~7) | ((u & 7) ^ (pos & 7))];
+    reinterpret_cast<uint4*>(reinterpret_cast<char*>(out) + (img_row0 + (size_t)y * Wp + x) * STEM_ROWB)[u] = v;
   }
+  (void)inside; (void)nimg;
 }
 
 void launch_stem(const uint8_t* crops, int ncrop, int nimg, int ih, int iw, const float* lut, const float* w,
                  const float* bias, float* out, int oh, int ow, cudaStream_t st) {
-  long long M = (long long)nimg * (oh + 2) * (ow + 2);
-  stem_kernel<<<(unsigned)((M + 63) / 64), 256, 0, st>>>(crops, ncrop, nimg, ih, iw, lut, w, bias, out, oh, ow);
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STEM_SMEM); attr = true; }
+  dim3 grid((ow + 2 + STEM_T - 1) / STEM_T, (oh + 2 + STEM_T - 1) / STEM_T, nimg);
+  stem_kernel<<<grid, 256, STEM_SMEM, st>>>(crops, ncrop, nimg, ih, iw, lut, w, bias, out, oh, ow);
 }
 
 // =============================================================================================
@@ -303,33 +368,86 @@ struct FuseArgs {
   int C, H, W, nimg, relu;
 };
 
+// One thread per (padded position, 16-channel chunk): a chunk is PS_CHUNK_BYTES contiguous bytes, so every access is a
+// run of 16-byte vectors and consecutive threads touch consecutive chunks (HBM-bound op: 4-channel threads with 8-byte
+// accesses reached 27 % of the copy bandwidth).
+__device__ __forceinline__ void chunk_load16(const float* row, int chunk, float (&v)[16]) {
+  const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(row) + (size_t)chunk * PS_CHUNK_BYTES);
+#if PE_FP16
+  const uint4 h0 = __ldg(p), h1 = __ldg(p + 1), l0 = __ldg(p + 2), l1 = __ldg(p + 3);
+  const uint32_t hw[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+  const uint32_t lw[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[i]));
+    const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[i]));
+    v[2 * i] = hf.x + lf.x; v[2 * i + 1] = hf.y + lf.y;
+  }
+#else
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint4 h = __ldg(p + i), l = __ldg(p + 4 + i);
+    v[4 * i + 0] = __uint_as_float(h.x) + __uint_as_float(l.x); v[4 * i + 1] = __uint_as_float(h.y) + __uint_as_float(l.y);
+    v[4 * i + 2] = __uint_as_float(h.z) + __uint_as_float(l.z); v[4 * i + 3] = __uint_as_float(h.w) + __uint_as_float(l.w);
+  }
+#endif
+}
+
+__device__ __forceinline__ void chunk_store16(float* row, int chunk, const float (&v)[16]) {
+  uint4* p = reinterpret_cast<uint4*>(reinterpret_cast<char*>(row) + (size_t)chunk * PS_CHUNK_BYTES);
+#if PE_FP16
+  uint2 h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) split4_h(make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]), h[i], l[i]);
+  p[0] = make_uint4(h[0].x, h[0].y, h[1].x, h[1].y); p[1] = make_uint4(h[2].x, h[2].y, h[3].x, h[3].y);
+  p[2] = make_uint4(l[0].x, l[0].y, l[1].x, l[1].y); p[3] = make_uint4(l[2].x, l[2].y, l[3].x, l[3].y);
+#else
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float4 hi, lo;
+    split4(make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]), hi, lo);
+    p[i] = make_uint4(__float_as_uint(hi.x), __float_as_uint(hi.y), __float_as_uint(hi.z), __float_as_uint(hi.w));
+    p[4 + i] = make_uint4(__float_as_uint(lo.x), __float_as_uint(lo.y), __float_as_uint(lo.z), __float_as_uint(lo.w));
+  }
+#endif
+}
+
 __global__ void __launch_bounds__(256) fuse_kernel(FuseArgs a) {
-  const int c4 = a.C >> 2;
-  const long long total = (long long)a.nimg * (a.H + 2) * (a.W + 2) * c4;
+  const int nch = a.C >> 4;
+  const long long total = (long long)a.nimg * (a.H + 2) * (a.W + 2) * nch;
   const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
   if (t >= total) return;
-  const int c = (int)(t % c4) * 4;
-  const long long m = t / c4;
+  const int chunk = (int)(t % nch);
+  const long long m = t / nch;
   const int Hp = a.H + 2, Wp = a.W + 2;
   const int img = (int)(m / (Hp * Wp));
   const int r = (int)(m % (Hp * Wp));
   const int py = r / Wp, px = r % Wp;
   const int rowF = ps_row_floats(a.C);
   float* orow = a.out + m * rowF;
+  uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<char*>(orow) + (size_t)chunk * PS_CHUNK_BYTES);
   if (py < 1 || py > a.H || px < 1 || px > a.W) {
-    ps_zero4(orow, c);
+#pragma unroll
+    for (int i = 0; i < PS_CHUNK_BYTES / 16; ++i) op[i] = make_uint4(0u, 0u, 0u, 0u);
     return;
   }
-  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int j = 0; j < a.n_in; ++j) {
+  float s[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s[i] = 0.f;
+  for (int j = 0; j < a.n_in; ++j) {                   // summed in branch order (fp32 addition order of the reference)
     const int u = a.up[j];
     const int h = a.H / u, w = a.W / u;
     const long long row = ((long long)img * (h + 2) + (py - 1) / u + 1) * (w + 2) + (px - 1) / u + 1;
-    const float4 v = ps_load4(a.in[j] + row * rowF, c);
-    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    float v[16];
+    chunk_load16(a.in[j] + row * rowF, chunk, v);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s[i] += v[i];
   }
-  if (a.relu) { s.x = fmaxf(s.x, 0.f); s.y = fmaxf(s.y, 0.f); s.z = fmaxf(s.z, 0.f); s.w = fmaxf(s.w, 0.f); }
-  ps_store4(orow, c, s);
+  if (a.relu) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s[i] = fmaxf(s[i], 0.f);
+  }
+  chunk_store16(orow, chunk, s);
 }
 
 void launch_fuse(const float* const* in, const int* up, int n_in, float* out, int C, int H, int W, int nimg, int relu,
@@ -337,7 +455,7 @@ void launch_fuse(const float* const* in, const int* up, int n_in, float* out, in
   FuseArgs a;
   for (int j = 0; j < 4; ++j) { a.in[j] = j < n_in ? in[j] : nullptr; a.up[j] = j < n_in ? up[j] : 1; }
   a.n_in = n_in; a.out = out; a.C = C; a.H = H; a.W = W; a.nimg = nimg; a.relu = relu;
-  long long total = (long long)nimg * (H + 2) * (W + 2) * (C / 4);
+  long long total = (long long)nimg * (H + 2) * (W + 2) * (C / 16);
   fuse_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a);
 }
 

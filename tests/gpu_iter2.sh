@@ -1,0 +1,9 @@
+#!/bin/bash
+TAG=${1:-it}
+mkdir -p gpurun_out
+timeout 300 python tests/layer_perf.py 128 2 > gpurun_out/layers_$TAG.txt 2>&1; head -30 gpurun_out/layers_$TAG.txt
+timeout 1200 python -m pytest tests -m gpu -q -s -x 2>&1 | grep -E "worst layers|keypoint \|dx\||passed|failed|Error|error|assert" | cut -c1-300 > gpurun_out/pytest_$TAG.log; cat gpurun_out/pytest_$TAG.log
+for ns in 0 100 400; do
+PE_TC_POLL_NS=$ns timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; python -c "
+import json; d=json.load(open('gpurun_out/bench_$TAG.json')); print('poll_ns=$ns', {k:d[k] for k in ('value','ms_per_step')}, d['e2e']['value'], d['roofline']['achieved'], d['clocks'])"; tail -3 gpurun_out/bench_$TAG.err
+done
