@@ -255,6 +255,7 @@ struct pe_model {
   std::vector<pe_tensor_desc> tensors;
   std::vector<float*> slots;
   std::vector<TcConvPlan*> tc;   // per op, or nullptr
+  std::vector<char> tc_s2d;      // per op: 1 = the stride-2 plan reads the space-to-depth scratch (else TMA gathers from the input)
   float* d_w = nullptr;
   float* d_s2d = nullptr;        // space-to-depth scratch for stride-2 convolutions on the tensor-core path
   float* d_lut = nullptr;
@@ -354,6 +355,7 @@ extern "C" int pe_model_create(pe_engine* e, const pe_model_desc* desc, const pe
   }
   // tensor-core plans for eligible convolutions
   m->tc.assign(desc->n_ops, nullptr);
+  m->tc_s2d.assign(desc->n_ops, 0);
   if (desc->use_tensor_cores) {
     size_t s2d_floats = 0;
     for (int i = 0; i < desc->n_ops; ++i) {
@@ -372,10 +374,17 @@ extern "C" int pe_model_create(pe_engine* e, const pe_model_desc* desc, const pe
       const pe_tensor_desc& to = m->tensors[op.out];
       TcConvPlan* plan = nullptr;
       const bool s2 = op.stride == 2;
-      cudaError_t ce = tc_conv_plan_create(&plan, s2 ? m->d_s2d : act_ptr(m, op.in[0]), act_ptr(m, op.out),
-                                           op.residual >= 0 ? act_ptr(m, op.residual) : nullptr, m->d_w + op.wtc_off,
-                                           m->d_w + op.b_off, s2 ? 4 * op.cin : op.cin, op.cout, s2 ? 2 : op.ksize, op.relu,
-                                           to.H, to.W, maximg);
+      cudaError_t ce = cudaErrorNotSupported;
+      if (s2)   // first choice: TMA gathers the strided rows from the input tensor itself
+        ce = tc_conv_plan_create(&plan, nullptr, act_ptr(m, op.out), nullptr, m->d_w + op.wtc_off, m->d_w + op.b_off, 4 * op.cin, op.cout, 2,
+                                 op.relu, to.H, to.W, maximg, act_ptr(m, op.in[0]));
+      if (ce == cudaErrorNotSupported) {
+        ce = tc_conv_plan_create(&plan, s2 ? m->d_s2d : act_ptr(m, op.in[0]), act_ptr(m, op.out),
+                                 op.residual >= 0 ? act_ptr(m, op.residual) : nullptr, m->d_w + op.wtc_off,
+                                 m->d_w + op.b_off, s2 ? 4 * op.cin : op.cin, op.cout, s2 ? 2 : op.ksize, op.relu,
+                                 to.H, to.W, maximg);
+        if (ce == cudaSuccess && s2) m->tc_s2d[i] = 1;
+      }
       if (ce == cudaSuccess) m->tc[i] = plan;
       else if (ce != cudaErrorNotSupported) {
         int rc = fail(PE_ERR_CUDA, "tensor-core plan for op %d failed: %s", i, cudaGetErrorString(ce));
@@ -419,7 +428,7 @@ static int forward(pe_model* m, int ncrop, int nimg) {
       case PE_OP_CONV: {
         const pe_tensor_desc& ti = m->tensors[op.in[0]];
         if (m->tc[i]) {
-          if (op.stride == 2) { launch_s2d(act_ptr(m, op.in[0]), op.cin, ti.H, ti.W, nimg, m->d_s2d, to.H, to.W, st); ++m->launches; }
+          if (m->tc_s2d[i]) { launch_s2d(act_ptr(m, op.in[0]), op.cin, ti.H, ti.W, nimg, m->d_s2d, to.H, to.W, st); ++m->launches; }
           cudaError_t ce = tc_conv_launch(m->tc[i], nimg, st);
           if (ce != cudaSuccess) return fail(PE_ERR_CUDA, "tensor-core conv op %zu: %s", i, cudaGetErrorString(ce));
         } else {
@@ -686,12 +695,16 @@ extern "C" int pe_conv_test(pe_engine* e, const float* in_nchw, int32_t nimg, in
     if (!w_tc) { rc = fail(PE_ERR_INVALID, "w_tc is NULL"); goto done; }
     CT(cudaMalloc(&d_wtc, wtc_floats * sizeof(float)));
     CT(cudaMemcpyAsync(d_wtc, w_tc, wtc_floats * sizeof(float), cudaMemcpyHostToDevice, st));
-    if (stride == 2) {
-      CT(cudaMalloc(&d_s, rows * ps_row_floats(4 * Cin) * sizeof(float)));
-      launch_s2d(d_in, Cin, Hi, Wi, nimg, d_s, H, W, st);
+    cudaError_t ce = cudaErrorNotSupported;
+    if (stride == 2) ce = tc_conv_plan_create(&plan, nullptr, d_out, nullptr, d_wtc, d_b, 4 * Cin, Cout, 2, relu, H, W, nimg, d_in);
+    if (ce == cudaErrorNotSupported) {
+      if (stride == 2) {
+        CT(cudaMalloc(&d_s, rows * ps_row_floats(4 * Cin) * sizeof(float)));
+        launch_s2d(d_in, Cin, Hi, Wi, nimg, d_s, H, W, st);
+      }
+      ce = tc_conv_plan_create(&plan, stride == 2 ? d_s : d_in, d_out, d_res, d_wtc, d_b, stride == 2 ? 4 * Cin : Cin, Cout,
+                               stride == 2 ? 2 : ks, relu, H, W, nimg);
     }
-    cudaError_t ce = tc_conv_plan_create(&plan, stride == 2 ? d_s : d_in, d_out, d_res, d_wtc, d_b, stride == 2 ? 4 * Cin : Cin, Cout,
-                                         stride == 2 ? 2 : ks, relu, H, W, nimg);
     if (ce != cudaSuccess) { rc = fail(PE_ERR_CUDA, "tc_conv_plan_create: %s", cudaGetErrorString(ce)); goto done; }
     CT(tc_conv_launch(plan, nimg, st));
   } else {

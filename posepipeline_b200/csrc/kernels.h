@@ -29,7 +29,10 @@ cudaError_t launch_decode(const float* hm, const float* hm_flip, const int* flip
 
 // Shifted-row GEMM on tensor cores (conv_tc.cu).  Returns cudaErrorNotSupported for shapes it does not cover.
 struct TcConvPlan;
+// gather_src != nullptr (ks = 2 only): the 2x2 layer is a stride-2 3x3 convolution whose space-to-depth input is gathered by
+// TMA from gather_src (the original [img][2H+2][2W+2][Cin/4] tensor); `in` is then unused and no s2d copy is needed.
 cudaError_t tc_conv_plan_create(TcConvPlan** plan, const float* in, float* out, const float* res, const float* wtc,
-                                const float* bias, int Cin, int Cout, int ks, int relu, int H, int W, int max_img);
+                                const float* bias, int Cin, int Cout, int ks, int relu, int H, int W, int max_img,
+                                const float* gather_src = nullptr);
 void tc_conv_plan_destroy(TcConvPlan* plan);
 cudaError_t tc_conv_launch(TcConvPlan* plan, int nimg, cudaStream_t st);
