@@ -3,9 +3,11 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <limits>
 #include <string>
 #include <vector>
+#include <map>
 
 #include "../../include/poseengine.h"
 #include "kernels.h"
@@ -275,6 +277,10 @@ struct pe_model {
   size_t ev_used = 0;
   cudaEvent_t ev_fwd0 = nullptr, ev_fwd1 = nullptr;
   double acc_conv_ms = 0, acc_total_ms = 0; int64_t acc_conv_launches = 0;
+  // CUDA graphs of the forward, one per (ncrop, nimg): the layer program is a static launch sequence, so from the second
+  // forward of a batch size on it is replayed as one graph launch (no per-kernel launch gaps; PE_GRAPH=0 disables)
+  struct FwdGraph { cudaGraphExec_t exec = nullptr; int64_t launches = 0; int seen = 0; };
+  std::map<std::pair<int, int>, FwdGraph> graphs;
   std::vector<double> op_ms;       // per-op accumulated device time while profiling
   std::vector<int> ev_op;          // op index of each recorded event pair
 };
@@ -296,6 +302,7 @@ extern "C" int pe_model_destroy(pe_model* m) {
   if (!m) return PE_OK;
   cudaSetDevice(m->e->device);
   cudaStreamSynchronize(m->e->stream);
+  for (auto& g : m->graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
   for (auto* p : m->tc) if (p) tc_conv_plan_destroy(p);
   for (auto* p : m->slots) if (p) cudaFree(p);
   cudaFree(m->d_w); cudaFree(m->d_s2d); cudaFree(m->d_lut); cudaFree(m->d_perm); cudaFree(m->d_crops); cudaFree(m->d_minv);
@@ -399,8 +406,42 @@ extern "C" int pe_model_create(pe_engine* e, const pe_model_desc* desc, const pe
   return PE_OK;
 }
 
+static int forward_eager(pe_model* m, int ncrop, int nimg);
+
 // run the layer program on `nimg` images whose uint8 crops are in d_crops (ncrop of them)
 static int forward(pe_model* m, int ncrop, int nimg) {
+  static const bool use_graph = !(getenv("PE_GRAPH") && atoi(getenv("PE_GRAPH")) == 0);
+  if (m->profile || !use_graph) return forward_eager(m, ncrop, nimg);
+  cudaStream_t st = m->e->stream;
+  pe_model::FwdGraph& g = m->graphs[std::make_pair(ncrop, nimg)];
+  if (g.exec) {
+    CU(cudaGraphLaunch(g.exec, st));
+    m->launches += g.launches;
+    m->nimg_last = nimg; m->ncrop_last = ncrop;
+    return PE_OK;
+  }
+  if (g.seen++ == 0) return forward_eager(m, ncrop, nimg);       // first time: eager (one-time attribute calls, warm-up)
+  const int64_t l0 = m->launches;
+  cudaGraph_t graph = nullptr;
+  CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  const int rc = forward_eager(m, ncrop, nimg);
+  const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+  if (rc != PE_OK || ce != cudaSuccess || !graph) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    g.seen = -1000000;                                           // do not try again for this batch size
+    return rc != PE_OK ? rc : forward_eager(m, ncrop, nimg);
+  }
+  g.launches = m->launches - l0;
+  const cudaError_t ci = cudaGraphInstantiate(&g.exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ci != cudaSuccess) { g.exec = nullptr; g.seen = -1000000; cudaGetLastError(); return forward_eager(m, ncrop, nimg); }
+  CU(cudaGraphLaunch(g.exec, st));
+  m->nimg_last = nimg; m->ncrop_last = ncrop;
+  return PE_OK;
+}
+
+static int forward_eager(pe_model* m, int ncrop, int nimg) {
   cudaStream_t st = m->e->stream;
   const pe_model_desc& d = m->d;
   m->ev_used = 0;
