@@ -827,10 +827,10 @@ static std::vector<TcCand> tc_enumerate(int Cin, int Cout, int ks, bool has_res,
         if (p.stage_bytes % (8 * CHB)) continue;                    // stage bases keep the swizzle phase (pattern period: 8 rows)
         // ring depth: as many stages as fit, at most 4.  Store-staging buffers per epilogue warp: two alternate for the output
         // stores; residual layers land the residual chunks of the next tile in them (one buffer per 16-column group of the
-        // warp, so a third when the warp owns three groups).  Shrink the staging before giving up a third stage.
+        // warp, so three or four when the warp owns that many groups).  Shrink the staging before giving up a third stage.
         const int ngh = (MT * NC / 16 + 1) / 2;
         int S = 0, nstg = 2;
-        const int cand[3] = {has_res ? std::max(2, std::min(ngh, 3)) : 2, 2, 1};
+        const int cand[3] = {has_res ? std::max(2, std::min(ngh, 4)) : 2, 2, 1};
         for (int ci = 0; ci < 3 && S < 3; ++ci) {
           const size_t staging = (size_t)EPI_WARPS * cand[ci] * 32 * CHB;
           if (staging + 2 * (size_t)p.stage_bytes > smem_total) continue;
