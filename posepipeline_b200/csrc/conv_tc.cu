@@ -64,6 +64,7 @@ struct TcParams {
   int gather;                // 2x2 layers: 1 = the activation windows are gathered by TMA from the ORIGINAL stride-2 input (no s2d copy)
   int cpp;                   // gather: 16-channel chunks per input parity (py,px)
   int relu, tmem_cols;
+  uint32_t div_hpwp_mul, div_hpwp_sh, div_wp_mul, div_wp_sh;   // exact n / (Hp*Wp) and n / Wp for n < 2^31: (n * mul) >> sh (64-bit product)
   int poll_ns;               // back-off between barrier polls of the producer / epilogue warps (spinning warps burn issue slots and power)
   int tiles_m, total_work;   // persistent schedule: work item w -> (tile = w % tiles_m, n-slice = w / tiles_m)
   uint32_t a_bytes, stage_bytes;
@@ -212,6 +213,20 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, int c0, int 
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
                ::"l"((uint64_t)tm), "r"(c0), "r"(c1), "r"(src)
                : "memory");
+}
+
+// n / d for n < 2^31 with host-computed mul = ceil(2^sh / d), sh = 31 + ceil(log2 d): exact, two instructions instead of a
+// ~100-clock runtime division (the epilogue's per-tile geometry cost 700 clocks with `/` and `%`)
+__device__ __forceinline__ uint32_t fastdiv(uint32_t n, uint32_t mul, uint32_t sh) { return (uint32_t)(((uint64_t)n * mul) >> sh); }
+
+// wait until at most n of this thread's bulk store groups still have to READ their shared-memory source
+__device__ __forceinline__ void bulk_wait_read(int n) {
+  switch (n) {
+    case 0: asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); break;
+    case 1: asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); break;
+    case 2: asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory"); break;
+    default: asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory"); break;
+  }
 }
 
 // Ring cursor without integer division (the issue loops are latency-critical: ONE warp's scalar instruction stream
@@ -480,7 +495,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 #if PE_TC_PROFILE
     if (p.prof && lane == 0) {
-      long long* o = p.prof + (size_t)blockIdx.x * 16 + (roleX ? 0 : 8);
+      long long* o = p.prof + (size_t)blockIdx.x * 32 + (roleX ? 0 : 8);
       o[0] = c_wf; o[1] = c_is; o[2] = c_wm; o[3] = c_wc; o[4] = clock64() - c_t0; o[5] = c_st;
     }
 #endif
@@ -497,7 +512,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
     const int hpwp = p.Hp * p.Wp;
     const uint32_t st_base = sStage + (uint32_t)(warp - 2) * (uint32_t)p.nstg * 32u * CHB;
-    uint32_t st_cnt = 0;
+    uint32_t st_slot = 0;
     uint32_t tl = 0, dg = 0, dgp = 0;
     int tile = blockIdx.x % p.tiles_m, nsl = blockIdx.x / p.tiles_m;
     constexpr int NV = CHB / 16;                         // 16-byte vectors per row chunk
@@ -509,7 +524,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t res_bar = bar_res + 8 * (uint32_t)(warp - 2);
     auto res_issue = [&](int tile_, int nsl_) {
       if (lane == 0) {
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");       // this warp's output stores have read the buffers
+        bulk_wait_read(0);                                                   // this warp's output stores have read the buffers
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         uint32_t nb = 0;
 #pragma unroll
@@ -524,7 +539,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     };
-    if (p.res && blockIdx.x < p.total_work) res_issue(tile, nsl);
+    // When: measured, a TMA store takes ~1000 clocks to read its 2 KB source under load, so waiting for the stores at the end
+    // of a tile stalled every epilogue warp that long.  Layers with >= 3 drain groups request a tile's residual after its
+    // FIRST drain (the previous tile's stores are long done) and add it after the LAST (an epilogue that is behind runs its
+    // drains back to back, so the distance must be several drains); layers with fewer (1x1) request the next tile's at the end
+    // of the current one.
+    const bool res_lazy = p.res && ndrain >= 3;
+    if (p.res && !res_lazy && blockIdx.x < p.total_work) res_issue(tile, nsl);
+#if PE_TC_PROFILE
+    long long e_wm = 0, e_dr = 0, e_rs = 0, e_wc = 0, e_co = 0, e_fi = 0, e_ri = 0, e_tc = 0, e_f1 = 0, e_f2 = 0, e_f3 = 0, e_f4 = 0, e_t = clock64();
+    const long long e_t0 = e_t;
+#define EPI_TICK(v) { const long long _c = clock64(); v += _c - e_t; e_t = _c; }
+#else
+#define EPI_TICK(v)
+#endif
     for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++tl) {
       const long long m0 = (long long)tile * 128 * MT;
       const int n0 = nsl * NC;
@@ -534,9 +562,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) {
         const long long m = m0 + mt * 128 + q * 32 + lane;
-        if (m < p.M) {
-          const int r = (int)((unsigned)m % (unsigned)hpwp);           // M < 2^31 (asserted on the host)
-          const int py = r / p.Wp, px = r - py * p.Wp;
+        if (m < p.M) {                                                   // M < 2^31 (asserted on the host)
+          const uint32_t r = (uint32_t)m - fastdiv((uint32_t)m, p.div_hpwp_mul, p.div_hpwp_sh) * (uint32_t)hpwp;
+          const int py = (int)fastdiv(r, p.div_wp_mul, p.div_wp_sh), px = (int)r - py * p.Wp;
           if (py >= 1 && py <= p.H && px >= 1 && px <= p.W) interior |= 1u << mt;
         }
       }
@@ -571,9 +599,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
 #endif
       };
+      EPI_TICK(e_tc)
       for (int d = 0; d < ndrain; ++d) {
         mbar_wait_relaxed(bar_main_full + 8 * dg, dgp, p.poll_ns);
         tc_fence_after();
+        EPI_TICK(e_wm)
         // one 16-column group per TMEM wait: tcgen05.ld is throughput-bound (64 clk per x16 load, tools/tmem_bench.cu), so
         // batching the waits buys nothing and costs 16 live registers.  Accumulators stay in the SCALED domain (weights
         // were multiplied by 2^k per channel); the residual is brought into that domain when it is added and the final
@@ -595,7 +625,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_main_empty + 8 * dg);
         if (++dg == NMAIN) { dg = 0; dgp ^= 1u; }
-        if (d == 0 && p.res) {
+        EPI_TICK(e_dr)
+        if (d == 0 && res_lazy) { res_issue(tile, nsl); __syncwarp(); }
+        if (p.res && d == (res_lazy ? ndrain - 1 : 0)) {
           mbar_wait_relaxed(res_bar, tl & 1u, p.poll_ns);
           const uint32_t sw = (CHB == 128) ? (lane & 7u) : ((lane >> 1) & 3u);   // swizzle of this lane's staged row
 #pragma unroll
@@ -621,6 +653,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             res_add16(acc[gi], v, g);
           }
           __syncwarp();
+          EPI_TICK(e_rs)
         }
       }
       const uint32_t interior_cur = interior;
@@ -630,6 +663,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t cbuf = tl & 1u;
       mbar_wait_relaxed(bar_corr_full + 8 * cbuf, (tl >> 1) & 1u, p.poll_ns);
       tc_fence_after();
+      EPI_TICK(e_wc)
 #pragma unroll
       for (int gi = 0; gi < NGH; ++gi) {
         if (2 * gi + half >= NG) continue;
@@ -641,6 +675,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_corr_empty + 8 * cbuf);
+      EPI_TICK(e_co)
       // ---- bias / ReLU / split / store (the MMA warps are already on the next tile)
 #pragma unroll
       for (int gi = 0; gi < NGH; ++gi) {
@@ -684,12 +719,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // stage this warp's 32 rows x CHB bytes in shared memory (hardware swizzle pattern of the store tensor map:
         // conflict-free 16-byte stores), then ONE bulk tensor store writes them as full lines (a per-thread row store
         // would scatter 16-byte pieces over 32 lines per instruction).  Rows past the tensor end are clipped by TMA.
-        const uint32_t sbuf = st_base + (p.nstg >= 2 ? (st_cnt & 1u) : 0u) * 32u * CHB;   // two buffers alternate (a third only holds residual rows)
-        if (lane == 0) {                                    // the buffer about to be overwritten has been read by its store
-          if (p.nstg >= 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-          else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        }
+        EPI_TICK(e_f1)
+        const uint32_t sbuf = st_base + st_slot * 32u * CHB;   // the nstg buffers rotate: a store has nstg-1 group times to read its source
+        if (lane == 0) bulk_wait_read(p.nstg - 1);          // the buffer about to be overwritten has been read by its store
         __syncwarp();
+        EPI_TICK(e_f2)
         const uint32_t srow = sbuf + (uint32_t)lane * CHB;
         // SWIZZLE_128B: 16-byte chunk index ^= row & 7;  SWIZZLE_64B: chunk index ^= (row >> 1) & 3
         const uint32_t sw = (CHB == 128) ? (lane & 7u) : ((lane >> 1) & 3u);
@@ -697,16 +731,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int i = 0; i < NV; ++i) st_shared_u4(srow + (((uint32_t)i ^ sw) << 4), ov[i]);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
+        EPI_TICK(e_f3)
         if (lane == 0) {
           const long long mrow = m0 + mt * 128 + q * 32;
           if (mrow < p.M) tma_store_2d(&tmO, (n0 + c0) / 16 * CF, (int)mrow, sbuf);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
-        ++st_cnt;
+        if (++st_slot == (uint32_t)p.nstg) st_slot = 0;
+        __syncwarp();
+        EPI_TICK(e_f4)
       }
       tile = tile_n; nsl = nsl_n;
-      if (p.res && w + (int)gridDim.x < p.total_work) res_issue(tile, nsl);   // next tile's residual chunks, one tile ahead
+      EPI_TICK(e_fi)
+      if (p.res && !res_lazy && w + (int)gridDim.x < p.total_work) res_issue(tile, nsl);   // next tile's residual chunks, one tile ahead
+      __syncwarp();
+      EPI_TICK(e_ri)
     }
+#if PE_TC_PROFILE
+    if (p.prof && warp == 2 && lane == 0) {
+      long long* o = p.prof + (size_t)blockIdx.x * 32 + 16;
+      o[0] = e_wm; o[1] = e_dr; o[2] = e_rs; o[3] = e_wc; o[4] = e_co; o[5] = e_fi; o[6] = e_ri; o[7] = e_tc; o[8] = clock64() - e_t0; o[9] = tl; o[10] = e_f1; o[11] = e_f2; o[12] = e_f3; o[13] = e_f4;
+    }
+#endif
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // staged rows fully written before smem goes away
   }
   tc_fence_before();
@@ -830,8 +876,8 @@ static std::vector<TcCand> tc_enumerate(int Cin, int Cout, int ks, bool has_res,
         // warp, so three or four when the warp owns that many groups).  Shrink the staging before giving up a third stage.
         const int ngh = (MT * NC / 16 + 1) / 2;
         int S = 0, nstg = 2;
-        const int cand[3] = {has_res ? std::max(2, std::min(ngh, 4)) : 2, 2, 1};
-        for (int ci = 0; ci < 3 && S < 3; ++ci) {
+        const int cand[4] = {has_res ? std::max(3, std::min(ngh, 4)) : 3, 3, 2, 1};
+        for (int ci = 0; ci < 4 && S < 3; ++ci) {
           const size_t staging = (size_t)EPI_WARPS * cand[ci] * 32 * CHB;
           if (staging + 2 * (size_t)p.stage_bytes > smem_total) continue;
           const int s_fit = (int)std::min<size_t>(4, (smem_total - staging) / p.stage_bytes);
@@ -879,6 +925,16 @@ static cudaError_t tc_build(TcConvPlan* pl, const TcCand& c, const float* in, fl
   pl->p.scale_pad = ((Cout + 63) / 64) * 64;
   pl->p.res = res; pl->p.bias = bias; pl->p.scale = wtc;
   pl->p.H = H; pl->p.W = W; pl->p.Hp = Hp; pl->p.Wp = Wp; pl->p.relu = relu;
+  {
+    auto magic = [](uint32_t d, uint32_t& mul, uint32_t& sh) {
+      uint32_t l = 0;
+      while ((1u << l) < d) ++l;                       // ceil(log2 d)
+      sh = 31 + l;
+      mul = (uint32_t)((((uint64_t)1 << sh) + d - 1) / d);
+    };
+    magic((uint32_t)(Hp * Wp), pl->p.div_hpwp_mul, pl->p.div_hpwp_sh);
+    magic((uint32_t)Wp, pl->p.div_wp_mul, pl->p.div_wp_sh);
+  }
   pl->p.poll_ns = env_int("PE_TC_POLL_NS", 0);
   pl->rows_per_img = Hp * Wp;
   pl->smem = c.smem;
@@ -1006,7 +1062,7 @@ cudaError_t tc_conv_plan_create(TcConvPlan** out, const float* in, float* outp, 
   if (e != cudaSuccess) { delete pl; return e; }
   pl->p.prof = nullptr;
 #if PE_TC_PROFILE
-  if (env_int("PE_TC_PROF", 0)) { cudaMalloc(&pl->p.prof, 148 * 16 * sizeof(long long)); cudaMemset(pl->p.prof, 0, 148 * 16 * sizeof(long long)); }
+  if (env_int("PE_TC_PROF", 0)) { cudaMalloc(&pl->p.prof, 148 * 32 * sizeof(long long)); cudaMemset(pl->p.prof, 0, 148 * 32 * sizeof(long long)); }
 #endif
   const TcCand& c = cands[pick];
   if (env_int("PE_TC_VERBOSE", 0))
@@ -1028,14 +1084,21 @@ cudaError_t tc_conv_launch(TcConvPlan* pl, int nimg, cudaStream_t st) {
   pl->kernel<<<grid, TC_THREADS, pl->smem, st>>>(pl->tmA, pl->tmW, pl->tmO, pl->tmR, p);
 #if PE_TC_PROFILE
   if (p.prof) {
-    long long h[148 * 16];
+    static long long h[148 * 32];
     cudaStreamSynchronize(st);
     cudaMemcpy(h, p.prof, sizeof h, cudaMemcpyDeviceToHost);
     for (int role = 0; role < 2; ++role) {
       double a[6] = {0, 0, 0, 0, 0, 0};
-      for (unsigned b = 0; b < grid; ++b) for (int k = 0; k < 6; ++k) a[k] += (double)h[b * 16 + role * 8 + k] / grid;
+      for (unsigned b = 0; b < grid; ++b) for (int k = 0; k < 6; ++k) a[k] += (double)h[b * 32 + role * 8 + k] / grid;
       fprintf(stderr, "conv_tc prof %s (NC=%d MT=%d TAPS=%d KC=%d nchunk=%d work=%d grid=%u res=%d): per-CTA cycles total %.0f | wait_full %.0f issue %.0f wait_main %.0f wait_corr %.0f | stages %.0f -> per stage: total %.0f wait_full %.0f issue %.0f wait_main %.0f\n",
               role ? "Y" : "X", pl->NC, pl->MT, pl->TAPS, pl->KC, p.nchunk, p.total_work, grid, p.res ? 1 : 0, a[4], a[0], a[1], a[2], a[3], a[5], a[4] / a[5], a[0] / a[5], a[1] / a[5], a[2] / a[5]);
+    }
+    {
+      double a[14] = {0};
+      for (unsigned b = 0; b < grid; ++b) for (int k = 0; k < 14; ++k) a[k] += (double)h[b * 32 + 16 + k] / grid;
+      const double t = a[9] > 0 ? a[9] : 1;
+      fprintf(stderr, "conv_tc prof E (NC=%d MT=%d TAPS=%d KC=%d nchunk=%d res=%d ndrain=%d): epilogue warp 2, cycles per tile: total %.0f | wait_main %.0f drain %.0f residual %.0f wait_corr %.0f corr %.0f final %.0f res_issue %.0f tile_calc %.0f (tiles %.0f) | final split: math %.0f wait_read %.0f sts+fence %.0f store %.0f\n",
+              pl->NC, pl->MT, pl->TAPS, pl->KC, p.nchunk, p.res ? 1 : 0, p.ndrain, a[8] / t, a[0] / t, a[1] / t, a[2] / t, a[3] / t, a[4] / t, a[5] / t, a[6] / t, a[7] / t, t, a[10] / t, a[11] / t, a[12] / t, a[13] / t);
     }
   }
 #endif
