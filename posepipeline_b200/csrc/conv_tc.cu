@@ -65,7 +65,7 @@ struct TcParams {
   int cpp;                   // gather: 16-channel chunks per input parity (py,px)
   int relu, tmem_cols;
   uint32_t div_hpwp_mul, div_hpwp_sh, div_wp_mul, div_wp_sh;   // exact n / (Hp*Wp) and n / Wp for n < 2^31: (n * mul) >> sh (64-bit product)
-  int poll_ns;               // back-off between barrier polls of the producer / epilogue warps (spinning warps burn issue slots and power)
+  int poll_ns;               // producer / epilogue waits: > 0 nanosleep back-off between polls, < 0 suspended try_wait with that time hint, 0 spin
   int tiles_m, total_work;   // persistent schedule: work item w -> (tile = w % tiles_m, n-slice = w / tiles_m)
   uint32_t a_bytes, stage_bytes;
   long long* prof;
@@ -107,8 +107,29 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 // same, for waits that are expected to be long (epilogue): back off so the polling does not crowd the LSU
-__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, uint32_t ns) {
+// suspending wait: the thread is parked by the hardware until the phase completes or the time hint expires (no issue slots,
+// no power while waiting); used for the long waits of the producer / epilogue warps when p.poll_ns < 0
+__device__ __forceinline__ bool mbar_try_suspend(uint32_t bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(hint_ns)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, int ns) {
   uint32_t spins = 0;
+  if (ns < 0) {
+    while (!mbar_try_suspend(bar, parity, (uint32_t)(-ns))) {
+      if (++spins > 100000000u) { printf("conv_tc: mbarrier timeout (suspend)\n"); __trap(); }
+    }
+    return;
+  }
   while (!mbar_try(bar, parity)) {
     if (ns) __nanosleep(ns);
     if (++spins > 100000000u) { printf("conv_tc: mbarrier timeout (relaxed)\n"); __trap(); }
@@ -935,7 +956,7 @@ static cudaError_t tc_build(TcConvPlan* pl, const TcCand& c, const float* in, fl
     magic((uint32_t)(Hp * Wp), pl->p.div_hpwp_mul, pl->p.div_hpwp_sh);
     magic((uint32_t)Wp, pl->p.div_wp_mul, pl->p.div_wp_sh);
   }
-  pl->p.poll_ns = env_int("PE_TC_POLL_NS", 0);
+  pl->p.poll_ns = env_int("PE_TC_POLL_NS", -1000);   // < 0: hardware-suspended waits with this time hint (ns); measured +1 % under the power cap
   pl->rows_per_img = Hp * Wp;
   pl->smem = c.smem;
   pl->ns = c.ns; pl->MT = c.MT; pl->NC = c.NC; pl->TAPS = ntaps; pl->KC = c.KC;
