@@ -896,16 +896,6 @@ static std::vector<TcCand> tc_enumerate(int Cin, int Cout, int ks, bool has_res,
         // stores; residual layers land the residual chunks of the next tile in them (one buffer per 16-column group of the
         // warp, so three or four when the warp owns that many groups).  Shrink the staging before giving up a third stage.
         const int ngh = (MT * NC / 16 + 1) / 2;
-        int S = 0, nstg = 2;
-        const int cand[4] = {has_res ? std::max(3, std::min(ngh, 4)) : 3, 3, 2, 1};
-        for (int ci = 0; ci < 4 && S < 3; ++ci) {
-          const size_t staging = (size_t)EPI_WARPS * cand[ci] * 32 * CHB;
-          if (staging + 2 * (size_t)p.stage_bytes > smem_total) continue;
-          const int s_fit = (int)std::min<size_t>(4, (smem_total - staging) / p.stage_bytes);
-          if (s_fit > S) { S = s_fit; nstg = cand[ci]; }
-        }
-        if (S < 2) continue;
-        p.S = S; p.nstg = nstg;
         int cols = 32;
         while (cols < ((MT * NC / 16 <= 6) ? 5 : 4) * MT * NC) cols <<= 1;
         p.tmem_cols = cols;
@@ -921,13 +911,38 @@ static std::vector<TcCand> tc_enumerate(int Cin, int Cout, int ks, bool has_res,
         const double mma = n_mma * std::max(NC / 2.0, 32.0 + NC / 4.0) + 300.0 * p.nstage;
         const double bytes = (double)nchunk * (p.a_bytes + (double)b_chunk);
         const double epi = (double)MT * (NC / 16) * 130.0 * (1 + p.ndrain * 0.5) + 1500.0;
-        const double item = std::max(std::max(mma, bytes / 40.0), epi) + (S < 3 ? 0.15 * mma : 0.0)
-                            + ((has_res && MT * NC / 16 > 6) ? 0.5 * epi : 0.0);
-        TcCand c;
-        c.p = p; c.ns = ns; c.MT = MT; c.NC = NC; c.KC = KC;
-        c.smem = (size_t)S * p.stage_bytes + (size_t)EPI_WARPS * nstg * 32 * CHB + 2048;
-        c.cost = items * item + 4000.0;
-        out.push_back(c);
+        // Ring depth S (2..4) against store-staging buffers per epilogue warp (1..4; residual layers land the residual chunks
+        // of a tile in them, one buffer per 16-column group of the warp): both want the same shared memory.  Measured: a
+        // store takes ~1000 clocks to read its source, so one staging buffer stalls every group of the final phase, and two
+        // stages stall the MMA warps -- which hurts more depends on the layer, so both trade-offs become candidates.
+        const int want = has_res ? std::max(3, std::min(ngh, 4)) : 3;
+        int lastS = -1, lastN = -1;
+        auto fit = [&](int nstg_) {
+          const size_t staging = (size_t)EPI_WARPS * nstg_ * 32 * CHB;
+          if (staging + 2 * (size_t)p.stage_bytes > smem_total) return 0;
+          return (int)std::min<size_t>(4, (smem_total - staging) / p.stage_bytes);
+        };
+        for (int variant = 0; variant < 2; ++variant) {
+          int S = 0, nstg = 0;
+          if (variant == 0) {                               // a third stage first, then as much staging as still fits
+            const int target = std::min(fit(1), 3);
+            for (int t = want; t >= 1 && !nstg; --t)
+              if (fit(t) >= target && target >= 2) nstg = t;
+            S = nstg ? fit(nstg) : 0;
+          } else {                                          // full staging first, the ring gets the rest
+            nstg = want; S = fit(want);
+          }
+          if (S < 2 || nstg < 1 || (S == lastS && nstg == lastN)) continue;
+          lastS = S; lastN = nstg;
+          p.S = S; p.nstg = nstg;
+          const double item = std::max(std::max(mma, bytes / 40.0), epi) + (S < 3 ? 0.15 * mma : 0.0) + (nstg < 2 ? 0.1 * epi : 0.0)
+                              + ((has_res && MT * NC / 16 > 6) ? 0.5 * epi : 0.0);
+          TcCand c;
+          c.p = p; c.ns = ns; c.MT = MT; c.NC = NC; c.KC = KC;
+          c.smem = (size_t)S * p.stage_bytes + (size_t)EPI_WARPS * nstg * 32 * CHB + 2048;
+          c.cost = items * item + 4000.0;
+          out.push_back(c);
+        }
       }
     }
   }
@@ -1009,7 +1024,7 @@ static cudaError_t tc_build(TcConvPlan* pl, const TcCand& c, const float* in, fl
 #include <tuple>
 #include <algorithm>
 typedef std::tuple<int, int, int, int, int, int, int> TcShapeKey;   // Cin, Cout, ks, H, W, residual, max_img
-static std::map<TcShapeKey, std::tuple<int, int, int>> g_tc_choice;  // -> ns, MT, KC
+static std::map<TcShapeKey, std::tuple<int, int, int, int>> g_tc_choice;  // -> ns, MT, KC, S*8 + nstg
 
 cudaError_t tc_conv_plan_create(TcConvPlan** out, const float* in, float* outp, const float* res, const float* wtc,
                                 const float* bias, int Cin, int Cout, int ks, int relu, int H, int W, int max_img,
@@ -1039,13 +1054,13 @@ cudaError_t tc_conv_plan_create(TcConvPlan** out, const float* in, float* outp, 
   auto hit = g_tc_choice.find(key);
   if (!pinned && hit != g_tc_choice.end()) {
     for (size_t i = 0; i < cands.size(); ++i)
-      if (std::make_tuple(cands[i].ns, cands[i].MT, cands[i].KC) == hit->second) pick = i;
+      if (std::make_tuple(cands[i].ns, cands[i].MT, cands[i].KC, cands[i].p.S * 8 + cands[i].p.nstg) == hit->second) pick = i;
   } else if (!pinned && env_int("PE_TC_AUTOTUNE", 1) && cands.size() > 1) {
     cudaStream_t ts;
     cudaEvent_t e0, e1;
     if (cudaStreamCreateWithFlags(&ts, cudaStreamNonBlocking) != cudaSuccess) return cudaGetLastError();
     cudaEventCreate(&e0); cudaEventCreate(&e1);
-    const size_t ntry = std::min<size_t>(cands.size(), 8);
+    const size_t ntry = std::min<size_t>(cands.size(), 10);
     std::vector<TcConvPlan> tmp(ntry);
     std::vector<float> ms_min(ntry, 1e30f);
     std::vector<char> ok(ntry, 0);
@@ -1068,15 +1083,15 @@ cudaError_t tc_conv_plan_create(TcConvPlan** out, const float* in, float* outp, 
     for (size_t i = 0; i < ntry; ++i) {
       if (!ok[i]) continue;
       if (env_int("PE_TC_VERBOSE", 0) > 1)
-        fprintf(stderr, "conv_tc tune: Cin=%d Cout=%d ks=%d %dx%d res=%d gather=%d  NS=%d MT=%d KC=%d S=%d -> %.3f ms (model %.0f)\n", Cin, Cout, ks, H, W,
-                res ? 1 : 0, gather_src ? 1 : 0, cands[i].ns, cands[i].MT, cands[i].KC, cands[i].p.S, ms_min[i], cands[i].cost);
+        fprintf(stderr, "conv_tc tune: Cin=%d Cout=%d ks=%d %dx%d res=%d gather=%d  NS=%d MT=%d KC=%d S=%d nstg=%d -> %.3f ms (model %.0f)\n", Cin, Cout, ks, H, W,
+                res ? 1 : 0, gather_src ? 1 : 0, cands[i].ns, cands[i].MT, cands[i].KC, cands[i].p.S, cands[i].p.nstg, ms_min[i], cands[i].cost);
       if (ms_min[i] < best_ms) { best_ms = ms_min[i]; pick = i; }
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     cudaStreamDestroy(ts);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    g_tc_choice[key] = std::make_tuple(cands[pick].ns, cands[pick].MT, cands[pick].KC);
+    g_tc_choice[key] = std::make_tuple(cands[pick].ns, cands[pick].MT, cands[pick].KC, cands[pick].p.S * 8 + cands[pick].p.nstg);
   }
   TcConvPlan* pl = new TcConvPlan();
   cudaError_t e = tc_build(pl, cands[pick], in, outp, res, wtc, bias, Cin, Cout, ks, relu, H, W, max_img, num_sms, gather_src);

@@ -279,3 +279,57 @@ def test_topdown_halpe136_and_wholebody133(eng):
         assert got.shape == (3, spec.num_joints, 3)
         _check_keypoints(got, ref32, ref64, min_good=0.7)
         m.close()
+
+
+# ------------------------------------------------------------------ a8: the tensor-core kernel's tiling / gather choices are value-neutral
+def _conv_case(eng, cin, cout, k, H, W, n, res, stride, seed):
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((n, cin, H, W)).astype(np.float32)
+    w = (rng.standard_normal((cout, cin, k, k)) / np.sqrt(cin * k * k)).astype(np.float32)
+    b = rng.standard_normal(cout).astype(np.float32)
+    r = rng.standard_normal((n, cout, H // stride, W // stride)).astype(np.float32) if res else None
+    return lambda: E.conv_test(eng, x, w, b, r, True, True, stride)
+
+
+def _with_env(fn, **env):
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update({k: str(v) for k, v in env.items()})
+    try:
+        return fn()
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def test_conv_tilings_are_bit_identical(eng):
+    """conv_tc picks its tiling by measurement (csrc/conv_tc.cu tc_conv_plan_create); every candidate must give the SAME bits:
+    the accumulation order over K does not depend on the N-split, tile height, stage size or ring depth."""
+    run = _conv_case(eng, 96, 96, 3, 48, 36, 5, True, 1, 11)
+    ref = _with_env(run, PE_TC_AUTOTUNE=0)
+    for env in ({"PE_TC_MT": 1}, {"PE_TC_MT": 2}, {"PE_TC_NS": 2}, {"PE_TC_AUTOTUNE": 1}):
+        got = _with_env(run, **env)
+        assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), env
+    run1 = _conv_case(eng, 64, 256, 1, 96, 72, 2, True, 1, 12)
+    ref1 = _with_env(run1, PE_TC_AUTOTUNE=0)
+    for env in ({"PE_TC_KC": 1}, {"PE_TC_KC": 4}, {"PE_TC_NS": 4}):
+        assert np.array_equal(_with_env(run1, **env).view(np.uint32), ref1.view(np.uint32)), env
+
+
+def test_stride2_tma_gather_equals_space_to_depth_copy(eng):
+    """Stride-2 3x3 layers: gathering the space-to-depth rows by TMA (element strides 2,2) from the original tensor must equal
+    the s2d_kernel copy + 2x2 convolution bit for bit, and both must match a float64 reference."""
+    for (cin, cout, H, W, n, seed) in ((48, 96, 96, 72, 3, 21), (192, 384, 24, 18, 4, 22), (64, 64, 192, 144, 1, 23)):
+        run = _conv_case(eng, cin, cout, 3, H, W, n, False, 2, seed)
+        gathered = _with_env(run, PE_TC_GATHER=1)
+        copied = _with_env(run, PE_TC_GATHER=0)
+        assert np.array_equal(gathered.view(np.uint32), copied.view(np.uint32)), (cin, cout, H, W)
+        rng = np.random.default_rng(seed)
+        x = rng.standard_normal((n, cin, H, W)).astype(np.float32)
+        w = (rng.standard_normal((cout, cin, 3, 3)) / np.sqrt(cin * 9)).astype(np.float32)
+        b = rng.standard_normal(cout).astype(np.float32)
+        ref = torch.relu(torch.nn.functional.conv2d(torch.from_numpy(x).double(), torch.from_numpy(w).double(), torch.from_numpy(b).double(),
+                                                    padding=1, stride=2)).numpy()
+        assert np.abs(gathered - ref).max() <= 2e-6 * np.abs(ref).max()
