@@ -7,7 +7,7 @@ cat gpurun_out/pytest_$TAG.log
 timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; cat gpurun_out/bench_$TAG.json; tail -3 gpurun_out/bench_$TAG.err
 timeout 300 python tests/layer_perf.py 128 2 > gpurun_out/layers_$TAG.txt 2>&1; head -40 gpurun_out/layers_$TAG.txt
 if [ "$2" != "noncu" ]; then
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 1920 --launch-count 660 --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench_$TAG.log 2>&1
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 2700 --launch-count 640 --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench_$TAG.log 2>&1
 python profiles/summarize_launches.py gpurun_out/launches_$TAG.csv --by-grid > gpurun_out/launches_$TAG.md; head -30 gpurun_out/launches_$TAG.md
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_tc --launch-skip 600 --launch-count 12 -o gpurun_out/full_$TAG -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_$TAG.log 2>&1; tail -3 gpurun_out/ncu_full_$TAG.log
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_tc --launch-skip 2300 --launch-count 14 -o gpurun_out/full_$TAG -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_$TAG.log 2>&1; tail -3 gpurun_out/ncu_full_$TAG.log
 fi
