@@ -17,11 +17,13 @@
 // absolute smem address bits, measured) -- and (b) the weights of ALL taps of those chunks (one 3-D TMA box).  A stage is
 // therefore 9*MT*3 MMAs for a 3x3 layer: the per-stage synchronisation cost is paid once per ~50 MMAs.
 //
-// Warp roles (12 warps; warp 10 idles -- registers are allocated per 4 warps):
+// Warp roles (16 warps, 128 registers per thread):
 //   0      TMA producer (one lane): activation windows + weights of a stage, one full barrier
 //   1      MMA issuer X: hi*hi  -> `main` accumulators; owns the drain-group protocol with the epilogue
-//   11     MMA issuer Y: hi*lo + lo*hi -> `corr` accumulator of the tile
-//   2..9   epilogue (TMEM lane quarter = warp & 3; the two warps of a quarter take even / odd 16-column groups)
+//   14     MMA issuer Y: hi*lo + lo*hi -> `corr` accumulator of the tile
+//   2..13  epilogue (TMEM lane quarter = warp & 3; the three warps of a quarter take the 16-column groups round-robin;
+//          measured: 12 epilogue warps instead of 8 took 6 % off the residual layers, which are epilogue-bound)
+//   15     idle
 // Why two issuers -- measured (tools/issue_bench.cu): for N <= 128 a tcgen05.mma blocks its issuing thread for the whole
 // shared-memory operand fetch (~51 clk at N = 48), so nothing else the issuing warp does overlaps with tensor work, and the
 // pure barrier skeleton of the one-issuer kernel cost as much as the MMAs.  Two issuers interleave in the tensor pipe
@@ -40,8 +42,9 @@
 constexpr uint32_t ROW16 = CHB / 16;          // 8 (tf32) / 4 (fp16)
 constexpr uint32_t LO16 = CHB / 32;           // 16-byte units from hi to lo: 4 / 2
 constexpr int KSTEPS = PE_FP16 ? 1 : 2;       // 16 x f16 = one K=16 MMA; 16 x tf32 = two K=8 MMAs
-constexpr int TC_THREADS = 384;
-constexpr int EPI_WARPS = 8;
+constexpr int TC_THREADS = 512;
+constexpr int EPI_WARPS = 12;
+constexpr int EPI_PARTS = EPI_WARPS / 4;      // epilogue warps per TMEM lane quarter: they split the 16-column groups round-robin
 constexpr int MAX_ACC_STEPS = 6;              // hi*hi MMA steps one TMEM accumulator may take before it is drained (see kernel)
 #ifndef PE_TC_PROFILE
 #define PE_TC_PROFILE 0                       // 1: per-CTA cycle counters of the two MMA warps (build flag; costs issue slots)
@@ -360,7 +363,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         while (tile >= p.tiles_m) { tile -= p.tiles_m; ++nsl; }
       }
     }
-  } else if (warp == 1 || warp == 3 + EPI_WARPS) {
+  } else if (warp == 1 || warp == 2 + EPI_WARPS) {
     // ===================== MMA issuers: warp-uniform control flow, one elected lane issues =====================
     const bool roleX = (warp == 1);
     // instruction descriptor: D=F32, A/B format, K-major both, N = NC, M = 128
@@ -521,11 +524,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 #endif
   } else if (warp >= 2 && warp < 2 + EPI_WARPS) {
-    // ===================== epilogue (warps 2..9; TMEM lane quarter = warp & 3; the two warps of a quarter take the even / odd
-    // 16-column groups, so TMEM drains, residual loads, the split and the stores of one tile run on 8 warps) ==========
+    // ===================== epilogue (warps 2..13; TMEM lane quarter = warp & 3; the EPI_PARTS warps of a quarter take the
+    // 16-column groups round-robin, so TMEM drains, residual adds, the split and the stores of one tile run on 12 warps) ====
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
-    constexpr int NGH = (NG + 1) / 2;                       // groups per warp (the odd warp of an odd NG has one fewer)
+    const int half = (warp - 2) >> 2;                       // which of the EPI_PARTS warps of this quarter
+    constexpr int NGH = (NG + EPI_PARTS - 1) / EPI_PARTS;                       // groups per warp (the odd warp of an odd NG has one fewer)
     const int rowF = ps_row_floats(p.Cout);
     constexpr int CF = PS_CHUNK_FLOATS;                     // floats per 16-channel chunk of a row
     constexpr int gpm = NC / 16;                            // 16-column groups per 128-row accumulator
@@ -549,11 +552,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         uint32_t nb = 0;
 #pragma unroll
-        for (int gi = 0; gi < NGH; ++gi) nb += (2 * gi + half < NG && gi < p.nstg) ? 1u : 0u;
+        for (int gi = 0; gi < NGH; ++gi) nb += (EPI_PARTS * gi + half < NG && gi < p.nstg) ? 1u : 0u;
         mbar_expect_tx(res_bar, nb * 32u * CHB);
 #pragma unroll
         for (int gi = 0; gi < NGH; ++gi) {
-          const int g = 2 * gi + half;
+          const int g = EPI_PARTS * gi + half;
           if (g < NG && gi < p.nstg)
             tma_load_2d(st_base + (uint32_t)gi * 32u * CHB, &tmR, (nsl_ * NC + (g % gpm) * 16) / 16 * CF,
                         tile_ * 128 * MT + (g / gpm) * 128 + q * 32, res_bar);
@@ -631,9 +634,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // phase multiplies by 2^-k: all exact
 #pragma unroll
         for (int gi = 0; gi < NGH; ++gi) {
-          if (2 * gi + half >= NG) continue;
+          if (EPI_PARTS * gi + half >= NG) continue;
           uint32_t r[16];
-          tc_ld16(t_lane + dg * GC + (2 * gi + half) * 16, r);
+          tc_ld16(t_lane + dg * GC + (EPI_PARTS * gi + half) * 16, r);
           if (d == 0) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) acc[gi][i] = __uint_as_float(r[i]);
@@ -653,7 +656,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t sw = (CHB == 128) ? (lane & 7u) : ((lane >> 1) & 3u);   // swizzle of this lane's staged row
 #pragma unroll
           for (int gi = 0; gi < NGH; ++gi) {
-            const int g = 2 * gi + half;
+            const int g = EPI_PARTS * gi + half;
             if (g >= NG) continue;
             uint4 v[NV];
             if (gi < p.nstg) {
@@ -687,9 +690,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       EPI_TICK(e_wc)
 #pragma unroll
       for (int gi = 0; gi < NGH; ++gi) {
-        if (2 * gi + half >= NG) continue;
+        if (EPI_PARTS * gi + half >= NG) continue;
         uint32_t r[16];
-        tc_ld16(t_lane + (NMAIN + cbuf) * GC + (2 * gi + half) * 16, r);
+        tc_ld16(t_lane + (NMAIN + cbuf) * GC + (EPI_PARTS * gi + half) * 16, r);
 #pragma unroll
         for (int i = 0; i < 16; ++i) acc[gi][i] += __uint_as_float(r[i]);
       }
@@ -700,7 +703,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // ---- bias / ReLU / split / store (the MMA warps are already on the next tile)
 #pragma unroll
       for (int gi = 0; gi < NGH; ++gi) {
-        const int g = 2 * gi + half;
+        const int g = EPI_PARTS * gi + half;
         if (g >= NG) continue;
         const int mt = g / gpm, c0 = (g % gpm) * 16;
         uint4 ov[NV];                                      // one staged row: [hi.. | lo..]
@@ -895,7 +898,7 @@ static std::vector<TcCand> tc_enumerate(int Cin, int Cout, int ks, bool has_res,
         // ring depth: as many stages as fit, at most 4.  Store-staging buffers per epilogue warp: two alternate for the output
         // stores; residual layers land the residual chunks of the next tile in them (one buffer per 16-column group of the
         // warp, so three or four when the warp owns that many groups).  Shrink the staging before giving up a third stage.
-        const int ngh = (MT * NC / 16 + 1) / 2;
+        const int ngh = (MT * NC / 16 + EPI_PARTS - 1) / EPI_PARTS;
         int cols = 32;
         while (cols < ((MT * NC / 16 <= 6) ? 5 : 4) * MT * NC) cols <<= 1;
         p.tmem_cols = cols;
