@@ -68,6 +68,7 @@ struct TcParams {
   int cpp;                   // gather: 16-channel chunks per input parity (py,px)
   int relu, tmem_cols;
   uint32_t div_hpwp_mul, div_hpwp_sh, div_wp_mul, div_wp_sh;   // exact n / (Hp*Wp) and n / Wp for n < 2^31: (n * mul) >> sh (64-bit product)
+  int mma_wait_ns;           // MMA warps: 0 = spin on test_wait (default), > 0 = suspended try_wait with this time hint
   int poll_ns;               // producer / epilogue waits: > 0 nanosleep back-off between polls, < 0 suspended try_wait with that time hint, 0 spin
   int tiles_m, total_work;   // persistent schedule: work item w -> (tile = w % tiles_m, n-slice = w / tiles_m)
   uint32_t a_bytes, stage_bytes;
@@ -185,6 +186,14 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// MMA-warp wait: spin (lowest latency) or hardware-suspended with a short time hint
+__device__ __forceinline__ void mbar_wait_mma(uint32_t bar, uint32_t parity, int hint_ns) {
+  if (hint_ns <= 0) { mbar_wait(bar, parity); return; }
+  uint32_t spins = 0;
+  while (!mbar_try_suspend(bar, parity, (uint32_t)hint_ns)) {
+    if (++spins > 100000000u) { printf("conv_tc: mbarrier timeout (mma)\n"); __trap(); }
+  }
+}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -397,7 +406,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #if PE_TC_PROFILE
           long long c0 = clock64();
 #endif
-          mbar_wait(bar_full + 8 * r.idx, r.phase);
+          mbar_wait_mma(bar_full + 8 * r.idx, r.phase, p.mma_wait_ns);
           tc_fence_after();
 #if PE_TC_PROFILE
           { const long long c1 = clock64(); c_wf += c1 - c0; c0 = c1; ++c_st; }
@@ -413,7 +422,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #if PE_TC_PROFILE
                 const long long cm = clock64();
 #endif
-                mbar_wait(bar_main_empty + 8 * dg, dgp ^ 1u);   // epilogue has drained this main buffer
+                mbar_wait_mma(bar_main_empty + 8 * dg, dgp ^ 1u, p.mma_wait_ns);   // epilogue has drained this main buffer
                 tc_fence_after();
 #if PE_TC_PROFILE
                 { const long long c1 = clock64(); c_wm += c1 - cm; c0 += c1 - cm; }
@@ -475,7 +484,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #if PE_TC_PROFILE
           long long c0 = clock64();
 #endif
-          mbar_wait(bar_full + 8 * r.idx, r.phase);
+          mbar_wait_mma(bar_full + 8 * r.idx, r.phase, p.mma_wait_ns);
           tc_fence_after();
 #if PE_TC_PROFILE
           { const long long c1 = clock64(); c_wf += c1 - c0; c0 = c1; ++c_st; }
@@ -974,6 +983,7 @@ static cudaError_t tc_build(TcConvPlan* pl, const TcCand& c, const float* in, fl
     magic((uint32_t)(Hp * Wp), pl->p.div_hpwp_mul, pl->p.div_hpwp_sh);
     magic((uint32_t)Wp, pl->p.div_wp_mul, pl->p.div_wp_sh);
   }
+  pl->p.mma_wait_ns = env_int("PE_TC_MMA_WAIT_NS", 0);
   pl->p.poll_ns = env_int("PE_TC_POLL_NS", -1000);   // < 0: hardware-suspended waits with this time hint (ns); measured +1 % under the power cap
   pl->rows_per_img = Hp * Wp;
   pl->smem = c.smem;
