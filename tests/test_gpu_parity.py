@@ -309,13 +309,27 @@ def test_conv_tilings_are_bit_identical(eng):
     the accumulation order over K does not depend on the N-split, tile height, stage size or ring depth."""
     run = _conv_case(eng, 96, 96, 3, 48, 36, 5, True, 1, 11)
     ref = _with_env(run, PE_TC_AUTOTUNE=0)
+    def forced(run_, env):
+        try:
+            return _with_env(run_, **env)
+        except E._lib.PoseEngineError as ex:              # a pinned tiling that does not exist in this build (e.g. tf32x3: 128-byte chunks)
+            assert "not supported" in str(ex), ex
+            return None
+
+    checked = 0
     for env in ({"PE_TC_MT": 1}, {"PE_TC_MT": 2}, {"PE_TC_NS": 2}, {"PE_TC_AUTOTUNE": 1}):
-        got = _with_env(run, **env)
-        assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), env
+        got = forced(run, env)
+        if got is not None:
+            checked += 1
+            assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), env
     run1 = _conv_case(eng, 64, 256, 1, 96, 72, 2, True, 1, 12)
     ref1 = _with_env(run1, PE_TC_AUTOTUNE=0)
     for env in ({"PE_TC_KC": 1}, {"PE_TC_KC": 4}, {"PE_TC_NS": 4}):
-        assert np.array_equal(_with_env(run1, **env).view(np.uint32), ref1.view(np.uint32)), env
+        got = forced(run1, env)
+        if got is not None:
+            checked += 1
+            assert np.array_equal(got.view(np.uint32), ref1.view(np.uint32)), env
+    assert checked >= 3
 
 
 def test_stride2_tma_gather_equals_space_to_depth_copy(eng):
