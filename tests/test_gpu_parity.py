@@ -347,3 +347,21 @@ def test_stride2_tma_gather_equals_space_to_depth_copy(eng):
         ref = torch.relu(torch.nn.functional.conv2d(torch.from_numpy(x).double(), torch.from_numpy(w).double(), torch.from_numpy(b).double(),
                                                     padding=1, stride=2)).numpy()
         assert np.abs(gathered - ref).max() <= 2e-6 * np.abs(ref).max()
+
+
+def test_topdown_is_independent_of_internal_batching(eng, model48):
+    """The same crops through max_crops=4 chunks (4+4+2, CUDA-graph replay of each chunk size) and through one 16-crop batch:
+    tiles of the flat row matrix mix images differently, the per-row arithmetic must not change by a bit."""
+    frames = helpers.frames(3)
+    eng.stage_frames(frames)
+    bbs = synthetic_bboxes(10, 78)
+    fidx = np.arange(10) % 3
+    a = model48.topdown(fidx, bbs)
+    a2 = model48.topdown(fidx, bbs)
+    big = E.TopDownModel(eng, helpers.state_dict("HRNet_W48_COCO"), E.METHODS["HRNet_W48_COCO"], max_crops=16, use_tensor_cores=USE_TC)
+    try:
+        b = big.topdown(fidx, bbs)
+    finally:
+        big.close()
+    assert np.array_equal(a.view(np.uint32), a2.view(np.uint32))
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
