@@ -253,7 +253,11 @@ def main():
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s",
-                         "frac": (achieved / tf_peak) if achieved else None, "traffic": None,
+                         "frac": (achieved / tf_peak) if achieved else None,
+                         # DRAM bytes of ONE launch of the top kernel (conv_tc<6,2,9,1>, the 48->48 3x3 layers at 96x72 on 512
+                         # images), dram__bytes_read.sum + dram__bytes_write.sum of the committed ncu --set full capture
+                         # (profiles/r01_tc_v7_ncu_full.md); its algorithmic bytes are 2 x 0.713 GB (input once + output once)
+                         "traffic": 1.383e9, "traffic_unit": "bytes per launch of the top kernel (ncu, 512 images)",
                          "kernel": "convolution kernels (conv_tc / conv_simt), all launches of a second pass of the same K steps with an event pair per launch",
                          "algorithmic_flop_per_crop": FLOP_PER_CROP, "conv_ms_total": conv_ms, "other_ms_total": other_ms,
                          "profiled_pass_ms_per_step": ms_prof / args.steps,
