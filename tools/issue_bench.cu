@@ -18,6 +18,16 @@ __device__ __forceinline__ uint64_t desc(uint32_t saddr, uint32_t row_bytes, uin
 __device__ __forceinline__ void mma_f16(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
   asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
 }
+// collector usage for the A operand: 1 = fill (keep A in the collector buffer), 2 = lastuse (reuse it), 0 = plain
+template <int CU>
+__device__ __forceinline__ void mma_f16_cu(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  if (CU == 1)
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%0], %1, %2, %3, p;\n}\n" ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+  else if (CU == 2)
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse [%0], %1, %2, %3, p;\n}\n" ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+  else
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
 __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
@@ -44,7 +54,38 @@ __global__ void __launch_bounds__(128, 1) issue_bench(int N, int burst, int gap,
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = __shfl_sync(0xffffffffu, *tslot, 0);
-  if (mode == 6 && (warp == 1 || warp == 2)) {
+  if (mode == 7 && (warp == 1 || (warp == 2 && burst < 0))) {
+    // triples (A_hi x W_hi, A_hi x W_lo, A_lo x W_hi) as the conv kernel issues them per tap; gap != 0: the first two share A through
+    // the collector buffer (fill / lastuse).  burst < 0: two warps, each its own accumulators (split by 128-row sub-tile).
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+    const uint64_t a0 = desc(sA, 64, 4), b0 = desc(sB, 64, 4);
+    const uint32_t bar = sBar + 16 + 8 * (warp - 1);
+    if ((threadIdx.x & 31) == 0) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar)); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    __syncwarp();
+    const uint32_t dm = tmem + (warp - 1) * 256, dc = dm + 128;
+    long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      if (elect_one()) {
+#pragma unroll
+        for (int u = 0; u < 9; ++u) {
+          const uint64_t a = a0 + (uint64_t)(u * 4 + (warp - 1) * 512), b = b0 + (uint64_t)(u * 192);
+          if (gap) {
+            mma_f16_cu<1>(dm, a, b, idesc, 1u);
+            mma_f16_cu<2>(dc, a, b + 2, idesc, 1u);
+          } else {
+            mma_f16_cu<0>(dm, a, b, idesc, 1u);
+            mma_f16_cu<0>(dc, a, b + 2, idesc, 1u);
+          }
+          mma_f16_cu<0>(dc, a + 2, b, idesc, 1u);
+        }
+      }
+      __syncwarp();
+    }
+    if (elect_one()) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+    while (!mbar_try(bar, 0u)) {}
+    long long t1 = clock64();
+    if ((threadIdx.x & 31) == 0) out[(warp - 1)] = t1 - t0;
+  } else if (mode == 6 && (warp == 1 || warp == 2)) {
     // two issuing warps: disjoint accumulators, same operands; each: burst then gap
     const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
     const uint64_t a0 = desc(sA, 64, 4), b0 = desc(sB, 64, 4);
@@ -132,6 +173,15 @@ int main() {
         if (cudaDeviceSynchronize() != cudaSuccess) { printf("error\n"); return 1; }
         cudaMemcpy(h, d_out, sizeof h, cudaMemcpyDeviceToHost);
         printf("%3d %2d %4d : %8.1f %8.1f\n", N, burst, gap, (double)h[0] / iters, (double)h[1] / iters);
+      }
+  printf("collector reuse of A (9 taps x [hi*hi, hi*lo, lo*hi]) -- N warps reuse : cycles per tap-triple (per warp)\n");
+  for (int N : {48, 64, 96, 128})
+    for (int nw : {1, 2})
+      for (int reuse : {0, 1}) {
+        issue_bench<<<1, 128, smem>>>(N, nw == 2 ? -1 : 1, reuse, iters, 7, d_out);
+        if (cudaDeviceSynchronize() != cudaSuccess) { printf("error %s\n", cudaGetErrorString(cudaGetLastError())); return 1; }
+        cudaMemcpy(h, d_out, sizeof h, cudaMemcpyDeviceToHost);
+        printf("%3d %d %d : %8.1f %8.1f\n", N, nw, reuse, (double)h[0] / iters / 9, nw == 2 ? (double)h[1] / iters / 9 : 0.0);
       }
   const char* names[] = {"", "tcgen05.fence::after", "elect.sync+syncwarp", "mbarrier.test_wait", "elect+tcgen05.commit", "clock64 pair"};
   for (int mode = 1; mode <= 5; ++mode) {
