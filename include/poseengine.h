@@ -152,6 +152,15 @@ int pe_conv_test(pe_engine* e, const float* in_nchw, int32_t nimg, int32_t Cin, 
                  const float* w_tc, const float* bias, const float* res_nchw, int32_t Cout, int32_t ks, int32_t stride,
                  int32_t relu, int32_t use_tc, float* out_nchw);
 
+/* host-only: the candidate tilings the tensor-core convolution planner would consider for a layer (no GPU needed; the
+ * CPU suite checks their shared-memory / TMEM / alignment invariants).  ks: 1, 3, or 2 (= the 2x2 space-to-depth form of a
+ * stride-2 3x3 layer, Cin already x4); gather: 1 = TMA gather mode of that form.  Each candidate fills PE_TC_CAND_FIELDS
+ * int32 values: n_split, MT, NC, KC, stages, staging_buffers, stage_bytes, smem_bytes, tmem_cols, rows_per_group, n_drain,
+ * window_rows.  Returns the number of candidates (<= cap) or a negative error. */
+#define PE_TC_CAND_FIELDS 12
+int pe_tc_plan_candidates(int32_t Cin, int32_t Cout, int32_t ks, int32_t has_residual, int32_t H, int32_t W, int32_t max_img,
+                          int32_t gather, int32_t* out, int32_t cap);
+
 /* ---- VideoPose3D lifter (wrappers/videopose3d.py:46-85; TemporalModelOptimized1f 243 frames) ---- */
 int pe_lifter_create(pe_engine* e, const float* weights, int64_t n_floats, const int64_t* offsets /*see lifter.py*/,
                      int32_t n_offsets, int32_t channels, pe_lifter** out);

@@ -86,6 +86,7 @@ def load():
         "pe_model_profile_read": (C.c_int, [vp, P(C.c_double), P(C.c_double), P(i64)]),
         "pe_model_profile_ops": (C.c_int, [vp, vp, i32]),
         "pe_conv_test": (C.c_int, [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
+        "pe_tc_plan_candidates": (C.c_int, [i32, i32, i32, i32, i32, i32, i32, i32, vp, i32]),
         "pe_lifter_create": (C.c_int, [vp, vp, i64, vp, i32, i32, P(vp)]),
         "pe_lifter_destroy": (C.c_int, [vp]),
         "pe_lift3d": (C.c_int, [vp, vp, i32, vp]),

@@ -1122,6 +1122,20 @@ cudaError_t tc_conv_plan_create(TcConvPlan** out, const float* in, float* outp, 
   return cudaSuccess;
 }
 
+int tc_plan_candidates(int Cin, int Cout, int ks, int has_res, int H, int W, int max_img, int gather, int32_t* out, int cap) {
+  if ((ks != 1 && ks != 2 && ks != 3) || Cin % 16 || Cout % 16 || Cout > 512 || !out || cap < 0) return -1;
+  const std::vector<TcCand> c = tc_enumerate(Cin, Cout, ks, has_res != 0, H, W, max_img, 148, gather != 0);
+  int n = 0;
+  for (const TcCand& k : c) {
+    if (n >= cap) break;
+    int32_t* o = out + (size_t)n * 12;
+    o[0] = k.ns; o[1] = k.MT; o[2] = k.NC; o[3] = k.KC; o[4] = k.p.S; o[5] = k.p.nstg; o[6] = (int32_t)k.p.stage_bytes;
+    o[7] = (int32_t)k.smem; o[8] = k.p.tmem_cols; o[9] = k.p.rpg; o[10] = k.p.ndrain; o[11] = k.p.Rpad;
+    ++n;
+  }
+  return n;
+}
+
 void tc_conv_plan_destroy(TcConvPlan* plan) { if (plan && plan->p.prof) cudaFree(plan->p.prof); delete plan; }
 
 cudaError_t tc_conv_launch(TcConvPlan* pl, int nimg, cudaStream_t st) {

@@ -779,6 +779,13 @@ done:
   return rc;
 }
 
+extern "C" int pe_tc_plan_candidates(int32_t Cin, int32_t Cout, int32_t ks, int32_t has_residual, int32_t H, int32_t W, int32_t max_img,
+                                     int32_t gather, int32_t* out, int32_t cap) {
+  const int n = tc_plan_candidates(Cin, Cout, ks, has_residual, H, W, max_img, gather, out, cap);
+  if (n < 0) return fail(PE_ERR_INVALID, "bad argument to pe_tc_plan_candidates");
+  return n;
+}
+
 extern "C" int pe_model_profile_ops(pe_model* m, double* ms_per_op, int32_t n_ops) {
   if (!m || !ms_per_op || n_ops != (int32_t)m->ops.size()) return fail(PE_ERR_INVALID, "bad argument to pe_model_profile_ops");
   for (int i = 0; i < n_ops; ++i) ms_per_op[i] = i < (int)m->op_ms.size() ? m->op_ms[i] : 0.0;

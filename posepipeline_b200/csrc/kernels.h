@@ -35,4 +35,5 @@ cudaError_t tc_conv_plan_create(TcConvPlan** plan, const float* in, float* out, 
                                 const float* bias, int Cin, int Cout, int ks, int relu, int H, int W, int max_img,
                                 const float* gather_src = nullptr);
 void tc_conv_plan_destroy(TcConvPlan* plan);
+int tc_plan_candidates(int Cin, int Cout, int ks, int has_res, int H, int W, int max_img, int gather, int32_t* out, int cap);
 cudaError_t tc_conv_launch(TcConvPlan* plan, int nimg, cudaStream_t st);

@@ -186,3 +186,48 @@ def test_videopose3d_oracle_shapes_and_normalisation():
     w = OV.windows(x, 121)
     assert w.shape == (5, 243, 17, 2) and np.array_equal(w[0, 0], x[0]) and np.array_equal(w[4, -1], x[4])
     assert np.array_equal(w[2, 121], x[2])
+
+
+# ------------------------------------------------------------------ host logic of the tensor-core planner (no GPU)
+def test_conv_planner_candidates_respect_hardware_limits():
+    """Every tiling the planner may hand to the auto-tuner must fit the SM: <= 227 KB dynamic shared memory, <= 512 TMEM
+    columns, stage bases on the swizzle period, >= 2 pipeline stages, and the HRNet-W48 / W32 layer shapes must all have a plan."""
+    import ctypes as C
+    from posepipeline_b200 import _lib
+    from posepipeline_b200.hrnet_spec import OP_CONV, build_program
+    lib = _lib.load()
+    fp16 = lib.pe_precision_mode() == 1
+    chunk_bytes = 64 if fp16 else 128
+    buf = (C.c_int32 * (64 * 12))()
+    seen = set()
+    for variant, (h, w) in (("w48", (384, 288)), ("w32", (256, 192))):
+        prog = build_program(variant, h, w, 17)
+        for op in prog.ops:
+            if op.kind != OP_CONV or op.cin % 16 or op.cout % 16:
+                continue
+            to = prog.tensors[op.out]
+            if op.stride == 2 and op.ksize != 3:
+                continue
+            key = (op.cin, op.cout, op.ksize, op.stride, to.H, to.W, op.residual >= 0)
+            if key in seen:
+                continue
+            seen.add(key)
+            cin, ks = (4 * op.cin, 2) if op.stride == 2 else (op.cin, op.ksize)
+            for gather in ((1, 0) if op.stride == 2 else (0,)):
+                n = lib.pe_tc_plan_candidates(cin, op.cout, ks, int(op.residual >= 0), to.H, to.W, 512, gather, buf, 64)
+                if gather and (not fp16 or n == 0):
+                    continue                                            # gather mode is optional (s2d copy is the fallback)
+                assert n > 0, key
+                for i in range(n):
+                    ns, mt, nc, kc, S, nstg, stage, smem, tmem, rpg, ndrain, rows = buf[12 * i:12 * i + 12]
+                    assert ns * nc == op.cout and nc % 16 == 0 and nc <= 128 and mt in (1, 2)
+                    assert 2 <= S <= 4 and 1 <= nstg <= 4
+                    assert smem <= 227 * 1024 and S * stage + 12 * nstg * 32 * chunk_bytes <= smem
+                    assert stage % (8 * chunk_bytes) == 0 and rows % 8 == 0
+                    n_main = 3 if mt * nc // 16 <= 6 else 2
+                    assert (n_main + 2) * mt * nc <= tmem <= 512
+                    assert (cin // 16) % kc == 0 and rpg >= 1 and ndrain >= 1
+                    steps = rpg * (ks if ks != 2 else 2) * (1 if fp16 else 2)       # hi*hi MMA steps per accumulation group
+                    assert steps <= (8 if ks == 2 and gather else 6) or rpg == 1
+    assert len(seen) >= 25
+    assert lib.pe_tc_plan_candidates(40, 48, 3, 0, 8, 8, 1, 0, buf, 64) < 0      # channel counts must be multiples of 16
