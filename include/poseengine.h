@@ -87,8 +87,14 @@ int pe_device_count(int* count);
 /* ---- engine: one per GPU.  `cuda_stream` may be NULL (engine creates its own) or a cudaStream_t
  * the caller times with its own events (bench.py passes torch's current stream). ---- */
 int pe_engine_create(int device, void* cuda_stream, pe_engine** out);
+/* Destroys the engine AND every model / lifter still alive on it.  All pe_*_destroy calls are idempotent: a handle that
+ * is unknown or already destroyed (e.g. a model released after its engine, as a garbage collector may do) returns PE_OK
+ * without being touched, and during process teardown (CUDA runtime unloading) only host memory is released.  This is the
+ * contract that lets a populate() worker (pose_pipeline/utils/standard_pipelines.py:100) return normally. */
 int pe_engine_destroy(pe_engine* e);
 int pe_engine_sync(pe_engine* e);
+/* Destroys every live engine of the process (the Python host registers it with atexit). */
+int pe_shutdown(void);
 
 /* Frame staging: replaces the per-frame host->device copy buried in
  * inference_top_down_pose_model (pose_pipeline/wrappers/mmpose.py:75) after cap.read() (:63).

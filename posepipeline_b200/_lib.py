@@ -2,9 +2,12 @@
 is built from csrc/ with nvcc; if that fails, importing raises."""
 from __future__ import annotations
 
+import atexit
 import ctypes as C
 import os
 import re
+import sys
+import weakref
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 # PE_PRECISION=tf32 selects the wide-range TF32x3 build (libposeengine_tf32.so); default is the fp16x2 build
@@ -69,6 +72,7 @@ def load():
         "pe_engine_create": (C.c_int, [C.c_int, vp, P(vp)]),
         "pe_engine_destroy": (C.c_int, [vp]),
         "pe_engine_sync": (C.c_int, [vp]),
+        "pe_shutdown": (C.c_int, []),
         "pe_stage_frames": (C.c_int, [vp, vp, i32, i32, i32, i64]),
         "pe_stage_frames_device": (C.c_int, [vp, vp, i32, i32, i32]),
         "pe_person_bbox": (C.c_int, [vp, i32, vp, vp, vp, i32, vp, vp]),
@@ -97,7 +101,34 @@ def load():
     if lib.pe_abi_version() != 1:
         raise ImportError("libposeengine ABI mismatch; rebuild with python -m posepipeline_b200.csrc.build --force")
     _lib = lib
+    atexit.register(shutdown)
     return lib
+
+
+# Python objects holding a live C handle (PoseEngine / TopDownModel / Lifter ...).  The atexit hook destroys every engine
+# (and with it every model / lifter) BEFORE interpreter finalisation and CUDA teardown, and clears the Python-side handles,
+# so no __del__ touches CUDA afterwards: a worker process that used the wrappers exits 0.
+_handles = weakref.WeakSet()
+
+
+def track(obj):
+    _handles.add(obj)
+    return obj
+
+
+def finalizing() -> bool:
+    return sys.is_finalizing()
+
+
+def shutdown():
+    """Destroy all engines, models and lifters of this process (idempotent; also usable between tests)."""
+    for o in list(_handles):
+        try:
+            o.h = None
+        except Exception:
+            pass
+    if _lib is not None:
+        _lib.pe_shutdown()
 
 
 def check(rc):

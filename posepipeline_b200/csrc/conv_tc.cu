@@ -1026,7 +1026,7 @@ static cudaError_t tc_build(TcConvPlan* pl, const TcCand& c, const float* in, fl
     return cudaErrorInvalidValue;
   }
   pl->kernel = tc_kernel_for(c.MT, c.NC, ntaps, c.KC);
-  return cudaFuncSetAttribute(pl->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+  return pe_smem_optin((const void*)pl->kernel, (int)(227 * 1024));
 }
 
 // Tiling choice.  The candidates compute bit-identical results (the accumulation order over K does not depend on the
@@ -1136,7 +1136,7 @@ int tc_plan_candidates(int Cin, int Cout, int ks, int has_res, int H, int W, int
   return n;
 }
 
-void tc_conv_plan_destroy(TcConvPlan* plan) { if (plan && plan->p.prof) cudaFree(plan->p.prof); delete plan; }
+void tc_conv_plan_destroy(TcConvPlan* plan, bool cuda_ok) { if (plan && plan->p.prof && cuda_ok) cudaFree(plan->p.prof); delete plan; }
 
 cudaError_t tc_conv_launch(TcConvPlan* pl, int nimg, cudaStream_t st) {
   TcParams p = pl->p;

@@ -10,9 +10,8 @@
 #include "pe_common.cuh"
 #include "kernels.h"
 
-__constant__ float c_gauss[64];  // 1-D Gaussian taps (cv2.getGaussianKernel(k, 0.3*((k-1)*0.5-1)+0.8), float32)
-
-void upload_gauss_kernel(const float* taps, int k) { cudaMemcpyToSymbol(c_gauss, taps, sizeof(float) * k); }
+// 1-D Gaussian taps (cv2.getGaussianKernel(k, 0.3*((k-1)*0.5-1)+0.8), float32) come per model through DecodeArgs::gauss
+// (device buffer of 64 floats) and are copied to shared memory: two models with different modulate_kernel values coexist.
 
 struct DecodeArgs {
   const float* hm;       // [n][K][H][W]
@@ -21,6 +20,7 @@ struct DecodeArgs {
   const float* center;   // [n][2]
   const float* scale;    // [n][2]
   float* out;            // [n][K][3]
+  const float* gauss;    // [64] taps (post == 2)
   int K, H, W, shift, post, ksize;
 };
 
@@ -60,6 +60,8 @@ __global__ void __launch_bounds__(256) decode_kernel(DecodeArgs a) {
   float* s_b = smem + 2 * HW;  // blurred
   __shared__ float s_v[8];
   __shared__ int s_i[8];
+  __shared__ float c_gauss[64];
+  if (threadIdx.x < 64) c_gauss[threadIdx.x] = a.gauss ? a.gauss[threadIdx.x] : 0.f;   // visible after block_argmax's barrier
 
   const int k = blockIdx.x, n = blockIdx.y;
   const float* src = a.hm + ((size_t)n * a.K + k) * HW;
@@ -163,16 +165,13 @@ int decode_smem_bytes(int H, int W) { return 3 * H * W * (int)sizeof(float); }
 
 cudaError_t launch_decode(const float* hm, const float* hm_flip, const int* flip_perm, const float* center,
                           const float* scale, float* out, int n, int K, int H, int W, int shift, int post, int ksize,
-                          cudaStream_t st) {
-  static int configured = 0;
+                          const float* gauss, cudaStream_t st) {
   const int smem = decode_smem_bytes(H, W);
-  if (configured < smem) {
-    cudaError_t e = cudaFuncSetAttribute(decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    configured = smem;
-  }
   if (smem > 220 * 1024) return cudaErrorInvalidValue;
-  DecodeArgs a{hm, hm_flip, flip_perm, center, scale, out, K, H, W, shift, post, ksize};
+  if (post == 2 && !gauss) return cudaErrorInvalidValue;
+  cudaError_t e = pe_smem_optin((const void*)decode_kernel, smem);
+  if (e != cudaSuccess) return e;
+  DecodeArgs a{hm, hm_flip, flip_perm, center, scale, out, gauss, K, H, W, shift, post, ksize};
   decode_kernel<<<dim3(K, n), 256, smem, st>>>(a);
   return cudaGetLastError();
 }

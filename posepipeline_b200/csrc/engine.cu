@@ -8,8 +8,12 @@
 #include <string>
 #include <vector>
 #include <map>
+#include <mutex>
+#include <set>
+#include <algorithm>
 
 #include "../../include/poseengine.h"
+#include "engine_internal.h"
 #include "kernels.h"
 #include "pe_common.cuh"
 
@@ -32,6 +36,45 @@ static int fail(int code, const char* fmt, ...) {
   } while (0)
 
 int pe_set_error(int code, const char* msg) { g_err = msg ? msg : ""; return code; }
+int pe_fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+// ------------------------------------------------------------------------------------------ live handles
+// Heap-allocated and never freed on purpose: handles may be released from interpreter-exit paths that run after this
+// library's static destructors would have run.
+struct Registry { std::mutex mu; std::set<void*> live[4]; };
+static Registry& registry() { static Registry* r = new Registry(); return *r; }
+void pe_handle_register(int kind, void* h) { Registry& r = registry(); std::lock_guard<std::mutex> g(r.mu); r.live[kind].insert(h); }
+bool pe_handle_release(int kind, void* h) { Registry& r = registry(); std::lock_guard<std::mutex> g(r.mu); return r.live[kind].erase(h) != 0; }
+bool pe_handle_alive(int kind, void* h) { Registry& r = registry(); std::lock_guard<std::mutex> g(r.mu); return r.live[kind].count(h) != 0; }
+cudaError_t pe_smem_optin(const void* func, int bytes) {
+  static std::mutex* mu = new std::mutex();
+  static std::map<std::pair<const void*, int>, int>* done = new std::map<std::pair<const void*, int>, int>();
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> g(*mu);
+  int& have = (*done)[std::make_pair(func, dev)];
+  if (have >= bytes) return cudaSuccess;
+  e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) have = bytes;
+  return e;
+}
+#define MODEL_ALIVE(m) do { if (!(m) || !pe_handle_alive(PE_H_MODEL, (m))) return fail(PE_ERR_STATE, "model handle is NULL or was destroyed (with its engine?)"); } while (0)
+#define ENGINE_ALIVE(e) do { if (!(e) || !pe_handle_alive(PE_H_ENGINE, (e))) return fail(PE_ERR_STATE, "engine handle is NULL or was destroyed"); } while (0)
+
+bool pe_cuda_usable(int device) {
+  const cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) { cudaGetLastError(); return false; }
+  return true;
+}
 
 extern "C" int pe_abi_version(void) { return PE_ABI_VERSION; }
 extern "C" int pe_precision_mode(void) { return PE_FP16 ? 1 : 0; }
@@ -45,15 +88,6 @@ extern "C" int pe_device_count(int* count) {
 }
 
 // ------------------------------------------------------------------------------------------ engine
-struct pe_engine {
-  int device = 0;
-  cudaStream_t stream = nullptr;
-  bool own_stream = false;
-  uint8_t* d_frames = nullptr;       // owned frame store
-  const uint8_t* frames = nullptr;   // current frames (owned store or caller's device memory)
-  size_t frames_cap = 0;
-  int n_frames = 0, fh = 0, fw = 0;
-};
 
 extern "C" int pe_engine_create(int device, void* cuda_stream, pe_engine** out) {
   if (!out) return fail(PE_ERR_INVALID, "out is NULL");
@@ -75,29 +109,49 @@ extern "C" int pe_engine_create(int device, void* cuda_stream, pe_engine** out) 
     CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     e->own_stream = true;
   }
+  pe_handle_register(PE_H_ENGINE, e);
   *out = e;
   return PE_OK;
 }
 
 extern "C" int pe_engine_destroy(pe_engine* e) {
-  if (!e) return PE_OK;
-  cudaSetDevice(e->device);
-  cudaStreamSynchronize(e->stream);
-  if (e->d_frames) cudaFree(e->d_frames);
-  if (e->own_stream) cudaStreamDestroy(e->stream);
+  if (!e || !pe_handle_alive(PE_H_ENGINE, e)) return PE_OK;
+  // children first (copies: the destroy calls edit the lists)
+  { const std::vector<pe_model*> c = e->models; for (pe_model* m : c) pe_model_destroy(m); }
+  { const std::vector<pe_lifter*> c = e->lifters; for (pe_lifter* l : c) pe_lifter_destroy(l); }
+  if (!pe_handle_release(PE_H_ENGINE, e)) return PE_OK;
+  if (pe_cuda_usable(e->device)) {
+    cudaStreamSynchronize(e->stream);
+    if (e->d_frames) cudaFree(e->d_frames);
+    if (e->own_stream) cudaStreamDestroy(e->stream);
+    cudaGetLastError();
+  }
   delete e;
   return PE_OK;
 }
 
+// Destroys every live engine (and with it every model / lifter / detector).  Called by the Python host's atexit hook so no
+// handle outlives the interpreter; safe to call more than once.
+extern "C" int pe_shutdown(void) {
+  for (;;) {
+    void* h = nullptr;
+    { Registry& r = registry(); std::lock_guard<std::mutex> g(r.mu); if (!r.live[PE_H_ENGINE].empty()) h = *r.live[PE_H_ENGINE].begin(); }
+    if (!h) break;
+    pe_engine_destroy((pe_engine*)h);
+  }
+  return PE_OK;
+}
+
 extern "C" int pe_engine_sync(pe_engine* e) {
-  if (!e) return fail(PE_ERR_INVALID, "engine is NULL");
+  ENGINE_ALIVE(e);
   CU(cudaStreamSynchronize(e->stream));
   return PE_OK;
 }
 
 extern "C" int pe_stage_frames(pe_engine* e, const uint8_t* frames, int32_t n, int32_t height, int32_t width,
                                int64_t frame_stride_bytes) {
-  if (!e || !frames || n <= 0 || height <= 0 || width <= 0) return fail(PE_ERR_INVALID, "bad argument to pe_stage_frames");
+  ENGINE_ALIVE(e);
+  if (!frames || n <= 0 || height <= 0 || width <= 0) return fail(PE_ERR_INVALID, "bad argument to pe_stage_frames");
   CU(cudaSetDevice(e->device));
   const size_t fb = (size_t)height * width * 3;
   if (frame_stride_bytes == 0) frame_stride_bytes = (int64_t)fb;
@@ -116,7 +170,8 @@ extern "C" int pe_stage_frames(pe_engine* e, const uint8_t* frames, int32_t n, i
 }
 
 extern "C" int pe_stage_frames_device(pe_engine* e, const uint8_t* d_frames, int32_t n, int32_t height, int32_t width) {
-  if (!e || !d_frames || n <= 0) return fail(PE_ERR_INVALID, "bad argument to pe_stage_frames_device");
+  ENGINE_ALIVE(e);
+  if (!d_frames || n <= 0) return fail(PE_ERR_INVALID, "bad argument to pe_stage_frames_device");
   e->frames = d_frames;
   e->n_frames = n; e->fh = height; e->fw = width;
   return PE_OK;
@@ -268,6 +323,7 @@ struct pe_model {
   float* d_cs = nullptr;        // center[max][2] then scale[max][2]
   float* d_hm = nullptr;        // [2*max][K][hh][hw]
   float* d_out = nullptr;       // [max][K][3]
+  float* d_gauss = nullptr;     // [64] 1-D Gaussian taps of this model's modulate_kernel
   // pinned staging
   double* h_minv = nullptr; int32_t* h_fidx = nullptr; float* h_cs = nullptr; float* h_out = nullptr;
   int nimg_last = 0, ncrop_last = 0;
@@ -298,20 +354,29 @@ static void gauss_taps(int k, float* out) {
   for (int i = 0; i < k; ++i) out[i] = (float)(t[i] * sum);
 }
 
-extern "C" int pe_model_destroy(pe_model* m) {
-  if (!m) return PE_OK;
-  cudaSetDevice(m->e->device);
-  cudaStreamSynchronize(m->e->stream);
-  for (auto& g : m->graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
-  for (auto* p : m->tc) if (p) tc_conv_plan_destroy(p);
-  for (auto* p : m->slots) if (p) cudaFree(p);
-  cudaFree(m->d_w); cudaFree(m->d_s2d); cudaFree(m->d_lut); cudaFree(m->d_perm); cudaFree(m->d_crops); cudaFree(m->d_minv);
-  cudaFree(m->d_fidx); cudaFree(m->d_cs); cudaFree(m->d_hm); cudaFree(m->d_out);
-  cudaFreeHost(m->h_minv); cudaFreeHost(m->h_fidx); cudaFreeHost(m->h_cs); cudaFreeHost(m->h_out);
-  for (auto& p : m->ev_conv) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
-  if (m->ev_fwd0) cudaEventDestroy(m->ev_fwd0);
-  if (m->ev_fwd1) cudaEventDestroy(m->ev_fwd1);
+// releases the device / pinned resources of a model; `registered` = it went through pe_handle_register
+static void model_free(pe_model* m, bool cuda_ok) {
+  if (cuda_ok) {
+    cudaStreamSynchronize(m->e->stream);
+    for (auto& g : m->graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
+    for (auto* p : m->slots) if (p) cudaFree(p);
+    cudaFree(m->d_w); cudaFree(m->d_s2d); cudaFree(m->d_lut); cudaFree(m->d_perm); cudaFree(m->d_crops); cudaFree(m->d_minv);
+    cudaFree(m->d_fidx); cudaFree(m->d_cs); cudaFree(m->d_hm); cudaFree(m->d_out); cudaFree(m->d_gauss);
+    cudaFreeHost(m->h_minv); cudaFreeHost(m->h_fidx); cudaFreeHost(m->h_cs); cudaFreeHost(m->h_out);
+    for (auto& p : m->ev_conv) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+    if (m->ev_fwd0) cudaEventDestroy(m->ev_fwd0);
+    if (m->ev_fwd1) cudaEventDestroy(m->ev_fwd1);
+    cudaGetLastError();
+  }
+  for (auto* p : m->tc) if (p) tc_conv_plan_destroy(p, cuda_ok);
   delete m;
+}
+
+extern "C" int pe_model_destroy(pe_model* m) {
+  if (!m || !pe_handle_release(PE_H_MODEL, m)) return PE_OK;      // unknown or already destroyed (e.g. with its engine)
+  pe_engine* e = m->e;
+  e->models.erase(std::remove(e->models.begin(), e->models.end(), m), e->models.end());
+  model_free(m, pe_cuda_usable(e->device));
   return PE_OK;
 }
 
@@ -320,6 +385,7 @@ extern "C" int pe_model_create(pe_engine* e, const pe_model_desc* desc, const pe
                                const float* norm_lut, const int32_t* flip_perm, pe_model** out) {
   if (!e || !desc || !ops || !tensors || !slot_elems || !weights || !norm_lut || !flip_perm || !out)
     return fail(PE_ERR_INVALID, "NULL argument to pe_model_create");
+  ENGINE_ALIVE(e);
   if (desc->max_crops <= 0 || desc->n_ops <= 0) return fail(PE_ERR_INVALID, "bad model description");
   if (desc->post_process == PE_POST_UNBIASED && (desc->blur_kernel < 3 || desc->blur_kernel > 63 || desc->blur_kernel % 2 == 0))
     return fail(PE_ERR_INVALID, "blur kernel must be odd and in [3,63]");
@@ -330,7 +396,7 @@ extern "C" int pe_model_create(pe_engine* e, const pe_model_desc* desc, const pe
   m->tensors.assign(tensors, tensors + desc->n_tensors);
   const int maxc = desc->max_crops, maximg = maxc * (desc->flip_test ? 2 : 1);
   const int K = desc->num_joints;
-#define CUM(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { int rc = fail(PE_ERR_CUDA, "%s failed: %s", #x, cudaGetErrorString(_e)); pe_model_destroy(m); return rc; } } while (0)
+#define CUM(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { int rc = fail(PE_ERR_CUDA, "%s failed: %s", #x, cudaGetErrorString(_e)); model_free(m, true); return rc; } } while (0)
   m->slots.assign(desc->n_slots, nullptr);
   for (int s = 0; s < desc->n_slots; ++s) {
     const size_t bytes = (size_t)slot_elems[s] / 16 * PS_CHUNK_BYTES * maximg;   // elems = padded pixels x channels
@@ -355,10 +421,13 @@ extern "C" int pe_model_create(pe_engine* e, const pe_model_desc* desc, const pe
   CUM(cudaMallocHost(&m->h_out, sizeof(float) * (size_t)maxc * K * 3));
   CUM(cudaEventCreate(&m->ev_fwd0));
   CUM(cudaEventCreate(&m->ev_fwd1));
-  if (desc->post_process == PE_POST_UNBIASED) {
-    float taps[64];
-    gauss_taps(desc->blur_kernel, taps);
-    upload_gauss_kernel(taps, desc->blur_kernel);
+  {
+    // Gaussian taps of THIS model's modulate_kernel (a device buffer per model: two models with different kernels coexist)
+    float taps[64] = {0};
+    if (desc->post_process == PE_POST_UNBIASED) gauss_taps(desc->blur_kernel, taps);
+    CUM(cudaMalloc(&m->d_gauss, sizeof taps));
+    CUM(cudaMemcpyAsync(m->d_gauss, taps, sizeof taps, cudaMemcpyHostToDevice, e->stream));
+    CUM(cudaStreamSynchronize(e->stream));       // `taps` is a stack buffer
   }
   // tensor-core plans for eligible convolutions
   m->tc.assign(desc->n_ops, nullptr);
@@ -395,13 +464,15 @@ extern "C" int pe_model_create(pe_engine* e, const pe_model_desc* desc, const pe
       if (ce == cudaSuccess) m->tc[i] = plan;
       else if (ce != cudaErrorNotSupported) {
         int rc = fail(PE_ERR_CUDA, "tensor-core plan for op %d failed: %s", i, cudaGetErrorString(ce));
-        pe_model_destroy(m);
+        model_free(m, true);
         return rc;
       }
     }
   }
   CUM(cudaStreamSynchronize(e->stream));
 #undef CUM
+  e->models.push_back(m);
+  pe_handle_register(PE_H_MODEL, m);
   *out = m;
   return PE_OK;
 }
@@ -519,7 +590,8 @@ static int profile_collect(pe_model* m) {
 }
 
 static int check_crops(pe_model* m, const int32_t* frame_idx, const double* bbox, int n) {
-  if (!m || !frame_idx || !bbox || n < 0) return fail(PE_ERR_INVALID, "bad argument");
+  MODEL_ALIVE(m);
+  if (!frame_idx || !bbox || n < 0) return fail(PE_ERR_INVALID, "bad argument");
   if (!m->e->frames) return fail(PE_ERR_STATE, "no frames staged: call pe_stage_frames first");
   for (int i = 0; i < n; ++i)
     if (frame_idx[i] < 0 || frame_idx[i] >= m->e->n_frames)
@@ -552,7 +624,7 @@ static int stage_crops(pe_model* m, const int32_t* frame_idx, const double* bbox
 static int run_decode(pe_model* m, const float* d_hm, const float* d_hm_flip, const float* d_center, const float* d_scale,
                       int nc, float* d_out) {
   cudaError_t ce = launch_decode(d_hm, d_hm_flip, m->d_perm, d_center, d_scale, d_out, nc, m->d.num_joints, m->d.hm_h,
-                                 m->d.hm_w, m->d.shift_heatmap, m->d.post_process, m->d.blur_kernel, m->e->stream);
+                                 m->d.hm_w, m->d.shift_heatmap, m->d.post_process, m->d.blur_kernel, m->d_gauss, m->e->stream);
   ++m->launches;
   if (ce != cudaSuccess) return fail(PE_ERR_CUDA, "decode launch: %s", cudaGetErrorString(ce));
   return PE_OK;
@@ -616,7 +688,8 @@ extern "C" int pe_warp_crops(pe_model* m, const int32_t* frame_idx, const double
 }
 
 extern "C" int pe_forward_heatmaps(pe_model* m, const uint8_t* crops, int32_t n, float* hm_plain, float* hm_flipped) {
-  if (!m || !crops || n <= 0 || !hm_plain) return fail(PE_ERR_INVALID, "bad argument to pe_forward_heatmaps");
+  MODEL_ALIVE(m);
+  if (!crops || n <= 0 || !hm_plain) return fail(PE_ERR_INVALID, "bad argument to pe_forward_heatmaps");
   CU(cudaSetDevice(m->e->device));
   cudaStream_t st = m->e->stream;
   const int maxc = m->d.max_crops, K = m->d.num_joints;
@@ -638,7 +711,8 @@ extern "C" int pe_forward_heatmaps(pe_model* m, const uint8_t* crops, int32_t n,
 
 extern "C" int pe_decode_heatmaps(pe_model* m, const float* hm_plain, const float* hm_flipped, const float* center,
                                   const float* scale, int32_t n, float* out_kpts) {
-  if (!m || !hm_plain || !center || !scale || !out_kpts || n <= 0) return fail(PE_ERR_INVALID, "bad argument to pe_decode_heatmaps");
+  MODEL_ALIVE(m);
+  if (!hm_plain || !center || !scale || !out_kpts || n <= 0) return fail(PE_ERR_INVALID, "bad argument to pe_decode_heatmaps");
   CU(cudaSetDevice(m->e->device));
   cudaStream_t st = m->e->stream;
   const int maxc = m->d.max_crops, K = m->d.num_joints;
@@ -658,7 +732,8 @@ extern "C" int pe_decode_heatmaps(pe_model* m, const float* hm_plain, const floa
 }
 
 extern "C" int pe_debug_tensor(pe_model* m, int32_t tensor_id, int32_t img, float* out_chw) {
-  if (!m || !out_chw || tensor_id < 0 || tensor_id >= (int)m->tensors.size()) return fail(PE_ERR_INVALID, "bad argument to pe_debug_tensor");
+  MODEL_ALIVE(m);
+  if (!out_chw || tensor_id < 0 || tensor_id >= (int)m->tensors.size()) return fail(PE_ERR_INVALID, "bad argument to pe_debug_tensor");
   if (img < 0 || img >= m->nimg_last) return fail(PE_ERR_STATE, "image %d not in the last forward batch (%d images)", img, m->nimg_last);
   CU(cudaSetDevice(m->e->device));
   const pe_tensor_desc& t = m->tensors[tensor_id];
@@ -674,13 +749,14 @@ extern "C" int pe_debug_tensor(pe_model* m, int32_t tensor_id, int32_t img, floa
 }
 
 extern "C" int pe_model_launch_count(pe_model* m, int64_t* count) {
-  if (!m || !count) return fail(PE_ERR_INVALID, "bad argument");
+  MODEL_ALIVE(m);
+  if (!count) return fail(PE_ERR_INVALID, "bad argument");
   *count = m->launches;
   return PE_OK;
 }
 
 extern "C" int pe_model_profile(pe_model* m, int32_t enable) {
-  if (!m) return fail(PE_ERR_INVALID, "bad argument");
+  MODEL_ALIVE(m);
   m->profile = enable;
   m->acc_conv_ms = m->acc_total_ms = 0; m->acc_conv_launches = 0;
   m->op_ms.assign(m->ops.size(), 0.0);
@@ -688,7 +764,7 @@ extern "C" int pe_model_profile(pe_model* m, int32_t enable) {
 }
 
 extern "C" int pe_model_profile_read(pe_model* m, double* conv_ms, double* other_ms, int64_t* conv_launches) {
-  if (!m) return fail(PE_ERR_INVALID, "bad argument");
+  MODEL_ALIVE(m);
   if (conv_ms) *conv_ms = m->acc_conv_ms;
   if (other_ms) *other_ms = m->acc_total_ms - m->acc_conv_ms;
   if (conv_launches) *conv_launches = m->acc_conv_launches;
@@ -699,7 +775,8 @@ extern "C" int pe_model_profile_read(pe_model* m, double* conv_ms, double* other
 extern "C" int pe_conv_test(pe_engine* e, const float* in_nchw, int32_t nimg, int32_t Cin, int32_t H, int32_t W,
                             const float* w_simt, const float* w_tc, const float* bias, const float* res_nchw, int32_t Cout,
                             int32_t ks, int32_t stride, int32_t relu, int32_t use_tc, float* out_nchw) {
-  if (!e || !in_nchw || !w_simt || !bias || !out_nchw || nimg <= 0) return fail(PE_ERR_INVALID, "bad argument to pe_conv_test");
+  ENGINE_ALIVE(e);
+  if (!in_nchw || !w_simt || !bias || !out_nchw || nimg <= 0) return fail(PE_ERR_INVALID, "bad argument to pe_conv_test");
   if (Cin % 16 || Cout % 16) return fail(PE_ERR_INVALID, "pe_conv_test needs channel counts that are multiples of 16");
   CU(cudaSetDevice(e->device));
   cudaStream_t st = e->stream;
@@ -787,7 +864,8 @@ extern "C" int pe_tc_plan_candidates(int32_t Cin, int32_t Cout, int32_t ks, int3
 }
 
 extern "C" int pe_model_profile_ops(pe_model* m, double* ms_per_op, int32_t n_ops) {
-  if (!m || !ms_per_op || n_ops != (int32_t)m->ops.size()) return fail(PE_ERR_INVALID, "bad argument to pe_model_profile_ops");
+  MODEL_ALIVE(m);
+  if (!ms_per_op || n_ops != (int32_t)m->ops.size()) return fail(PE_ERR_INVALID, "bad argument to pe_model_profile_ops");
   for (int i = 0; i < n_ops; ++i) ms_per_op[i] = i < (int)m->op_ms.size() ? m->op_ms[i] : 0.0;
   return PE_OK;
 }

@@ -1,0 +1,34 @@
+// Internal (non-ABI) definitions shared by the translation units of libposeengine.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <vector>
+
+#include "../../include/poseengine.h"
+
+struct pe_engine {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  uint8_t* d_frames = nullptr;       // owned frame store
+  const uint8_t* frames = nullptr;   // current frames (owned store or caller's device memory)
+  size_t frames_cap = 0;
+  int n_frames = 0, fh = 0, fw = 0;
+  // handles created on this engine and still alive: pe_engine_destroy destroys them first, so a model / lifter handle
+  // released after its engine (garbage-collection order is arbitrary on the Python side) is a no-op, never a dangling `e`
+  std::vector<pe_model*> models;
+  std::vector<pe_lifter*> lifters;
+};
+
+// Live-handle registry (engine.cu).  Every pe_*_destroy first asks pe_handle_release(): false = the handle is not (or no
+// longer) alive -> the destroy call returns PE_OK without touching it.
+enum { PE_H_ENGINE = 0, PE_H_MODEL = 1, PE_H_LIFTER = 2, PE_H_DETECTOR = 3 };
+void pe_handle_register(int kind, void* h);
+bool pe_handle_release(int kind, void* h);
+bool pe_handle_alive(int kind, void* h);
+// true when the CUDA runtime can still be used on `device` (false during process teardown: cudaErrorCudartUnloading,
+// destroyed primary context); destroy paths then only release host memory
+bool pe_cuda_usable(int device);
+
+int pe_set_error(int code, const char* msg);
+int pe_fail(int code, const char* fmt, ...);

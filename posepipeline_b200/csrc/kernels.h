@@ -22,10 +22,12 @@ void launch_ps_to_chw(const float* in, int C, int H, int W, int img, float* out,
 void launch_s2d(const float* in, int C, int Hin, int Win, int nimg, float* out, int Hout, int Wout, cudaStream_t st);
 void launch_chw_to_ps(const float* in, int C, int H, int W, int nimg, float* out, cudaStream_t st);
 
-void upload_gauss_kernel(const float* taps, int k);
+// opt a kernel into `bytes` of dynamic shared memory on the CURRENT device (the attribute is per device; cached per
+// (function, device) so the steady state costs one map lookup)
+cudaError_t pe_smem_optin(const void* func, int bytes);
 cudaError_t launch_decode(const float* hm, const float* hm_flip, const int* flip_perm, const float* center,
                           const float* scale, float* out, int n, int K, int H, int W, int shift, int post, int ksize,
-                          cudaStream_t st);
+                          const float* gauss /*64 taps on the device, post == 2*/, cudaStream_t st);
 
 // Shifted-row GEMM on tensor cores (conv_tc.cu).  Returns cudaErrorNotSupported for shapes it does not cover.
 struct TcConvPlan;
@@ -34,6 +36,6 @@ struct TcConvPlan;
 cudaError_t tc_conv_plan_create(TcConvPlan** plan, const float* in, float* out, const float* res, const float* wtc,
                                 const float* bias, int Cin, int Cout, int ks, int relu, int H, int W, int max_img,
                                 const float* gather_src = nullptr);
-void tc_conv_plan_destroy(TcConvPlan* plan);
+void tc_conv_plan_destroy(TcConvPlan* plan, bool cuda_ok = true);
 int tc_plan_candidates(int Cin, int Cout, int ks, int has_res, int H, int W, int max_img, int gather, int32_t* out, int cap);
 cudaError_t tc_conv_launch(TcConvPlan* plan, int nimg, cudaStream_t st);

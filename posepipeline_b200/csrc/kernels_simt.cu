@@ -179,8 +179,7 @@ __global__ void __launch_bounds__(256, 2) stem_kernel(const uint8_t* __restrict_
 
 void launch_stem(const uint8_t* crops, int ncrop, int nimg, int ih, int iw, const float* lut, const float* w,
                  const float* bias, float* out, int oh, int ow, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STEM_SMEM); attr = true; }
+  if (pe_smem_optin((const void*)stem_kernel, (int)STEM_SMEM) != cudaSuccess) return;   // the launch below then fails and is reported
   dim3 grid((ow + 2 + STEM_T - 1) / STEM_T, (oh + 2 + STEM_T - 1) / STEM_T, nimg);
   stem_kernel<<<grid, 256, STEM_SMEM, st>>>(crops, ncrop, nimg, ih, iw, lut, w, bias, out, oh, ow);
 }

@@ -14,13 +14,15 @@
 #include <string>
 #include <vector>
 
+#include <algorithm>
+
 #include "../../include/poseengine.h"
+#include "engine_internal.h"
 #include "kernels.h"
 #include "pe_common.cuh"
 
-struct pe_engine_view { int device; cudaStream_t stream; };  // leading fields of pe_engine (engine.cu)
-
 struct pe_lifter {
+  pe_engine* e = nullptr;
   int device; cudaStream_t stream;
   int channels;
   float* d_w = nullptr;
@@ -29,8 +31,6 @@ struct pe_lifter {
   float* d_in = nullptr; float* d_out = nullptr;
   size_t cap_rows = 0;
 };
-
-int pe_set_error(int code, const char* msg);  // engine.cu
 
 __global__ void lifter_pack_input(const float* __restrict__ kp, int n_frames, int pad, float* __restrict__ out, int T0) {
   // out: PS rows [T0][48ch -> 3 chunks of (hi16|lo16)], channels 0..33 = (joint, xy) of the edge-replicated frame
@@ -49,9 +49,9 @@ extern "C" int pe_lifter_create(pe_engine* e, const float* weights, int64_t n_fl
                                 int32_t channels, pe_lifter** out) {
   if (!e || !weights || !offsets || !out || n_offsets != 20 || channels % 48 != 0 && channels % 64 != 0)
     return pe_set_error(PE_ERR_INVALID, "bad argument to pe_lifter_create (need 20 offsets: 10 layers x (w,b))");
-  const pe_engine_view* ev = reinterpret_cast<const pe_engine_view*>(e);
+  if (!pe_handle_alive(PE_H_ENGINE, e)) return pe_set_error(PE_ERR_INVALID, "pe_lifter_create: engine handle is not alive");
   pe_lifter* l = new pe_lifter();
-  l->device = ev->device; l->stream = ev->stream; l->channels = channels;
+  l->e = e; l->device = e->device; l->stream = e->stream; l->channels = channels;
   l->off.assign(offsets, offsets + n_offsets);
   cudaSetDevice(l->device);
   if (cudaMalloc(&l->d_w, sizeof(float) * n_floats) != cudaSuccess ||
@@ -60,21 +60,27 @@ extern "C" int pe_lifter_create(pe_engine* e, const float* weights, int64_t n_fl
     delete l;
     return pe_set_error(PE_ERR_CUDA, "pe_lifter_create: weight upload failed");
   }
+  e->lifters.push_back(l);
+  pe_handle_register(PE_H_LIFTER, l);
   *out = l;
   return PE_OK;
 }
 
 extern "C" int pe_lifter_destroy(pe_lifter* l) {
-  if (!l) return PE_OK;
-  cudaSetDevice(l->device);
-  cudaStreamSynchronize(l->stream);
-  cudaFree(l->d_w); cudaFree(l->d_a); cudaFree(l->d_b); cudaFree(l->d_c); cudaFree(l->d_in); cudaFree(l->d_out);
+  if (!l || !pe_handle_release(PE_H_LIFTER, l)) return PE_OK;     // unknown or already destroyed (e.g. with its engine)
+  l->e->lifters.erase(std::remove(l->e->lifters.begin(), l->e->lifters.end(), l), l->e->lifters.end());
+  if (pe_cuda_usable(l->device)) {
+    cudaStreamSynchronize(l->stream);
+    cudaFree(l->d_w); cudaFree(l->d_a); cudaFree(l->d_b); cudaFree(l->d_c); cudaFree(l->d_in); cudaFree(l->d_out);
+    cudaGetLastError();
+  }
   delete l;
   return PE_OK;
 }
 
 extern "C" int pe_lift3d(pe_lifter* l, const float* kp2d_norm, int32_t n_frames, float* out3d) {
-  if (!l || !kp2d_norm || !out3d || n_frames <= 0) return pe_set_error(PE_ERR_INVALID, "bad argument to pe_lift3d");
+  if (!l || !pe_handle_alive(PE_H_LIFTER, l)) return pe_set_error(PE_ERR_STATE, "lifter handle is NULL or was destroyed (with its engine?)");
+  if (!kp2d_norm || !out3d || n_frames <= 0) return pe_set_error(PE_ERR_INVALID, "bad argument to pe_lift3d");
   cudaSetDevice(l->device);
   cudaStream_t st = l->stream;
   const int pad = 121, C = l->channels;

@@ -213,6 +213,7 @@ class PoseEngine:
         self.h = h
         self.device = device
         self._frames_keepalive = None
+        _lib.track(self)
 
     def stage_frames(self, frames: np.ndarray):
         """frames (n,H,W,3) uint8 BGR as cv2 returns them.  Asynchronous H2D on the engine stream."""
@@ -233,11 +234,14 @@ class PoseEngine:
         check(self.lib.pe_engine_sync(self.h))
 
     def close(self):
+        """Destroys the engine and every model / lifter created on it (their Python objects become inert)."""
         if getattr(self, "h", None):
             self.lib.pe_engine_destroy(self.h)
             self.h = None
 
     def __del__(self):
+        if _lib.finalizing():          # interpreter exit: _lib.shutdown() (atexit) has already released everything
+            return
         try:
             self.close()
         except Exception:
@@ -341,6 +345,7 @@ class TopDownModel:
                                        ptr(lut), ptr(perm), C.byref(h)))
         self.h = h
         self.desc = desc
+        _lib.track(self)
 
     # ---- the hot path
     def topdown(self, frame_idx: Sequence[int], bboxes_xywh: np.ndarray) -> np.ndarray:
@@ -412,10 +417,12 @@ class TopDownModel:
 
     def close(self):
         if getattr(self, "h", None):
-            self.lib.pe_model_destroy(self.h)
+            self.lib.pe_model_destroy(self.h)      # no-op in C if the engine was destroyed first
             self.h = None
 
     def __del__(self):
+        if _lib.finalizing():
+            return
         try:
             self.close()
         except Exception:
@@ -451,6 +458,7 @@ class Lifter:
         h = C.c_void_p()
         check(self.lib.pe_lifter_create(engine.h, ptr(w), w.size, ptr(offs_a), len(offs), channels, C.byref(h)))
         self.h = h
+        _lib.track(self)
 
     def lift(self, kp2d_norm: np.ndarray) -> np.ndarray:
         """(N,17,2) normalised screen coordinates -> (N,17,3) float32."""
@@ -465,6 +473,8 @@ class Lifter:
             self.h = None
 
     def __del__(self):
+        if _lib.finalizing():
+            return
         try:
             self.close()
         except Exception:

@@ -1,4 +1,5 @@
 #!/bin/bash
+set -o pipefail
 VAR=$1; shift
 for v in "$@"; do
 env $VAR=$v timeout 600 python bench.py --steps 6 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "

@@ -1,4 +1,5 @@
 #!/bin/bash
+set -o pipefail
 mkdir -p gpurun_out
 
 PE_TC_PROF=1 timeout 300 python tests/layer_perf.py 128 1 2>&1 | grep "conv_tc prof" | sed 's/per-CTA cycles //' > gpurun_out/prof9.txt

@@ -1,4 +1,5 @@
 #!/bin/bash
+set -o pipefail
 TAG=${1:-it}
 mkdir -p gpurun_out
 timeout 300 python tests/tc_bringup.py 13 3 2>&1 | grep -E "TC  |FAIL|rror|timeout" | awk '{print $1,$2,$(NF-3),$(NF-2),$(NF-1)}'

@@ -1,8 +1,11 @@
 #!/bin/bash
+set -o pipefail
 # one GPU-box visit: parity suite, bench line, per-layer times, ncu launch list of one timed step, one --set full capture
 TAG=${1:-cur}
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -m gpu -q -s 2>&1 | grep -E "worst layers|keypoint \|dx\||passed|failed|Error|error|assert" | cut -c1-500 > gpurun_out/pytest_$TAG.log
+# the driver's exact command first (exit code of the interpreter counts: round 1 segfaulted AFTER "15 passed")
+timeout 1500 python3 -m pytest tests/ -x -q -m gpu -p no:cacheprovider > gpurun_out/pytest_full_$TAG.log 2>&1; echo "pytest -m gpu rc=$?" | tee gpurun_out/pytest_rc_$TAG.txt
+grep -E "worst layers|keypoint \|dx\||passed|failed|Error|error|assert" gpurun_out/pytest_full_$TAG.log | cut -c1-500 > gpurun_out/pytest_$TAG.log
 cat gpurun_out/pytest_$TAG.log
 timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; cat gpurun_out/bench_$TAG.json; tail -3 gpurun_out/bench_$TAG.err
 timeout 300 python tests/layer_perf.py 128 2 > gpurun_out/layers_$TAG.txt 2>&1; head -40 gpurun_out/layers_$TAG.txt

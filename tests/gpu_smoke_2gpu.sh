@@ -1,4 +1,5 @@
 #!/bin/bash
+set -o pipefail
 mkdir -p gpurun_out
 timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
 timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -2

@@ -63,3 +63,44 @@ def test_process_videopose3d_wrapper(synthetic_env):
     assert out["keypoints_3d"].shape == (150, 17, 3) and out["keypoints_3d"].dtype == np.float64
     assert out["keypoints_valid"] == [True] * 150
     assert np.abs(out["keypoints_3d"] - ref["keypoints_3d"]).max() <= 1e-3
+
+
+# ------------------------------------------------------------------ handle lifetime / process exit
+_EXIT_SCRIPT = r"""
+import os, sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+os.environ["PE_SYNTHETIC_WEIGHTS"] = "1"; os.environ["PE_MAX_CROPS"] = "2"
+import numpy as np, torch
+torch.zeros(1, device="cuda")                        # a populate() worker normally has torch's CUDA context alive too
+import fakes
+fakes.make_fake_pose_pipeline()
+from posepipeline_b200.wrappers import mmpose as W, videopose3d as V
+from posepipeline_b200 import engine as E
+m = W.get_model("HRNet_W48_COCO"); l = V.get_lifter()
+from posepipeline_b200.synthetic import synthetic_frames, synthetic_bboxes
+W.get_engine().stage_frames(synthetic_frames(1, 3))
+kp = m.topdown([0], synthetic_bboxes(1, 5))
+assert kp.shape == (1, 17, 3)
+mode = {mode!r}
+if mode == "engine_first":                           # release order a garbage collector may pick
+    W.get_engine().close(); m.close(); l.close()
+    try:
+        m.topdown([0], synthetic_bboxes(1, 5)); raise SystemExit(3)
+    except E._lib.PoseEngineError:
+        pass
+elif mode == "second_engine":                        # handles of two engines, nothing closed
+    e2 = E.PoseEngine(0); l2 = E.Lifter(e2, __import__("posepipeline_b200.weights", fromlist=["x"]).synthetic_videopose3d_state_dict(0))
+print("ok", flush=True)
+"""                                                  # no close(): module globals keep models / lifter / engine alive
+
+
+@pytest.mark.parametrize("mode", ["leak", "engine_first", "second_engine"])
+def test_worker_process_exits_cleanly(mode):
+    """A process that used the drop-in wrappers and never closed anything must exit 0 (round 1: rc 139 at interpreter
+    exit), as a populate() worker does (reference utils/standard_pipelines.py:100)."""
+    import subprocess
+    import sys
+    from conftest import ROOT
+    r = subprocess.run([sys.executable, "-X", "faulthandler", "-c", _EXIT_SCRIPT.format(root=ROOT, mode=mode)],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ok" in r.stdout, (r.returncode, r.stdout[-500:], r.stderr[-2000:])
