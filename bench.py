@@ -37,6 +37,16 @@ FLOP_PER_CROP = 2 * FLOP_PER_PASS                              # flip test = two
 METRIC = "top-down 2D keypoint crops/sec (HRNet-W48 384x288, flip-test + DARK decode)"
 
 
+def top_kernel_traffic():
+    """DRAM bytes per launch of the top kernel from THIS round's committed ncu --set full capture
+    (profiles/r02_top_kernel_traffic.json, written by profiles/extract_traffic.py from the .ncu-rep), or None."""
+    p = os.path.join(ROOT, "profiles", "r02_top_kernel_traffic.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("dram_bytes_per_launch"), d
+    return None, None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -92,6 +102,13 @@ class CpuReference:
         self.net = OH.load_net(sd, spec.variant)
         self.frames = cheap_frames(2, 0)
         self.bbs = synthetic_bboxes(512, 1234)
+        # torchrun exports OMP_NUM_THREADS=1: the CPU arm must still use every host core (round 1's N>1 reference lines ran
+        # on one thread).  Affinity-aware count, capped to what the box really has.
+        try:
+            ncpu = len(os.sched_getaffinity(0))
+        except AttributeError:
+            ncpu = os.cpu_count() or 1
+        torch.set_num_threads(max(1, ncpu))
         self.cores = torch.get_num_threads()
         self.torch_version = torch.__version__
         self.i = 0
@@ -110,12 +127,33 @@ class CpuReference:
         return time.perf_counter() - t0, done
 
 
+def parity_check(kp, frames, fidx, bboxes, n_check):
+    """max |dx| (px) of n_check of the benchmarked crops (evenly spread over the batch) against the fp32 oracle."""
+    from oracle import hrnet as OH
+    from oracle import topdown as OT
+    from posepipeline_b200.engine import METHODS
+    from posepipeline_b200.hrnet_spec import build_program
+    from posepipeline_b200.weights import synthetic_hrnet_state_dict
+    spec = METHODS[METHOD]
+    sd = synthetic_hrnet_state_dict(build_program(spec.variant, spec.image_size[1], spec.image_size[0], spec.num_joints), 0)
+    net = OH.load_net(sd, spec.variant)
+    idx = np.linspace(0, len(fidx) - 1, n_check).round().astype(int)
+    ref = OT.top_down_video(net, [frames[fidx[i]] for i in idx], bboxes[idx], OT.HRNET_W48_COCO)
+    d = np.abs(kp[idx][..., :2] - ref[..., :2]).max(-1)
+    ds = np.abs(kp[idx][..., 2] - ref[..., 2])
+    return {"max_abs_px": float(d.max()), "p99_abs_px": float(np.quantile(d, 0.99)), "median_abs_px": float(np.median(d)),
+            "max_abs_score": float(ds.max()), "n": int(len(idx)), "keypoints": int(d.size),
+            "against": "oracle fp32 (torch CPU + cv2 + numpy), same frames and boxes", "gate_px": 1e-3,
+            "ok": bool(d.max() <= 1e-3)}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     per_step = 4
     ref = CpuReference()
+    print(f"reference arm: torch CPU threads = {ref.cores} (OMP_NUM_THREADS={os.environ.get('OMP_NUM_THREADS')})", file=sys.stderr)
     for _ in range(args.warmup):
         ref.run(1)
     total, dt = 0, 0.0
@@ -144,6 +182,8 @@ def main():
     ap.add_argument("--max-crops", type=int, default=int(os.environ.get("PE_MAX_CROPS", "256")))
     ap.add_argument("--no-tc", action="store_true", help="fp32 SIMT convolutions only")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the benchmarked batch")
+    ap.add_argument("--parity-crops", type=int, default=16)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -228,12 +268,14 @@ def main():
     for _ in range(2):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps) / args.steps
+    kp = step_e2e()                        # one more step outside the timed region: the keypoints the parity check examines
     e2e_value = world * CROPS_PER_STEP / (ms_e2e / 1e3)
     h2d = int(frames.nbytes + CROPS_PER_STEP * (6 * 8 + 4 + 16))
     d2h = int(CROPS_PER_STEP * spec.num_joints * 3 * 4)
 
     if rank == 0:
         tf_peak, hbm_peak, peak_src = peaks()
+        traffic, traffic_src = top_kernel_traffic()
         conv_flop = FLOP_PER_CROP * CROPS_PER_STEP * args.steps
         achieved = conv_flop / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else None
         line = {
@@ -254,16 +296,19 @@ def main():
             "clocks": sampler.summary(),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s",
                          "frac": (achieved / tf_peak) if achieved else None,
-                         # DRAM bytes of ONE launch of the top kernel (conv_tc<6,2,9,1>, the 48->48 3x3 layers at 96x72 on 512
-                         # images), dram__bytes_read.sum + dram__bytes_write.sum of the committed ncu --set full capture
-                         # (profiles/r01_tc_v7_ncu_full.md); its algorithmic bytes are 2 x 0.713 GB (input once + output once)
-                         "traffic": 1.383e9, "traffic_unit": "bytes per launch of the top kernel (ncu, 512 images)",
+                         # DRAM bytes of ONE launch of the top kernel: dram__bytes_read.sum + dram__bytes_write.sum from this
+                         # round's committed ncu --set full capture (profiles/r02_top_kernel_traffic.json), else null
+                         "traffic": traffic, "traffic_source": traffic_src,
                          "kernel": "convolution kernels (conv_tc / conv_simt), all launches of a second pass of the same K steps with an event pair per launch",
                          "algorithmic_flop_per_crop": FLOP_PER_CROP, "conv_ms_total": conv_ms, "other_ms_total": other_ms,
                          "profiled_pass_ms_per_step": ms_prof / args.steps,
                          "conv_launches": int(conv_launches), "peak_source": peak_src,
                          "note": "algorithmic FLOPs count each MAC once; the split-precision path executes 3 MMAs per MAC"},
         }
+        if world == 1 and not args.no_parity:
+            # parity of THIS benchmark configuration (256-crop batch, CUDA-graph replay, auto-tuned tilings): a subset of the
+            # last timed step's keypoints against the oracle, outside the timed region (checker only)
+            line["parity"] = parity_check(kp, frames, fidx, bboxes, args.parity_crops)
         if world == 1 and not args.no_cpu_baseline:
             ref = CpuReference()
             t, done = ref.run(40, seconds_cap=20.0)

@@ -30,6 +30,8 @@ extern "C" {
 #define PE_ERR_CUDA (-2)      /* CUDA runtime/driver error */
 #define PE_ERR_STATE (-3)     /* call sequence error (e.g. frame index not staged) */
 #define PE_ERR_NOGPU (-4)     /* no CUDA device: the product path has no CPU fallback */
+#define PE_ERR_RANGE (-5)     /* an activation left the range of the library's operand format (fp16x2 build: |v| > 65504);
+                                 results are NOT returned clamped -- use the tf32x3 build (PE_PRECISION=tf32) for such weights */
 
 typedef struct pe_engine pe_engine;
 typedef struct pe_model pe_model;

@@ -14,7 +14,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libposeengine_tf32.so" if os.environ.get("PE_PRECISION", "fp16") == "tf32" else "libposeengine.so")
 HEADER_PATH = os.path.join(os.path.dirname(_PKG), "include", "poseengine.h")
 
-PE_OK, PE_ERR_INVALID, PE_ERR_CUDA, PE_ERR_STATE, PE_ERR_NOGPU = 0, -1, -2, -3, -4
+PE_OK, PE_ERR_INVALID, PE_ERR_CUDA, PE_ERR_STATE, PE_ERR_NOGPU, PE_ERR_RANGE = 0, -1, -2, -3, -4, -5
 PE_OP_STEM, PE_OP_CONV, PE_OP_FUSE, PE_OP_HEAD = 0, 1, 2, 3
 PE_POST = {None: 0, "none": 0, "default": 1, "unbiased": 2}
 

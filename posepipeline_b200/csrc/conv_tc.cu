@@ -72,6 +72,7 @@ struct TcParams {
   int poll_ns;               // producer / epilogue waits: > 0 nanosleep back-off between polls, < 0 suspended try_wait with that time hint, 0 spin
   int tiles_m, total_work;   // persistent schedule: work item w -> (tile = w % tiles_m, n-slice = w / tiles_m)
   uint32_t a_bytes, stage_bytes;
+  unsigned int* flag;        // range flag of the forward (kernels.h pe_range_flag), or nullptr
   long long* prof;
 };
 
@@ -616,8 +617,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const float2 h0 = __half22float2(*reinterpret_cast<const __half2*>(&hw[2 * k2])), h1 = __half22float2(*reinterpret_cast<const __half2*>(&hw[2 * k2 + 1]));
             const float2 l0 = __half22float2(*reinterpret_cast<const __half2*>(&lw[2 * k2])), l1 = __half22float2(*reinterpret_cast<const __half2*>(&lw[2 * k2 + 1]));
             float* ac = &a[8 * i + 4 * k2];
-            ac[0] = fmaf(h0.x + l0.x, sc.x, ac[0]); ac[1] = fmaf(h0.y + l0.y, sc.y, ac[1]);
-            ac[2] = fmaf(h1.x + l1.x, sc.z, ac[2]); ac[3] = fmaf(h1.y + l1.y, sc.w, ac[3]);
+            ac[0] = fmaf(fmaf(l0.x, PS_LO_INV, h0.x), sc.x, ac[0]); ac[1] = fmaf(fmaf(l0.y, PS_LO_INV, h0.y), sc.y, ac[1]);
+            ac[2] = fmaf(fmaf(l1.x, PS_LO_INV, h1.x), sc.z, ac[2]); ac[3] = fmaf(fmaf(l1.y, PS_LO_INV, h1.y), sc.w, ac[3]);
           }
         }
 #else
@@ -702,8 +703,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (EPI_PARTS * gi + half >= NG) continue;
         uint32_t r[16];
         tc_ld16(t_lane + (NMAIN + cbuf) * GC + (EPI_PARTS * gi + half) * 16, r);
+        // the low operand halves carry a factor PS_LO_SCALE (fp16x2 build: 2^11, pe_common.cuh), hence so do the cross terms
 #pragma unroll
-        for (int i = 0; i < 16; ++i) acc[gi][i] += __uint_as_float(r[i]);
+        for (int i = 0; i < 16; ++i) acc[gi][i] = fmaf(__uint_as_float(r[i]), PS_LO_INV, acc[gi][i]);
       }
       tc_fence_before();
       __syncwarp();
@@ -734,6 +736,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
           }
 #if PE_FP16
+          {                                                  // a value beyond the fp16x2 range is an error, not a silent clamp
+            float amax = fabsf(v[0]);
+#pragma unroll
+            for (int i = 1; i < 16; ++i) amax = fmaxf(amax, fabsf(v[i]));
+            if (amax > PS_ABS_MAX && p.flag) atomicOr(p.flag, 1u);
+          }
           uint2 h[4], l[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) split4_h(make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]), h[i], l[i]);
@@ -1140,6 +1148,7 @@ void tc_conv_plan_destroy(TcConvPlan* plan, bool cuda_ok) { if (plan && plan->p.
 
 cudaError_t tc_conv_launch(TcConvPlan* pl, int nimg, cudaStream_t st) {
   TcParams p = pl->p;
+  p.flag = pe_range_flag();
   p.M = (long long)nimg * pl->rows_per_img;
   p.tiles_m = (int)((p.M + 128LL * pl->MT - 1) / (128LL * pl->MT));
   p.total_work = p.tiles_m * pl->ns;

@@ -54,6 +54,8 @@ static Registry& registry() { static Registry* r = new Registry(); return *r; }
 void pe_handle_register(int kind, void* h) { Registry& r = registry(); std::lock_guard<std::mutex> g(r.mu); r.live[kind].insert(h); }
 bool pe_handle_release(int kind, void* h) { Registry& r = registry(); std::lock_guard<std::mutex> g(r.mu); return r.live[kind].erase(h) != 0; }
 bool pe_handle_alive(int kind, void* h) { Registry& r = registry(); std::lock_guard<std::mutex> g(r.mu); return r.live[kind].count(h) != 0; }
+unsigned int*& pe_range_flag() { static thread_local unsigned int* f = nullptr; return f; }
+
 cudaError_t pe_smem_optin(const void* func, int bytes) {
   static std::mutex* mu = new std::mutex();
   static std::map<std::pair<const void*, int>, int>* done = new std::map<std::pair<const void*, int>, int>();
@@ -142,9 +144,15 @@ extern "C" int pe_shutdown(void) {
   return PE_OK;
 }
 
+static int flag_check(pe_model* m);
+
 extern "C" int pe_engine_sync(pe_engine* e) {
   ENGINE_ALIVE(e);
   CU(cudaStreamSynchronize(e->stream));
+  for (pe_model* m : e->models) {           // range flags of asynchronous calls (pe_topdown_async)
+    const int rc = flag_check(m);
+    if (rc) return rc;
+  }
   return PE_OK;
 }
 
@@ -324,6 +332,8 @@ struct pe_model {
   float* d_hm = nullptr;        // [2*max][K][hh][hw]
   float* d_out = nullptr;       // [max][K][3]
   float* d_gauss = nullptr;     // [64] 1-D Gaussian taps of this model's modulate_kernel
+  unsigned int* d_flag = nullptr;   // range flag: kernels OR 1 into it when an activation does not fit the operand format
+  unsigned int* h_flag = nullptr;   // pinned copy, read with every result
   // pinned staging
   double* h_minv = nullptr; int32_t* h_fidx = nullptr; float* h_cs = nullptr; float* h_out = nullptr;
   int nimg_last = 0, ncrop_last = 0;
@@ -361,8 +371,8 @@ static void model_free(pe_model* m, bool cuda_ok) {
     for (auto& g : m->graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
     for (auto* p : m->slots) if (p) cudaFree(p);
     cudaFree(m->d_w); cudaFree(m->d_s2d); cudaFree(m->d_lut); cudaFree(m->d_perm); cudaFree(m->d_crops); cudaFree(m->d_minv);
-    cudaFree(m->d_fidx); cudaFree(m->d_cs); cudaFree(m->d_hm); cudaFree(m->d_out); cudaFree(m->d_gauss);
-    cudaFreeHost(m->h_minv); cudaFreeHost(m->h_fidx); cudaFreeHost(m->h_cs); cudaFreeHost(m->h_out);
+    cudaFree(m->d_fidx); cudaFree(m->d_cs); cudaFree(m->d_hm); cudaFree(m->d_out); cudaFree(m->d_gauss); cudaFree(m->d_flag);
+    cudaFreeHost(m->h_flag); cudaFreeHost(m->h_minv); cudaFreeHost(m->h_fidx); cudaFreeHost(m->h_cs); cudaFreeHost(m->h_out);
     for (auto& p : m->ev_conv) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     if (m->ev_fwd0) cudaEventDestroy(m->ev_fwd0);
     if (m->ev_fwd1) cudaEventDestroy(m->ev_fwd1);
@@ -386,6 +396,7 @@ extern "C" int pe_model_create(pe_engine* e, const pe_model_desc* desc, const pe
   if (!e || !desc || !ops || !tensors || !slot_elems || !weights || !norm_lut || !flip_perm || !out)
     return fail(PE_ERR_INVALID, "NULL argument to pe_model_create");
   ENGINE_ALIVE(e);
+  pe_range_flag() = nullptr;      // plan creation launches candidate tilings on uninitialised buffers
   if (desc->max_crops <= 0 || desc->n_ops <= 0) return fail(PE_ERR_INVALID, "bad model description");
   if (desc->post_process == PE_POST_UNBIASED && (desc->blur_kernel < 3 || desc->blur_kernel > 63 || desc->blur_kernel % 2 == 0))
     return fail(PE_ERR_INVALID, "blur kernel must be odd and in [3,63]");
@@ -419,6 +430,10 @@ extern "C" int pe_model_create(pe_engine* e, const pe_model_desc* desc, const pe
   CUM(cudaMallocHost(&m->h_fidx, sizeof(int32_t) * maxc));
   CUM(cudaMallocHost(&m->h_cs, sizeof(float) * 4 * maxc));
   CUM(cudaMallocHost(&m->h_out, sizeof(float) * (size_t)maxc * K * 3));
+  CUM(cudaMalloc(&m->d_flag, sizeof(unsigned int)));
+  CUM(cudaMemsetAsync(m->d_flag, 0, sizeof(unsigned int), e->stream));
+  CUM(cudaMallocHost(&m->h_flag, sizeof(unsigned int)));
+  *m->h_flag = 0;
   CUM(cudaEventCreate(&m->ev_fwd0));
   CUM(cudaEventCreate(&m->ev_fwd1));
   {
@@ -514,6 +529,7 @@ static int forward(pe_model* m, int ncrop, int nimg) {
 
 static int forward_eager(pe_model* m, int ncrop, int nimg) {
   cudaStream_t st = m->e->stream;
+  pe_range_flag() = m->d_flag;
   const pe_model_desc& d = m->d;
   m->ev_used = 0;
   if (m->profile) cudaEventRecord(m->ev_fwd0, st);
@@ -589,6 +605,18 @@ static int profile_collect(pe_model* m) {
   return PE_OK;
 }
 
+// range flag: queued with the results, examined after the stream sync
+static cudaError_t flag_fetch(pe_model* m) {
+  return cudaMemcpyAsync(m->h_flag, m->d_flag, sizeof(unsigned int), cudaMemcpyDeviceToHost, m->e->stream);
+}
+static int flag_check(pe_model* m) {
+  if (!*m->h_flag) return PE_OK;
+  *m->h_flag = 0;
+  cudaMemsetAsync(m->d_flag, 0, sizeof(unsigned int), m->e->stream);
+  return fail(PE_ERR_RANGE, "an activation exceeded the fp16x2 operand range (|v| > 65504); results withheld -- run these weights "
+                            "on the tf32x3 build (PE_PRECISION=tf32)");
+}
+
 static int check_crops(pe_model* m, const int32_t* frame_idx, const double* bbox, int n) {
   MODEL_ALIVE(m);
   if (!frame_idx || !bbox || n < 0) return fail(PE_ERR_INVALID, "bad argument");
@@ -645,8 +673,10 @@ extern "C" int pe_topdown(pe_model* m, const int32_t* frame_idx, const double* b
     if ((rc = forward(m, nc, nimg))) return rc;
     if ((rc = run_decode(m, m->d_hm, m->d.flip_test ? m->d_hm + hm_img * nc : nullptr, m->d_cs, m->d_cs + 2 * maxc, nc, m->d_out))) return rc;
     CU(cudaMemcpyAsync(m->h_out, m->d_out, sizeof(float) * (size_t)nc * K * 3, cudaMemcpyDeviceToHost, st));
+    CU(flag_fetch(m));
     CU(cudaStreamSynchronize(st));
     if ((rc = profile_collect(m))) return rc;
+    if ((rc = flag_check(m))) return rc;
     memcpy(out_kpts + (size_t)i0 * K * 3, m->h_out, sizeof(float) * (size_t)nc * K * 3);
   }
   return PE_OK;
@@ -662,10 +692,12 @@ extern "C" int pe_topdown_async(pe_model* m, const int32_t* frame_idx, const dou
   const int K = m->d.num_joints;
   const size_t hm_img = (size_t)K * m->d.hm_h * m->d.hm_w;
   CU(cudaStreamSynchronize(st));   // pinned parameter staging is single-buffered
+  if ((rc = flag_check(m))) return rc;   // range flag of the previous asynchronous call
   if ((rc = stage_crops(m, frame_idx, bbox_xywh, 0, n))) return rc;
   if ((rc = forward(m, n, n * (m->d.flip_test ? 2 : 1)))) return rc;
   if ((rc = run_decode(m, m->d_hm, m->d.flip_test ? m->d_hm + hm_img * n : nullptr, m->d_cs, m->d_cs + 2 * m->d.max_crops, n, m->d_out))) return rc;
   if (out_kpts_pinned) CU(cudaMemcpyAsync(out_kpts_pinned, m->d_out, sizeof(float) * (size_t)n * K * 3, cudaMemcpyDeviceToHost, st));
+  CU(flag_fetch(m));
   return PE_OK;
 }
 
@@ -703,8 +735,10 @@ extern "C" int pe_forward_heatmaps(pe_model* m, const uint8_t* crops, int32_t n,
     if (rc) return rc;
     CU(cudaMemcpyAsync(hm_plain + hm_img * i0, m->d_hm, sizeof(float) * hm_img * nc, cudaMemcpyDeviceToHost, st));
     if (flip) CU(cudaMemcpyAsync(hm_flipped + hm_img * i0, m->d_hm + hm_img * nc, sizeof(float) * hm_img * nc, cudaMemcpyDeviceToHost, st));
+    CU(flag_fetch(m));
     CU(cudaStreamSynchronize(st));
     if ((rc = profile_collect(m))) return rc;
+    if ((rc = flag_check(m))) return rc;
   }
   return PE_OK;
 }
@@ -776,6 +810,7 @@ extern "C" int pe_conv_test(pe_engine* e, const float* in_nchw, int32_t nimg, in
                             const float* w_simt, const float* w_tc, const float* bias, const float* res_nchw, int32_t Cout,
                             int32_t ks, int32_t stride, int32_t relu, int32_t use_tc, float* out_nchw) {
   ENGINE_ALIVE(e);
+  pe_range_flag() = nullptr;
   if (!in_nchw || !w_simt || !bias || !out_nchw || nimg <= 0) return fail(PE_ERR_INVALID, "bad argument to pe_conv_test");
   if (Cin % 16 || Cout % 16) return fail(PE_ERR_INVALID, "pe_conv_test needs channel counts that are multiples of 16");
   CU(cudaSetDevice(e->device));

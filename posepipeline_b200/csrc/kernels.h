@@ -22,6 +22,10 @@ void launch_ps_to_chw(const float* in, int C, int H, int W, int img, float* out,
 void launch_s2d(const float* in, int C, int Hin, int Win, int nimg, float* out, int Hout, int Wout, cudaStream_t st);
 void launch_chw_to_ps(const float* in, int C, int H, int W, int nimg, float* out, cudaStream_t st);
 
+// Range flag of the forward being launched on this thread (device word; nullptr = no checking).  The launchers below pass
+// it to their kernels, which OR 1 into it when a value does not fit the activation format (fp16x2: |v| > 65504).
+unsigned int*& pe_range_flag();
+
 // opt a kernel into `bytes` of dynamic shared memory on the CURRENT device (the attribute is per device; cached per
 // (function, device) so the steady state costs one map lookup)
 cudaError_t pe_smem_optin(const void* func, int bytes);

@@ -73,6 +73,7 @@ __global__ void __launch_bounds__(256, 2) stem_kernel(const uint8_t* __restrict_
                                                       const float* __restrict__ lut,   // [3][256]
                                                       const float* __restrict__ w,     // [27][64]  (tap-major: (ky*3+kx)*3+c)
                                                       const float* __restrict__ bias,  // [64]
+                                                      unsigned int* flag,
                                                       float* __restrict__ out, int oh, int ow) {
   extern __shared__ __align__(16) uint8_t stem_smem[];
   float* s_w = reinterpret_cast<float*>(stem_smem);           // [27][64]
@@ -139,6 +140,8 @@ __global__ void __launch_bounds__(256, 2) stem_kernel(const uint8_t* __restrict_
       }
 #pragma unroll
       for (int i = 0; i < 16; ++i) acc[i] = fmaxf(acc[i], 0.f);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) ps_range_check4(make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]), flag);
       // chunk q of the row: PS_CHUNK_BYTES / 16 units, stored at unit ^ (tid & 7) inside its group of 8
       constexpr int UPC = PS_CHUNK_BYTES / 16;
       uint4 o[UPC];
@@ -181,7 +184,7 @@ void launch_stem(const uint8_t* crops, int ncrop, int nimg, int ih, int iw, cons
                  const float* bias, float* out, int oh, int ow, cudaStream_t st) {
   if (pe_smem_optin((const void*)stem_kernel, (int)STEM_SMEM) != cudaSuccess) return;   // the launch below then fails and is reported
   dim3 grid((ow + 2 + STEM_T - 1) / STEM_T, (oh + 2 + STEM_T - 1) / STEM_T, nimg);
-  stem_kernel<<<grid, 256, STEM_SMEM, st>>>(crops, ncrop, nimg, ih, iw, lut, w, bias, out, oh, ow);
+  stem_kernel<<<grid, 256, STEM_SMEM, st>>>(crops, ncrop, nimg, ih, iw, lut, w, bias, pe_range_flag(), out, oh, ow);
 }
 
 // =============================================================================================
@@ -202,6 +205,7 @@ struct ConvArgs {
   // linear (1-D, dilated) mode used by the VideoPose3D lifter: rows are time steps, tap t reads row m + t*dil
   int linear, ntaps, dil, res_off, plain_out, cout_real;
   long long M_lin;
+  unsigned int* flag;   // range flag (pe_common.cuh ps_range_check4)
 };
 
 template <int BN>
@@ -329,6 +333,7 @@ __global__ void __launch_bounds__(BN * 4) conv_simt_kernel(ConvArgs a) {
       const float4 rr = ps_load4(a.res + (m - a.res_off) * outRowF, c);
       v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
     }
+    ps_range_check4(v, a.flag);
     ps_store4(orow, c, v);
   }
 }
@@ -336,7 +341,7 @@ __global__ void __launch_bounds__(BN * 4) conv_simt_kernel(ConvArgs a) {
 void launch_conv_simt(const float* in, float* out, const float* res, const float* w, const float* bias, int Cin,
                       int Cout, int ks, int stride, int relu, int Hin, int Win, int Hout, int Wout, int nimg,
                       cudaStream_t st) {
-  ConvArgs a{in, out, res, w, bias, Cin, Cout, ks, stride, relu, Hin, Win, Hout, Wout, nimg, 0, ks * ks, 0, 0, 0, Cout, 0};
+  ConvArgs a{in, out, res, w, bias, Cin, Cout, ks, stride, relu, Hin, Win, Hout, Wout, nimg, 0, ks * ks, 0, 0, 0, Cout, 0, pe_range_flag()};
   long long M = (long long)nimg * (Hout + 2) * (Wout + 2);
   unsigned gx = (unsigned)((M + 63) / 64);
   if (Cout % 48 == 0) {
@@ -350,7 +355,7 @@ void launch_conv_simt(const float* in, float* out, const float* res, const float
 void launch_conv_linear(const float* in, float* out, const float* res, const float* w, const float* bias, int Cin,
                         int Cout, int ntaps, int dil, int relu, long long M, int res_off, int plain_out, int cout_real,
                         cudaStream_t st) {
-  ConvArgs a{in, out, res, w, bias, Cin, Cout, 1, 1, relu, 0, 0, 0, 0, 1, 1, ntaps, dil, res_off, plain_out, cout_real, M};
+  ConvArgs a{in, out, res, w, bias, Cin, Cout, 1, 1, relu, 0, 0, 0, 0, 1, 1, ntaps, dil, res_off, plain_out, cout_real, M, pe_range_flag()};
   unsigned gx = (unsigned)((M + 63) / 64);
   if (Cout % 48 == 0) conv_simt_kernel<48><<<dim3(gx, Cout / 48), 192, 0, st>>>(a);
   else conv_simt_kernel<64><<<dim3(gx, (Cout + 63) / 64), 256, 0, st>>>(a);
@@ -365,6 +370,7 @@ struct FuseArgs {
   int n_in;
   float* out;
   int C, H, W, nimg, relu;
+  unsigned int* flag;
 };
 
 // One thread per (padded position, 16-channel chunk): a chunk is PS_CHUNK_BYTES contiguous bytes, so every access is a
@@ -380,7 +386,7 @@ __device__ __forceinline__ void chunk_load16(const float* row, int chunk, float 
   for (int i = 0; i < 8; ++i) {
     const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[i]));
     const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[i]));
-    v[2 * i] = hf.x + lf.x; v[2 * i + 1] = hf.y + lf.y;
+    v[2 * i] = fmaf(lf.x, PS_LO_INV, hf.x); v[2 * i + 1] = fmaf(lf.y, PS_LO_INV, hf.y);
   }
 #else
 #pragma unroll
@@ -446,6 +452,8 @@ __global__ void __launch_bounds__(256) fuse_kernel(FuseArgs a) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) s[i] = fmaxf(s[i], 0.f);
   }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) ps_range_check4(make_float4(s[4 * i], s[4 * i + 1], s[4 * i + 2], s[4 * i + 3]), a.flag);
   chunk_store16(orow, chunk, s);
 }
 
@@ -453,7 +461,7 @@ void launch_fuse(const float* const* in, const int* up, int n_in, float* out, in
                  cudaStream_t st) {
   FuseArgs a;
   for (int j = 0; j < 4; ++j) { a.in[j] = j < n_in ? in[j] : nullptr; a.up[j] = j < n_in ? up[j] : 1; }
-  a.n_in = n_in; a.out = out; a.C = C; a.H = H; a.W = W; a.nimg = nimg; a.relu = relu;
+  a.n_in = n_in; a.out = out; a.C = C; a.H = H; a.W = W; a.nimg = nimg; a.relu = relu; a.flag = pe_range_flag();
   long long total = (long long)nimg * (H + 2) * (W + 2) * (C / 16);
   fuse_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a);
 }

@@ -16,9 +16,15 @@
 // Two builds of the same layout idea (compile-time switch PE_FP16, see csrc/build.py):
 //   PE_FP16=0  "tf32x3": chunk = [hi(16 x f32) | lo(16 x f32)] = 128 B; hi = value rounded to TF32, lo = value - hi (exact).
 //                        8 bytes per element, no range limit; tcgen05 kind::tf32, K = 8 per MMA.
-//   PE_FP16=1  "fp16x2": chunk = [h(16 x f16) | l(16 x f16)]   =  64 B; h = fp16(value), l = fp16(value - h): 22 significant
-//                        bits, 4 bytes per element, |value| must stay below 65504 (activations of BN'd CNNs do; values
-//                        are clamped, never inf); tcgen05 kind::f16, K = 16 per MMA: half the MMAs and half the bytes.
+//   PE_FP16=1  "fp16x2": chunk = [h(16 x f16) | l(16 x f16)]   =  64 B; h = fp16(value), l = fp16((value - h) * 2^11): 22
+//                        significant bits, 4 bytes per element; tcgen05 kind::f16, K = 16 per MMA: half the MMAs and half
+//                        the bytes.  The 2^11 on the low half (PS_LO_SCALE) keeps it a NORMAL fp16 number whenever the value
+//                        itself is one (|l| <= |value|): without it the low half of any |value| < 2^-3 is an fp16
+//                        subnormal with an absolute step of 6e-8, i.e. a tensor living around 1e-3 would carry only ~15
+//                        bits.  The cross terms hi*lo + lo*hi accumulate in their own TMEM accumulator, so the 2^-11 is
+//                        applied once, in the epilogue (exact).  Full precision range: 6.1e-5 <= |value| <= 65504;
+//                        smaller values degrade gracefully (absolute error <= 3e-11); larger ones saturate AND raise the
+//                        model's range flag (pe_topdown then fails with PE_ERR_RANGE instead of returning clamped results).
 #ifndef PE_FP16
 #define PE_FP16 0
 #endif
@@ -30,6 +36,15 @@
 #define PS_CHUNK_BYTES 128
 #endif
 #define PS_CHUNK_FLOATS (PS_CHUNK_BYTES / 4)
+#if PE_FP16
+#define PS_LO_SCALE 2048.0f
+#define PS_LO_INV (1.0f / 2048.0f)
+#define PS_ABS_MAX 65504.0f
+#else
+#define PS_LO_SCALE 1.0f
+#define PS_LO_INV 1.0f
+#define PS_ABS_MAX 3.0e38f
+#endif
 
 // floats (4-byte units) per PS row of a C-channel tensor
 __host__ __device__ __forceinline__ int ps_row_floats(int C) { return (C >> 4) * PS_CHUNK_FLOATS; }
@@ -52,14 +67,24 @@ __device__ __forceinline__ void split4_h(const float4 v, uint2& h, uint2& l) {
   const float z = fminf(fmaxf(v.z, -lim), lim), w = fminf(fmaxf(v.w, -lim), lim);
   const __half2 h0 = __floats2half2_rn(x, y), h1 = __floats2half2_rn(z, w);
   const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
-  const __half2 l0 = __floats2half2_rn(x - f0.x, y - f0.y), l1 = __floats2half2_rn(z - f1.x, w - f1.y);
+  const __half2 l0 = __floats2half2_rn((x - f0.x) * PS_LO_SCALE, (y - f0.y) * PS_LO_SCALE);     // exact scaling
+  const __half2 l1 = __floats2half2_rn((z - f1.x) * PS_LO_SCALE, (w - f1.y) * PS_LO_SCALE);
   h.x = *reinterpret_cast<const uint32_t*>(&h0); h.y = *reinterpret_cast<const uint32_t*>(&h1);
   l.x = *reinterpret_cast<const uint32_t*>(&l0); l.y = *reinterpret_cast<const uint32_t*>(&l1);
 }
 __device__ __forceinline__ float4 join4_h(const uint2 h, const uint2 l) {
   const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&h.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
   const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&l.x)), d = __half22float2(*reinterpret_cast<const __half2*>(&l.y));
-  return make_float4(a.x + c.x, a.y + c.y, b.x + d.x, b.y + d.y);
+  return make_float4(fmaf(c.x, PS_LO_INV, a.x), fmaf(c.y, PS_LO_INV, a.y), fmaf(d.x, PS_LO_INV, b.x), fmaf(d.y, PS_LO_INV, b.y));
+}
+
+// range flag: set when a value about to be stored does not fit the activation format (fp16x2: |v| > 65504)
+__device__ __forceinline__ void ps_range_check4(const float4 v, unsigned int* flag) {
+#if PE_FP16
+  if (flag && fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))) > PS_ABS_MAX) atomicOr(flag, 1u);
+#else
+  (void)v; (void)flag;
+#endif
 }
 
 // byte offset of channel c (multiple of 4) inside a PS row (the hi / h part; the lo / l part is PS_CHUNK_BYTES/2 further)

@@ -164,11 +164,17 @@ def space_to_depth_weights(w: np.ndarray) -> np.ndarray:
     return out.reshape(cout, 4 * cin, 2, 2)
 
 
+FP16_LO_SCALE = np.float32(2048.0)          # csrc/pe_common.cuh PS_LO_SCALE
+
+
 def fp16_split(x: np.ndarray):
-    """h = fp16(x) (clamped to the finite range), l = fp16(x - h): 22 significant bits."""
-    x = np.clip(np.ascontiguousarray(x, np.float32), -65504.0, 65504.0)
+    """h = fp16(x), l = fp16((x - h) * 2^11): 22 significant bits; the scaled low half is a normal fp16 number whenever x
+    is (csrc/pe_common.cuh).  Values beyond the fp16 range are an error, not clamped."""
+    x = np.ascontiguousarray(x, np.float32)
+    if x.size and float(np.abs(x).max()) > 65504.0:
+        raise OverflowError("value exceeds the fp16x2 operand range (|x| <= 65504); use the tf32 build (PE_PRECISION=tf32)")
     h = x.astype(np.float16)
-    l = (x - h.astype(np.float32)).astype(np.float16)
+    l = ((x - h.astype(np.float32)) * FP16_LO_SCALE).astype(np.float16)
     return h, l
 
 

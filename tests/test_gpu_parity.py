@@ -155,55 +155,129 @@ def _oracle_activations(net, prog, x):
     return out
 
 
-def test_every_layer_matches_oracle(eng):
+def rescaled_state_dict(sd, log2_scale):
+    """The SAME network with two internal tensors multiplied by 2^log2_scale and their consumers divided by it (powers of
+    two: the fp32 oracle's downstream values do not change by a bit).  Tensors: the stem output (backbone.bn2 -> consumed by
+    layer1.0.conv1 and layer1.0.downsample.0) and the hidden tensor of a stage-3 BasicBlock (branches.1.0.bn1 -> conv2).
+    What changes is where those activations sit in the engine's operand format (fp16x2: full precision for
+    6.1e-5 <= |v| <= 65504, csrc/pe_common.cuh)."""
+    f = np.float32(2.0 ** log2_scale)
+    out = dict(sd)
+    for bn, consumers in (("backbone.bn2", ["backbone.layer1.0.conv1", "backbone.layer1.0.downsample.0"]),
+                          ("backbone.stage3.0.branches.1.0.bn1", ["backbone.stage3.0.branches.1.0.conv2"])):
+        out[f"{bn}.weight"] = sd[f"{bn}.weight"] * f
+        out[f"{bn}.bias"] = sd[f"{bn}.bias"] * f
+        for c in consumers:
+            out[f"{c}.weight"] = sd[f"{c}.weight"] / f
+    return out
+
+
+RESCALED = ("backbone.bn2", "backbone.stage3.0.branches.1.0.bn1")
+
+
+@pytest.mark.parametrize("log2_scale", [0, 10, -10])
+def test_every_layer_matches_oracle(eng, log2_scale):
+    """Every tensor of the network against the fp32 oracle.  log2_scale != 0 is the dynamic-range test of the fp16x2 operand
+    format: two mid-network tensors live 2^10 higher / lower, everything downstream must still hold the
+    same gates."""
     spec = E.METHODS["HRNet_W48_COCO"]
-    m = E.TopDownModel(eng, helpers.state_dict("HRNet_W48_COCO"), spec, max_crops=1, use_tensor_cores=USE_TC, unique_slots=True)
+    sd = helpers.state_dict("HRNet_W48_COCO")
+    if log2_scale:
+        sd = rescaled_state_dict(sd, log2_scale)
+    m = E.TopDownModel(eng, sd, spec, max_crops=1, use_tensor_cores=USE_TC, unique_slots=True)
     frames = helpers.frames(3)
     bb = synthetic_bboxes(1, 21)[0]
     x, c, s, crop = OT.preprocess(cv2.cvtColor(frames[1], cv2.COLOR_BGR2RGB), bb, OT.HRNET_W48_COCO)
     hm, hmf = m.forward_heatmaps(crop[None])
-    net = helpers.oracle_net("HRNet_W48_COCO")
+    net = helpers.oracle_net("HRNet_W48_COCO")                  # the unscaled oracle: scaled tensors are compared after un-scaling
     xt = torch.from_numpy(x)[None]
     ref = _oracle_activations(net, m.program, torch.cat([xt, xt.flip(3)]))
     errs = []
     for op in m.program.ops:
         if op.kind == OP_HEAD:
             continue
+        f = 2.0 ** log2_scale if (op.bn in RESCALED and op.residual < 0) else 1.0
         for img in (0, 1):
-            got = m.debug_tensor(op.out, img)
+            got = m.debug_tensor(op.out, img) / np.float32(f)
             r = ref[op.out][img].numpy()
             errs.append((float(np.abs(got - r).max() / (np.abs(r).max() + 1e-20)), op.conv or "fuse", img))
     rh = ref[m.program.out_tensor].numpy()
     e_hm = max(np.abs(hm[0] - rh[0]).max() / np.abs(rh[0]).max(), np.abs(hmf[0] - rh[1]).max() / np.abs(rh[1]).max())
     errs.sort(reverse=True)
-    print("worst layers (max-abs-err / max-abs, accumulated from the input):", errs[:5], "heatmap:", e_hm)
+    print(f"worst layers [2^{log2_scale}] (max-abs-err / max-abs, accumulated from the input):", errs[:5], "heatmap:", e_hm)
     m.close()
     # Errors are accumulated from the network input through up to ~100 layers and measured against the max of each
     # map; the synthetic calibration makes the last fuse a thresholded, sparse map (y - thr with y ~ thr), which
     # amplifies relative error ~5x there and again in the head.  The keypoint gate (1e-3 px) is tested end to end below.
-    assert errs[0][0] < 5e-5, errs[:5]
+    # Gates = 3x the round-1 measurement (worst layer 1.2e-5, heatmap 1.75e-5).
+    assert errs[0][0] < 4e-5, errs[:5]
     assert sorted(e for e, _, _ in errs)[len(errs) // 2] < 5e-6
-    assert e_hm <= 1.5e-4
+    assert e_hm <= 5e-5
+
+
+def test_out_of_range_activation_is_an_error_not_a_clamp(eng):
+    """fp16x2 build: an activation beyond +-65504 must fail the call with PE_ERR_RANGE (round 1 clamped silently); the
+    wide-range tf32x3 build computes the same network normally."""
+    spec = E.METHODS["HRNet_W48_COCO"]
+    sd = rescaled_state_dict(helpers.state_dict("HRNet_W48_COCO"), 15)          # stem output up to ~1.6e5
+    m = E.TopDownModel(eng, sd, spec, max_crops=1, use_tensor_cores=USE_TC)
+    frames = helpers.frames(3)
+    eng.stage_frames(frames)
+    bb = synthetic_bboxes(1, 21)
+    try:
+        if eng.lib.pe_precision_mode() == 1:
+            with pytest.raises(E._lib.PoseEngineError) as ei:
+                m.topdown([1], bb)
+            assert ei.value.code == E._lib.PE_ERR_RANGE
+            with pytest.raises(E._lib.PoseEngineError):              # the flag is per call, not sticky-cleared by a failure
+                m.topdown([1], bb)
+        else:
+            got = m.topdown([1], bb)
+            ref = helpers.oracle_keypoints("HRNet_W48_COCO", frames, [1], bb)
+            assert np.median(np.abs(got[..., :2] - ref[..., :2])) <= 1e-3
+    finally:
+        m.close()
+
+
+def test_checkpoint_file_round_trip(eng, model48, tmp_path):
+    """An mmpose-style ``{'state_dict':..., 'meta':...}`` .pth (what the reference loads, wrappers/mmpose.py:35) read back by
+    weights.load_checkpoint gives the same engine bits as the in-memory tensors."""
+    from posepipeline_b200.weights import load_checkpoint
+    sd = helpers.state_dict("HRNet_W48_COCO")
+    path = str(tmp_path / "hrnet_w48_coco_384x288_dark-e881a4b6_20210203.pth")
+    torch.save({"meta": {"mmpose_version": "0.29.0"}, "state_dict": {k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}}, path)
+    sd2 = load_checkpoint(path)
+    assert set(sd2) == set(sd) and all(np.array_equal(sd2[k], sd[k]) for k in sd)
+    m = E.TopDownModel(eng, sd2, E.METHODS["HRNet_W48_COCO"], max_crops=4, use_tensor_cores=USE_TC)
+    frames = helpers.frames(3)
+    eng.stage_frames(frames)
+    bbs = synthetic_bboxes(3, 77)
+    try:
+        assert np.array_equal(m.topdown([0, 1, 2], bbs).view(np.uint32), model48.topdown([0, 1, 2], bbs).view(np.uint32))
+    finally:
+        m.close()
 
 
 # ------------------------------------------------------------------ end to end
-def _check_keypoints(got, ref32, ref64, tol=1e-3, cond_thr=1e-4, min_good=0.9):
-    """The gate: |dx| <= tol px wherever the oracle itself is well conditioned, i.e. its own fp32 and fp64 runs agree to
-    cond_thr px (DARK's Taylor step divides by the local Hessian: on a flat or ridge-like peak the oracle's fp32 rounding
-    alone moves the keypoint by more than that).  Elsewhere the error must stay proportional to the oracle's own."""
+def _check_keypoints(got, ref32, ref64, uncond_tol, tol=1e-3, cond_thr=1e-4, min_good=0.95):
+    """Two gates, both reported.  (1) UNCONDITIONAL: max |dx| over every keypoint <= uncond_tol (set per test to <= 3x the
+    measured value).  (2) |dx| <= tol = 1e-3 px wherever the oracle itself is well conditioned, i.e. its own fp32 and fp64
+    runs agree to cond_thr px -- DARK's Taylor step divides by the local Hessian, so on a flat or ridge-like peak the
+    oracle's own fp32 rounding moves the keypoint by several 1e-4 px, and two faithful fp32 implementations of the reference
+    (mmpose on cuDNN vs on oneDNN) differ by about that much too.  >= min_good of the keypoints must be well conditioned."""
     assert got.shape == ref32.shape
     cond = np.abs(ref32[..., :2] - ref64[..., :2]).max(-1)
     good = cond <= cond_thr
     d = np.abs(got[..., :2] - ref32[..., :2]).max(-1)
     worst = np.argsort(d.ravel())[::-1][:3]
-    print("keypoint |dx| px: max over well-conditioned", d[good].max(), "p99", np.quantile(d, 0.99), "well-conditioned", good.mean(),
-          "worst (d, oracle self-error):", [(float(d.ravel()[i]), float(cond.ravel()[i])) for i in worst])
-    assert good.mean() > min_good, good.mean()
+    print("keypoint |dx| px: UNCONDITIONAL max", d.max(), "| max over well-conditioned", d[good].max(), "p99", np.quantile(d, 0.99),
+          "well-conditioned", good.mean(), "worst (d, oracle self-error):", [(float(d.ravel()[i]), float(cond.ravel()[i])) for i in worst])
+    assert good.mean() >= min_good, good.mean()
     assert d[good].max() <= tol, (d[good].max(), np.argwhere(d > tol))
-    assert np.all(d[~good] <= 50 * cond[~good] + tol), (d[~good], cond[~good])
+    assert d.max() <= uncond_tol, (d.max(), uncond_tol)
     sc = np.abs(got[..., 2] - ref32[..., 2])
-    assert np.all(sc <= 1e-4 * np.maximum(1.0, np.abs(ref32[..., 2]))), sc.max()
-    return d[good].max(), good.mean()
+    assert np.all(sc <= 3e-5 * np.maximum(1.0, np.abs(ref32[..., 2]))), sc.max()
+    return d.max(), d[good].max(), good.mean()
 
 
 def test_topdown_end_to_end_keypoints(eng, model48):
@@ -215,8 +289,8 @@ def test_topdown_end_to_end_keypoints(eng, model48):
     got = model48.topdown(fidx, bbs)
     ref32 = helpers.oracle_keypoints("HRNet_W48_COCO", frames, fidx, bbs, "float32")
     ref64 = helpers.oracle_keypoints("HRNet_W48_COCO", frames, fidx, bbs, "float64")
-    worst, frac = _check_keypoints(got, ref32, ref64)
-    print(f"max |dx| over well-conditioned keypoints = {worst:.2e} px ({frac:.1%} well conditioned)")
+    umax, worst, frac = _check_keypoints(got, ref32, ref64, uncond_tol=4e-4)      # measured 1.2e-4 (2 float32 ulps at x ~ 1000 px)
+    print(f"max |dx| = {umax:.2e} px unconditional, {worst:.2e} over well-conditioned keypoints ({frac:.1%} well conditioned)")
     again = model48.topdown(fidx, bbs)
     assert np.array_equal(got, again)                                    # deterministic
     assert model48.topdown([], np.zeros((0, 4))).shape == (0, 17, 3)     # empty input
@@ -234,7 +308,7 @@ def test_topdown_w32_config1(eng):
     assert got.shape == (1, 17, 3)
     # 'default' post-processing quantises to quarter pixels: equal unless the argmax itself is a near-tie
     same = np.abs(got[..., :2] - ref[..., :2]).max(-1) <= 1e-3
-    assert same.mean() >= 0.9, (got, ref)
+    assert same.mean() >= 16 / 17, (got, ref)               # at most one near-tie argmax among the 17 joints
     assert np.abs(got[..., 2] - ref[..., 2]).max() <= 1e-4 * max(1.0, np.abs(ref[..., 2]).max())
     m.close()
 
@@ -277,7 +351,9 @@ def test_topdown_halpe136_and_wholebody133(eng):
         ref32 = helpers.oracle_keypoints(method, frames, fidx, bbs, "float32")
         ref64 = helpers.oracle_keypoints(method, frames, fidx, bbs, "float64")
         assert got.shape == (3, spec.num_joints, 3)
-        _check_keypoints(got, ref32, ref64, min_good=0.7)
+        # 3 crops x 133/136 joints: the ill-conditioned tail (oracle fp32-vs-fp64 2.4e-4..3.7e-4 px) measured 1.10e-3 px in
+        # round 1; the unconditional gate is 1.5x that, the 1e-3 px gate applies to the well-conditioned >= 95 %
+        _check_keypoints(got, ref32, ref64, uncond_tol=1.7e-3)
         m.close()
 
 
@@ -365,3 +441,20 @@ def test_topdown_is_independent_of_internal_batching(eng, model48):
         big.close()
     assert np.array_equal(a.view(np.uint32), a2.view(np.uint32))
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+# ------------------------------------------------------------------ the wide-range tf32x3 build of the same sources
+@pytest.mark.skipif(os.environ.get("PE_SUBRUN") == "1", reason="already inside the tf32 sub-run")
+def test_tf32_build_passes_the_parity_suite():
+    """PE_PRECISION selects the library at import time, so the second precision runs this file in a subprocess: the driver's
+    single ``pytest -m gpu`` invocation covers both builds."""
+    import subprocess
+    import sys
+    if not os.path.exists(os.path.join(ROOT, "posepipeline_b200", "libposeengine_tf32.so")):
+        pytest.fail("libposeengine_tf32.so missing: __graft_entry__.build() builds it")
+    env = dict(os.environ, PE_PRECISION="tf32", PE_SUBRUN="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_parity.py", "-m", "gpu", "-q", "-x", "-s", "-p", "no:cacheprovider"],
+                       cwd=ROOT, env=env, capture_output=True, text=True, timeout=1500)
+    tail = "\n".join(l[:300] for l in r.stdout.splitlines() if "keypoint |dx|" in l or "worst layers" in l or "passed" in l or "failed" in l)
+    print("tf32 sub-run:\n" + tail)
+    assert r.returncode == 0, (r.returncode, r.stdout[-3000:], r.stderr[-2000:])
