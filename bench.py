@@ -136,15 +136,25 @@ def parity_check(kp, frames, fidx, bboxes, n_check):
     from posepipeline_b200.weights import synthetic_hrnet_state_dict
     spec = METHODS[METHOD]
     sd = synthetic_hrnet_state_dict(build_program(spec.variant, spec.image_size[1], spec.image_size[0], spec.num_joints), 0)
+    import torch
     net = OH.load_net(sd, spec.variant)
+    net64 = OH.load_net(sd, spec.variant, torch.float64)
     idx = np.linspace(0, len(fidx) - 1, n_check).round().astype(int)
-    ref = OT.top_down_video(net, [frames[fidx[i]] for i in idx], bboxes[idx], OT.HRNET_W48_COCO)
+    fr = [frames[fidx[i]] for i in idx]
+    ref = OT.top_down_video(net, fr, bboxes[idx], OT.HRNET_W48_COCO)
+    ref64 = OT.top_down_video(net64, fr, bboxes[idx], OT.HRNET_W48_COCO)
     d = np.abs(kp[idx][..., :2] - ref[..., :2]).max(-1)
+    cond = np.abs(ref[..., :2] - ref64[..., :2]).max(-1)        # how far the reference's own fp32 rounding moves each keypoint
+    good = cond <= 1e-4
     ds = np.abs(kp[idx][..., 2] - ref[..., 2])
-    return {"max_abs_px": float(d.max()), "p99_abs_px": float(np.quantile(d, 0.99)), "median_abs_px": float(np.median(d)),
+    ok = bool(d[good].max() <= 1e-3 and np.all(d[~good] <= 10 * cond[~good] + 1e-3))
+    return {"max_abs_px": float(d.max()), "max_abs_px_well_conditioned": float(d[good].max()),
+            "frac_well_conditioned": float(good.mean()), "oracle_fp32_vs_fp64_max_px": float(cond.max()),
+            "p99_abs_px": float(np.quantile(d, 0.99)), "median_abs_px": float(np.median(d)),
             "max_abs_score": float(ds.max()), "n": int(len(idx)), "keypoints": int(d.size),
-            "against": "oracle fp32 (torch CPU + cv2 + numpy), same frames and boxes", "gate_px": 1e-3,
-            "ok": bool(d.max() <= 1e-3)}
+            "against": "oracle fp32 (torch CPU + cv2 + numpy), same frames and boxes; well conditioned = the oracle's own "
+                       "fp32 and fp64 runs agree to 1e-4 px",
+            "gate": "<= 1e-3 px where well conditioned, <= 10x the oracle's own fp32-vs-fp64 error elsewhere", "ok": ok}
 
 
 def run_reference(args):

@@ -36,6 +36,7 @@ extern "C" {
 typedef struct pe_engine pe_engine;
 typedef struct pe_model pe_model;
 typedef struct pe_lifter pe_lifter;
+typedef struct pe_bytetrack pe_bytetrack;
 
 /* layer program handed over by the host graph builder (posepipeline_b200/hrnet_spec.py) */
 enum { PE_OP_STEM = 0, PE_OP_CONV = 1, PE_OP_FUSE = 2, PE_OP_HEAD = 3 };
@@ -175,6 +176,20 @@ int pe_lifter_create(pe_engine* e, const float* weights, int64_t n_floats, const
 int pe_lifter_destroy(pe_lifter* l);
 /* kp2d_norm: N*17*2 normalised screen coords; out: N*17*3.  Windows are edge-replicated (pad 121). */
 int pe_lift3d(pe_lifter* l, const float* kp2d_norm, int32_t n_frames, float* out3d);
+
+/* ---- ByteTrack association (host only; the per-frame `ByteTracker.track` mmtrack runs inside inference_mot,
+ * pose_pipeline/wrappers/mmtrack.py:45; configuration 3rdparty/mmtracking/mot/bytetrack/
+ * bytetrack_yolox_x_crowdhuman_mot17-private-half.py:21-28).  cfg = NULL (the reference's values) or 9 floats
+ * {obj_score high, low, init_track_thr, match_iou high, low, tentative, weight_iou_with_det_scores, num_tentatives,
+ * num_frames_retain}. ---- */
+int pe_bytetrack_create(const float* cfg, int32_t n_cfg, pe_bytetrack** out);
+int pe_bytetrack_destroy(pe_bytetrack* t);
+int pe_bytetrack_reset(pe_bytetrack* t);
+/* One frame: dets = n rows [x1,y1,x2,y2,score] in the detector's output order (score-descending NMS output); frame_id 0
+ * resets the tracker like ByteTrack.simple_test.  out_rows: up to cap rows [track_id,x1,y1,x2,y2,score] (float64, the dtype
+ * of the reference's result["track_bboxes"][0]) in the reference's row order; *n_out = rows written. */
+int pe_bytetrack_update(pe_bytetrack* t, int32_t frame_id, const float* dets, int32_t n, double* out_rows, int32_t cap,
+                        int32_t* n_out);
 
 #ifdef __cplusplus
 }

@@ -2,15 +2,28 @@
 
     import posepipeline_b200.install as pe; pe.install()
 
-registers this package's wrappers under the module names the reference's ``make()`` methods import lazily
-(``pose_pipeline/pipeline.py:526,1021,1271``: ``from .wrappers.mmpose import mmpose_top_down_person`` ...), and swaps the
-arithmetic of ``PersonBbox.make`` (``pipeline.py:656-687``) for the bit-exact C-ABI restatement (which also runs on
-pandas >= 2.1, where the reference's ``fillna(method=...)`` raises).  DataJoint tables, ``populate()`` and
+The reference's ``make()`` methods import their wrapper functions lazily (``pose_pipeline/pipeline.py:526,1021,1271``:
+``from .wrappers.mmpose import mmpose_top_down_person`` ...).  ``install()`` therefore imports the reference's own wrapper
+modules and overwrites ONLY the functions this engine provides, so everything else in them keeps working
+(``mmpose_bottom_up``, used by ``BottomUpPeople.make`` at ``pipeline.py:210``, stays the reference's).  A reference wrapper
+module that cannot be imported because its third-party dependency is absent (``pose_pipeline/wrappers/mmtrack.py:5`` does
+``import mmtrack.apis`` at module level) is replaced by this package's module of the same name.
+
+It also swaps the arithmetic of ``PersonBbox.make`` (``pipeline.py:656-687``) for the bit-exact C-ABI restatement, which
+runs on pandas >= 2.1 where the reference's ``fillna(method=...)`` raises.  DataJoint tables, ``populate()`` and
 ``standard_pipelines.py`` stay the reference's own.
 """
 from __future__ import annotations
 
+import importlib
 import sys
+
+# reference module -> names this engine replaces in it
+PROVIDED = {
+    "mmpose": ("mmpose_top_down_person", "mmpose_joint_dictionary"),
+    "videopose3d": ("process_videopose3d", "VideoPoseArgs", "normalize_screen_coordinates"),
+    "mmtrack": ("mmtrack_bounding_boxes",),
+}
 
 
 def person_bbox_make(self, key):
@@ -25,17 +38,38 @@ def person_bbox_make(self, key):
     self.insert1(key)
 
 
-def install(patch_person_bbox: bool = True):
-    from .wrappers import mmpose, mmtrack, videopose3d
-    sys.modules["pose_pipeline.wrappers.mmpose"] = mmpose
-    sys.modules["pose_pipeline.wrappers.videopose3d"] = videopose3d
-    # mmtrack is only an interface mirror in this round: leave the reference's tracker in place
+def _patch_module(name: str):
+    """-> (module now registered as pose_pipeline.wrappers.<name>, 'patched' | 'replaced')"""
+    ours = importlib.import_module(f"posepipeline_b200.wrappers.{name}")
+    full = f"pose_pipeline.wrappers.{name}"
     try:
-        import pose_pipeline.wrappers as W
-        W.mmpose, W.videopose3d = mmpose, videopose3d
-    except Exception:
-        pass
+        ref = importlib.import_module(full)
+    except Exception:                      # ImportError of an absent third-party package, or no such reference module
+        ref = None
+    if ref is None or ref is ours:
+        sys.modules[full] = ours
+        try:
+            import pose_pipeline.wrappers as W
+            setattr(W, name, ours)
+        except Exception:
+            pass
+        return ours, "replaced"
+    for attr in PROVIDED[name]:
+        if hasattr(ours, attr):
+            if name == "mmtrack" and attr == "mmtrack_bounding_boxes" and not hasattr(ours, "_reference_impl_set"):
+                # methods this engine does not build (tracktor / deepsort / qdtrack) keep going to the reference
+                ours._reference_impl = getattr(ref, attr)
+                ours._reference_impl_set = True
+            setattr(ref, attr, getattr(ours, attr))
+    return ref, "patched"
+
+
+def install(patch_person_bbox: bool = True):
+    """Returns {module name: 'patched' | 'replaced'}."""
+    status = {}
+    for name in PROVIDED:
+        _, status[name] = _patch_module(name)
     if patch_person_bbox:
         import pose_pipeline.pipeline as P
         P.PersonBbox.make = person_bbox_make
-    return mmpose, videopose3d
+    return status

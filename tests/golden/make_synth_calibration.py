@@ -5,6 +5,12 @@ script calibrates (a) a per-channel bias on the last fuse sum so the 48 final fe
 bumps, and (b) a sparse positive head, so synthetic heatmaps look like a trained network's:
 ~0 background with O(1) peaks.  Only 48 + 17*48 + 17 numbers per variant are stored.
 
+The threshold is the 99.5 % quantile of each feature (round 1 used 97 %): only the tips of the feature blobs survive, so
+the peaks are compact (smaller than DARK's 17x17 blur) rather than plateaus.  Measured with the oracle alone, fp32 run vs
+fp64 run of the SAME network (i.e. how far the reference's own rounding moves a keypoint): at 97 % the benchmark crops
+disagreed by up to 1.5e-3 px and 720p crops by 0.24 px; at 99.5 % by 6e-5 px on the parity-test crops, with a tail of a few
+1e-3 px left on ~4 % of the benchmark keypoints (two peaks of nearly equal height).
+
     python tests/golden/make_synth_calibration.py
 """
 import os, sys
@@ -24,7 +30,7 @@ from oracle import topdown as T
 OUT = os.path.join(ROOT, "posepipeline_b200", "data", "synthetic_head_calibration.npz")
 
 
-def calibrate(variant, in_h, in_w, K, seed, cfg, n_crops=10, q=0.97):
+def calibrate(variant, in_h, in_w, K, seed, cfg, n_crops=10, q=0.995):
     prog = build_program(variant, in_h, in_w, K)
     sd = W.synthetic_hrnet_state_dict(prog, seed, calibrated=False)
     net = load_net(sd, variant)

@@ -275,6 +275,7 @@ def _check_keypoints(got, ref32, ref64, uncond_tol, tol=1e-3, cond_thr=1e-4, min
     assert good.mean() >= min_good, good.mean()
     assert d[good].max() <= tol, (d[good].max(), np.argwhere(d > tol))
     assert d.max() <= uncond_tol, (d.max(), uncond_tol)
+    assert np.all(d[~good] <= 10 * cond[~good] + tol), (d[~good], cond[~good])    # never worse than ~10x the reference's own rounding
     sc = np.abs(got[..., 2] - ref32[..., 2])
     assert np.all(sc <= 3e-5 * np.maximum(1.0, np.abs(ref32[..., 2]))), sc.max()
     return d.max(), d[good].max(), good.mean()
@@ -351,9 +352,9 @@ def test_topdown_halpe136_and_wholebody133(eng):
         ref32 = helpers.oracle_keypoints(method, frames, fidx, bbs, "float32")
         ref64 = helpers.oracle_keypoints(method, frames, fidx, bbs, "float64")
         assert got.shape == (3, spec.num_joints, 3)
-        # 3 crops x 133/136 joints: the ill-conditioned tail (oracle fp32-vs-fp64 2.4e-4..3.7e-4 px) measured 1.10e-3 px in
-        # round 1; the unconditional gate is 1.5x that, the 1e-3 px gate applies to the well-conditioned >= 95 %
-        _check_keypoints(got, ref32, ref64, uncond_tol=1.7e-3)
+        # 3 crops x 133/136 joints; round 1 (q = 97 % calibration, unscaled low halves) measured 1.10e-3 px on the
+        # ill-conditioned tail; with compact synthetic peaks and the 2^11-scaled low halves the unconditional gate is 1e-3
+        _check_keypoints(got, ref32, ref64, uncond_tol=1e-3)
         m.close()
 
 
