@@ -294,11 +294,14 @@ class _TableMeta(type):
     def __bool__(cls):
         return True
 
-    def __getattr__(cls, name):
-        if name in ("populate", "insert1", "insert", "fetch", "fetch1", "delete", "delete_quick", "proj", "primary_key",
-                    "heading_names", "key_source", "drop", "drop_quick"):
+    _FORWARD = frozenset(("populate", "insert1", "insert", "fetch", "fetch1", "delete", "delete_quick", "proj", "primary_key",
+                          "heading_names", "heading", "key_source", "drop", "drop_quick"))
+
+    def __getattribute__(cls, name):
+        # table methods called on the class act on an instance (DataJoint's TableMeta does the same)
+        if name in _TableMeta._FORWARD and type.__getattribute__(cls, "_declared"):
             return getattr(cls(), name)
-        raise AttributeError(name)
+        return type.__getattribute__(cls, name)
 
 
 _ATTR = re.compile(r"^(\w+)\s*(?:=\s*(.+?))?\s*:\s*([^#]+?)\s*(?:#.*)?$")
