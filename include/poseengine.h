@@ -171,9 +171,14 @@ int pe_tc_plan_candidates(int32_t Cin, int32_t Cout, int32_t ks, int32_t has_res
                           int32_t gather, int32_t* out, int32_t cap);
 
 /* ---- VideoPose3D lifter (wrappers/videopose3d.py:46-85; TemporalModelOptimized1f 243 frames) ---- */
-int pe_lifter_create(pe_engine* e, const float* weights, int64_t n_floats, const int64_t* offsets /*see lifter.py*/,
-                     int32_t n_offsets, int32_t channels, pe_lifter** out);
+/* offsets: 10 layers (expand_conv, layers_conv[0..7], shrink) x 3 float offsets into `weights`: SIMT packing
+ * [tap][Cin][Cout], folded bias [Cout], tensor-core packing (engine.pack_tc_weights) or -1. */
+int pe_lifter_create(pe_engine* e, const float* weights, int64_t n_floats, const int64_t* offsets, int32_t n_offsets,
+                     int32_t channels, pe_lifter** out);
 int pe_lifter_destroy(pe_lifter* l);
+/* 1 when the temporal convolutions run on the tcgen05 kernel (after the first pe_lift3d), 0 = fp32 SIMT GEMMs */
+int pe_lifter_uses_tensor_cores(pe_lifter* l);
+int pe_lifter_launch_count(pe_lifter* l, int64_t* count);
 /* kp2d_norm: N*17*2 normalised screen coords; out: N*17*3.  Windows are edge-replicated (pad 121). */
 int pe_lift3d(pe_lifter* l, const float* kp2d_norm, int32_t n_frames, float* out3d);
 

@@ -87,6 +87,25 @@ def process_videopose3d(keypoints: np.ndarray, height: int, width: int, net: Tem
     return {"keypoints_3d": keypoints_3d, "keypoints_valid": [True] * N}
 
 
+@torch.no_grad()
+def dilated_whole_sequence(net: TemporalModelOptimized1f, kp_norm: np.ndarray) -> np.ndarray:
+    """The same network evaluated ONCE over the edge-padded sequence with dilations 1,3,9,27,81 instead of once per 243-frame
+    window with strides (identical sums of identical products; tests/test_oracle.py checks it against the windowed form).
+    Used as the checker for long sequences, where the windowed form (176 MMAC per frame) is too slow on a CPU."""
+    pad = (net.receptive_field() - 1) // 2
+    dt = next(net.parameters()).dtype
+    xp = np.pad(kp_norm, ((pad, pad), (0, 0), (0, 0)), "edge").reshape(1, -1, 34).transpose(0, 2, 1)
+    y = torch.from_numpy(np.ascontiguousarray(xp)).to(dt)
+    y = F.relu(net.expand_bn(F.conv1d(y, net.expand_conv.weight)))
+    dil = 3
+    for i in range(4):
+        res = y[:, :, dil:-dil]
+        y = F.relu(net.layers_bn[2 * i](F.conv1d(y, net.layers_conv[2 * i].weight, dilation=dil)))
+        y = res + F.relu(net.layers_bn[2 * i + 1](F.conv1d(y, net.layers_conv[2 * i + 1].weight)))
+        dil *= 3
+    return net.shrink(y)[0].T.reshape(-1, 17, 3).double().numpy()
+
+
 def load_lifter(state_dict, dtype=torch.float32):
     net = TemporalModelOptimized1f()
     sd = {k: (v if isinstance(v, torch.Tensor) else torch.from_numpy(np.asarray(v).copy())) for k, v in state_dict.items()}

@@ -94,6 +94,8 @@ def load():
         "pe_lifter_create": (C.c_int, [vp, vp, i64, vp, i32, i32, P(vp)]),
         "pe_lifter_destroy": (C.c_int, [vp]),
         "pe_lift3d": (C.c_int, [vp, vp, i32, vp]),
+        "pe_lifter_uses_tensor_cores": (C.c_int, [vp]),
+        "pe_lifter_launch_count": (C.c_int, [vp, P(i64)]),
         "pe_bytetrack_create": (C.c_int, [vp, i32, P(vp)]),
         "pe_bytetrack_destroy": (C.c_int, [vp]),
         "pe_bytetrack_reset": (C.c_int, [vp]),

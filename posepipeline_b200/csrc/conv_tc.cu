@@ -59,6 +59,17 @@ struct TcParams {
   int H, W, Hp, Wp;
   int nchunk, Cout;
   int Rpad, RB, nbA, halo;   // activation window: Rpad rows loaded as nbA boxes of RB rows; halo = window rows BEFORE the tile's first row
+  // Segmented windows (wide images): contiguous mode loads ONE run of 128*MT + halo rows that serves every stencil row, which
+  // costs 2*(W+3) extra rows per tile -- more than the tile itself once W > 128.  Segmented mode loads one run of
+  // 128*MT + 2 rows per stencil row instead (nseg runs, seg_step rows apart in the tensor, Rseg rows apart in shared memory).
+  int nseg, nb_seg, Rseg, seg_step;
+  int row_step;              // shared-memory rows between two stencil rows of the window: Wp (contiguous), Rseg (segmented), dilation (1-D)
+  int in_coff, out_coff, res_coff;   // first 16-channel chunk of this layer's view inside wider input / output / residual tensors
+  int res_rowF;              // floats per row of the residual tensor
+  int res_row_off;           // residual row = output row + res_row_off (1-D temporal layers read a centre-cropped residual)
+  int res_post;              // 1 = residual added AFTER the activation (VideoPose3D blocks), 0 = before (HRNet / Darknet blocks)
+  int no_border;             // 1 = every row < M is an output row (1-D / GEMM layers); 0 = rows on the zero border are written as zeros
+  int act;                   // 0 none, 1 ReLU, 2 SiLU
   int S;                     // pipeline stages
   int nstage;                // stages per tile = nchunk / KC
   int rpg;                   // stencil rows per drain group
@@ -66,7 +77,7 @@ struct TcParams {
   int nstg;                  // epilogue store-staging buffers per warp (1..3)
   int gather;                // 2x2 layers: 1 = the activation windows are gathered by TMA from the ORIGINAL stride-2 input (no s2d copy)
   int cpp;                   // gather: 16-channel chunks per input parity (py,px)
-  int relu, tmem_cols;
+  int tmem_cols;
   uint32_t div_hpwp_mul, div_hpwp_sh, div_wp_mul, div_wp_sh;   // exact n / (Hp*Wp) and n / Wp for n < 2^31: (n * mul) >> sh (64-bit product)
   int mma_wait_ns;           // MMA warps: 0 = spin on test_wait (default), > 0 = suspended try_wait with this time hint
   int poll_ns;               // producer / epilogue waits: > 0 nanosleep back-off between polls, < 0 suspended try_wait with that time hint, 0 spin
@@ -358,12 +369,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const int par = j / p.cpp, jj = j - par * p.cpp;
               int qq = g_q, nn = g_n;
               for (int b = 0; b < g_nbox; ++b) {
-                tma_load_4d(dst + (uint32_t)b * 2u * (uint32_t)p.Wp * CHB, &tmA, jj * (CHB / 4), (par & 1) - 2, 4 * qq - 2 + (par >> 1), nn, full);
+                tma_load_4d(dst + (uint32_t)b * 2u * (uint32_t)p.Wp * CHB, &tmA, (p.in_coff + jj) * (CHB / 4), (par & 1) - 2, 4 * qq - 2 + (par >> 1), nn, full);
                 if (++qq == (p.Hp >> 1)) { qq = 0; ++nn; }
               }
             } else
-            for (int b = 0; b < p.nbA; ++b)
-              tma_load_2d(dst + (uint32_t)kc * a_bytes + (uint32_t)b * p.RB * CHB, &tmA, j * (CHB / 4), m0 - p.halo + b * p.RB, full);
+            for (int sg = 0; sg < p.nseg; ++sg)
+              for (int b = 0; b < p.nb_seg; ++b)
+                tma_load_2d(dst + (uint32_t)kc * a_bytes + (uint32_t)(sg * p.Rseg + b * p.RB) * CHB, &tmA, (p.in_coff + j) * (CHB / 4),
+                            m0 - p.halo + sg * p.seg_step + b * p.RB, full);
             // weights: box {one chunk row, NC output channels, TAPS taps} of the [tap][chunk*Cout + n][CHB] tensor
             tma_load_3d(dst + (uint32_t)KC * a_bytes + (uint32_t)kc * b_chunk_bytes, &tmW, 0, j * p.Cout + n0, 0, full);
           }
@@ -383,7 +396,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t desc_hi = (uint32_t)(d0 >> 32);                    // identical for A and B tiles
     const uint32_t ring_lo0 = (uint32_t)d0;
     const uint32_t stage16 = stage_bytes >> 4, a16 = a_bytes >> 4;
-    const uint32_t wp16 = (uint32_t)p.Wp * ROW16;                     // one image row down, in 16-byte units of the window
+    const uint32_t wp16 = (uint32_t)p.row_step * ROW16;               // one stencil row down, in 16-byte units of the window
     Ring r;
 #if PE_TC_PROFILE
     long long c_wf = 0, c_is = 0, c_wm = 0, c_wc = 0, c_st = 0;
@@ -539,7 +552,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;                       // which of the EPI_PARTS warps of this quarter
     constexpr int NGH = (NG + EPI_PARTS - 1) / EPI_PARTS;                       // groups per warp (the odd warp of an odd NG has one fewer)
-    const int rowF = ps_row_floats(p.Cout);
+    const int rowF = p.res_rowF;                            // floats per row of the residual tensor (plain-load fallback)
     constexpr int CF = PS_CHUNK_FLOATS;                     // floats per 16-channel chunk of a row
     constexpr int gpm = NC / 16;                            // 16-column groups per 128-row accumulator
     const int ndrain = p.ndrain;
@@ -568,8 +581,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int gi = 0; gi < NGH; ++gi) {
           const int g = EPI_PARTS * gi + half;
           if (g < NG && gi < p.nstg)
-            tma_load_2d(st_base + (uint32_t)gi * 32u * CHB, &tmR, (nsl_ * NC + (g % gpm) * 16) / 16 * CF,
-                        tile_ * 128 * MT + (g / gpm) * 128 + q * 32, res_bar);
+            tma_load_2d(st_base + (uint32_t)gi * 32u * CHB, &tmR, (p.res_coff + (nsl_ * NC + (g % gpm) * 16) / 16) * CF,
+                        tile_ * 128 * MT + (g / gpm) * 128 + q * 32 + p.res_row_off, res_bar);
         }
       }
     };
@@ -578,7 +591,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // FIRST drain (the previous tile's stores are long done) and add it after the LAST (an epilogue that is behind runs its
     // drains back to back, so the distance must be several drains); layers with fewer (1x1) request the next tile's at the end
     // of the current one.
-    const bool res_lazy = p.res && ndrain >= 3;
+    const bool res_lazy = p.res && (ndrain >= 3 || p.res_post);
     if (p.res && !res_lazy && blockIdx.x < p.total_work) res_issue(tile, nsl);
 #if PE_TC_PROFILE
     long long e_wm = 0, e_dr = 0, e_rs = 0, e_wc = 0, e_co = 0, e_fi = 0, e_ri = 0, e_tc = 0, e_f1 = 0, e_f2 = 0, e_f3 = 0, e_f4 = 0, e_t = clock64();
@@ -596,7 +609,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) {
         const long long m = m0 + mt * 128 + q * 32 + lane;
-        if (m < p.M) {                                                   // M < 2^31 (asserted on the host)
+        if (m < p.M && p.no_border) interior |= 1u << mt;
+        else if (m < p.M) {                                              // M < 2^31 (asserted on the host)
           const uint32_t r = (uint32_t)m - fastdiv((uint32_t)m, p.div_hpwp_mul, p.div_hpwp_sh) * (uint32_t)hpwp;
           const int py = (int)fastdiv(r, p.div_wp_mul, p.div_wp_sh), px = (int)r - py * p.Wp;
           if (py >= 1 && py <= p.H && px >= 1 && px <= p.W) interior |= 1u << mt;
@@ -633,6 +647,47 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
 #endif
       };
+      // this lane's residual row chunk of group g: from the warp's staging buffer gi (TMA-loaded), or a plain load when the
+      // warp owns more groups than staging buffers; rows on the zero border read as zeros
+      auto res_fetch = [&](int gi, int g, uint4 (&v)[NV]) {
+        const uint32_t sw = (CHB == 128) ? (lane & 7u) : ((lane >> 1) & 3u);   // swizzle of this lane's staged row
+        if (gi < p.nstg) {
+          const uint32_t srow = st_base + (uint32_t)gi * 32u * CHB + (uint32_t)lane * CHB;
+#pragma unroll
+          for (int i = 0; i < NV; ++i)
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[i].x), "=r"(v[i].y), "=r"(v[i].z), "=r"(v[i].w)
+                         : "r"(srow + (((uint32_t)i ^ sw) << 4)) : "memory");
+        } else if ((interior >> (g / gpm)) & 1u) {       // more groups than staging buffers: plain loads
+          const long long m = m0 + (g / gpm) * 128 + q * 32 + lane + p.res_row_off;
+          const uint4* rp = reinterpret_cast<const uint4*>(p.res + m * rowF + (p.res_coff + n0 / 16 + g % gpm) * CF);
+#pragma unroll
+          for (int i = 0; i < NV; ++i) v[i] = __ldg(rp + i);
+        } else {
+#pragma unroll
+          for (int i = 0; i < NV; ++i) v[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
+      };
+      // same without the per-channel scaling: a += float(chunk)
+      auto res_add16_unit = [&](float (&a)[16], const uint4 (&v)[NV]) {
+#if PE_FP16
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const uint32_t* hw = reinterpret_cast<const uint32_t*>(&v[i]);
+          const uint32_t* lw = reinterpret_cast<const uint32_t*>(&v[2 + i]);
+#pragma unroll
+          for (int k2 = 0; k2 < 4; ++k2) {
+            const float2 h0 = __half22float2(*reinterpret_cast<const __half2*>(&hw[k2])), l0 = __half22float2(*reinterpret_cast<const __half2*>(&lw[k2]));
+            a[8 * i + 2 * k2] += fmaf(l0.x, PS_LO_INV, h0.x); a[8 * i + 2 * k2 + 1] += fmaf(l0.y, PS_LO_INV, h0.y);
+          }
+        }
+#else
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 hv = *reinterpret_cast<const float4*>(&v[i]), lv = *reinterpret_cast<const float4*>(&v[4 + i]);
+          a[4 * i + 0] += hv.x + lv.x; a[4 * i + 1] += hv.y + lv.y; a[4 * i + 2] += hv.z + lv.z; a[4 * i + 3] += hv.w + lv.w;
+        }
+#endif
+      };
       EPI_TICK(e_tc)
       for (int d = 0; d < ndrain; ++d) {
         mbar_wait_relaxed(bar_main_full + 8 * dg, dgp, p.poll_ns);
@@ -661,29 +716,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (++dg == NMAIN) { dg = 0; dgp ^= 1u; }
         EPI_TICK(e_dr)
         if (d == 0 && res_lazy) { res_issue(tile, nsl); __syncwarp(); }
-        if (p.res && d == (res_lazy ? ndrain - 1 : 0)) {
+        if (p.res && !p.res_post && d == (res_lazy ? ndrain - 1 : 0)) {
           mbar_wait_relaxed(res_bar, tl & 1u, p.poll_ns);
-          const uint32_t sw = (CHB == 128) ? (lane & 7u) : ((lane >> 1) & 3u);   // swizzle of this lane's staged row
 #pragma unroll
           for (int gi = 0; gi < NGH; ++gi) {
             const int g = EPI_PARTS * gi + half;
             if (g >= NG) continue;
             uint4 v[NV];
-            if (gi < p.nstg) {
-              const uint32_t srow = st_base + (uint32_t)gi * 32u * CHB + (uint32_t)lane * CHB;
-#pragma unroll
-              for (int i = 0; i < NV; ++i)
-                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[i].x), "=r"(v[i].y), "=r"(v[i].z), "=r"(v[i].w)
-                             : "r"(srow + (((uint32_t)i ^ sw) << 4)) : "memory");
-            } else if ((interior >> (g / gpm)) & 1u) {       // more groups than staging buffers: plain loads
-              const long long m = m0 + (g / gpm) * 128 + q * 32 + lane;
-              const uint4* rp = reinterpret_cast<const uint4*>(p.res + m * rowF + (n0 / 16 + g % gpm) * CF);
-#pragma unroll
-              for (int i = 0; i < NV; ++i) v[i] = __ldg(rp + i);
-            } else {
-#pragma unroll
-              for (int i = 0; i < NV; ++i) v[i] = make_uint4(0u, 0u, 0u, 0u);
-            }
+            res_fetch(gi, g, v);
             res_add16(acc[gi], v, g);
           }
           __syncwarp();
@@ -711,7 +751,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_corr_empty + 8 * cbuf);
       EPI_TICK(e_co)
-      // ---- bias / ReLU / split / store (the MMA warps are already on the next tile)
+      if (p.res && p.res_post) mbar_wait_relaxed(res_bar, tl & 1u, p.poll_ns);
+      // ---- bias / activation / split / store (the MMA warps are already on the next tile)
 #pragma unroll
       for (int gi = 0; gi < NGH; ++gi) {
         const int g = EPI_PARTS * gi + half;
@@ -731,9 +772,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             v[4 * i + 0] = fmaf(acc[gi][4 * i + 0], s4.x, b4.x); v[4 * i + 1] = fmaf(acc[gi][4 * i + 1], s4.y, b4.y);
             v[4 * i + 2] = fmaf(acc[gi][4 * i + 2], s4.z, b4.z); v[4 * i + 3] = fmaf(acc[gi][4 * i + 3], s4.w, b4.w);
           }
-          if (p.relu) {
+          if (p.act == 1) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+          } else if (p.act == 2) {                           // SiLU (YOLOX ConvModule): x * sigmoid(x) = x / (1 + exp(-x))
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __fdiv_rn(v[i], 1.0f + expf(-v[i]));
+          }
+          if (p.res && p.res_post) {                         // residual after the activation (VideoPose3D: x = res + ReLU(bn(conv)))
+            uint4 rv[NV];
+            res_fetch(gi, g, rv);
+            float one[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) one[i] = 0.f;
+            res_add16_unit(one, rv);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += one[i];
           }
 #if PE_FP16
           {                                                  // a value beyond the fp16x2 range is an error, not a silent clamp
@@ -761,8 +815,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // conflict-free 16-byte stores), then ONE bulk tensor store writes them as full lines (a per-thread row store
         // would scatter 16-byte pieces over 32 lines per instruction).  Rows past the tensor end are clipped by TMA.
         EPI_TICK(e_f1)
-        const uint32_t sbuf = st_base + st_slot * 32u * CHB;   // the nstg buffers rotate: a store has nstg-1 group times to read its source
-        if (lane == 0) bulk_wait_read(p.nstg - 1);          // the buffer about to be overwritten has been read by its store
+        // the nstg buffers rotate: a store has nstg-1 group times to read its source.  Post-activation residual layers keep
+        // group gi's residual in buffer gi until this point, so its output goes to that same buffer
+        if (p.res && p.res_post) st_slot = (uint32_t)gi % (uint32_t)p.nstg;
+        const uint32_t sbuf = st_base + st_slot * 32u * CHB;
+        if (lane == 0) bulk_wait_read((p.res && p.res_post) ? (gi < p.nstg ? p.nstg : 0) : p.nstg - 1);   // the buffer about to be overwritten has been read by its store
         __syncwarp();
         EPI_TICK(e_f2)
         const uint32_t srow = sbuf + (uint32_t)lane * CHB;
@@ -775,7 +832,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         EPI_TICK(e_f3)
         if (lane == 0) {
           const long long mrow = m0 + mt * 128 + q * 32;
-          if (mrow < p.M) tma_store_2d(&tmO, (n0 + c0) / 16 * CF, (int)mrow, sbuf);
+          if (mrow < p.M) tma_store_2d(&tmO, (p.out_coff + (n0 + c0) / 16) * CF, (int)mrow, sbuf);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
         if (++st_slot == (uint32_t)p.nstg) st_slot = 0;
@@ -805,13 +862,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 typedef void (*TcKernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams);
-// (MT, NC, TAPS, KC) instantiations: MT*NC in {16..128} columns; 3x3 (9 taps) and 2x2 (4 taps) stages hold one 16-channel
-// chunk, 1x1 stages hold up to four
+// (MT, NC, TAPS, KC) instantiations: MT*NC in {16..128} columns; 3x3 (9 taps), 2x2 (4 taps) and 1-D (3 taps) stages hold one
+// 16-channel chunk, 1x1 stages hold up to four
 static TcKernelFn tc_kernel_for(int MT, int NC, int TAPS, int KC) {
 #define TCK(mt, nc, taps, kc) if (MT == mt && NC == nc && TAPS == taps && KC == kc) return conv_tc_kernel<(mt) * (nc) / 16, mt, taps, kc>;
-#define TCK_ALL(mt, nc) TCK(mt, nc, 9, 1) TCK(mt, nc, 4, 1) TCK(mt, nc, 1, 1) TCK(mt, nc, 1, 2) TCK(mt, nc, 1, 4)
-  TCK_ALL(1, 16) TCK_ALL(1, 32) TCK_ALL(2, 32) TCK_ALL(1, 48) TCK_ALL(2, 48) TCK_ALL(1, 64) TCK_ALL(2, 64) TCK_ALL(1, 96)
-  TCK(1, 128, 1, 1) TCK(1, 128, 1, 2) TCK(1, 128, 1, 4) TCK(1, 128, 4, 1)
+#define TCK_ALL(mt, nc) TCK(mt, nc, 9, 1) TCK(mt, nc, 4, 1) TCK(mt, nc, 3, 1) TCK(mt, nc, 1, 1) TCK(mt, nc, 1, 2) TCK(mt, nc, 1, 4)
+  TCK_ALL(1, 16) TCK_ALL(1, 32) TCK_ALL(2, 32) TCK_ALL(1, 48) TCK_ALL(2, 48) TCK_ALL(1, 64) TCK_ALL(2, 64) TCK_ALL(1, 80) TCK_ALL(1, 96)
+  TCK_ALL(1, 128)
 #undef TCK_ALL
 #undef TCK
   return nullptr;
@@ -861,9 +918,26 @@ static CUresult encode_nd(CUtensorMap* tm, const void* gptr, int rank, const uin
                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 }
 
-cudaError_t tc_conv_launch(TcConvPlan* pl, int nimg, cudaStream_t st);
+// geometry of a layer kind
+struct TcGeom {
+  int ntaps, tapw, nrows;          // taps, taps per stencil row, stencil rows
+  int halo_before, halo_after;     // rows of the contiguous window before / after the tile
+  int row_step;                    // tensor rows between two stencil rows
+  bool two_d;
+};
+static bool tc_geom(int kind, int W, int dil, TcGeom* g) {
+  const int Wp = W + 2;
+  switch (kind) {
+    case TC_KIND_3x3: *g = {9, 3, 3, Wp + 1, Wp + 1, Wp, true}; return true;
+    case TC_KIND_1x1: *g = {1, 1, 1, 0, 0, 0, true}; return true;
+    case TC_KIND_2x2: *g = {4, 2, 2, 0, Wp + 1, Wp, true}; return true;
+    case TC_KIND_LIN3: *g = {3, 1, 3, 0, 2 * dil, dil, false}; return dil >= 1;
+    case TC_KIND_LIN1: *g = {1, 1, 1, 0, 0, 0, false}; return true;
+  }
+  return false;
+}
 
-// One feasible tiling of a layer: N-split, accumulators per CTA, chunks per stage, ring depth.
+// One feasible tiling of a layer: N-split, accumulators per CTA, chunks per stage, ring depth, window form.
 struct TcCand {
   TcParams p;
   int ns, MT, NC, KC;
@@ -871,97 +945,114 @@ struct TcCand {
   double cost;      // model estimate (clocks per CTA), used to rank and as the choice when auto-tuning is off
 };
 
-static std::vector<TcCand> tc_enumerate(int Cin, int Cout, int ks, bool has_res, int H, int W, int max_img, int num_sms, bool gather) {
+static std::vector<TcCand> tc_enumerate(int kind, int Cin, int Cout, bool has_res, int H, int W, int dil, long long Mmax, int num_sms, bool gather) {
   std::vector<TcCand> out;
-  const int Hp = H + 2, Wp = W + 2, ntaps = ks * ks, nchunk = Cin / 16;
-  const int halo = ks == 3 ? Wp + 1 : 0;
-  const int halo_after = ks == 1 ? 0 : Wp + 1;
-  const long long Mmax = (long long)max_img * Hp * Wp;
+  TcGeom g;
+  if (!tc_geom(kind, W, dil, &g)) return out;
+  const int Hp = H + 2, Wp = W + 2, ntaps = g.ntaps, nchunk = Cin / 16;
   const size_t smem_total = 227 * 1024 - 2048;                    // dynamic shared memory budget minus alignment slack + barriers
-  (void)H; (void)W;
-  for (int ns = 1; ns <= 8; ns *= 2) {
-    if (Cout % ns) continue;
-    const int NC = Cout / ns;
-    if (NC % 16 || NC > 128) continue;
+  static const int NCS[] = {128, 96, 80, 64, 48, 32, 16};
+  for (int NC : NCS) {
+    if (Cout % NC) continue;
+    const int ns = Cout / NC;
+    if (ns > 8 && NC < 64) continue;                              // many thin slices re-read the activations ns times: never competitive
     for (int MT = 2; MT >= 1; --MT) {
-      for (int KC = (ks == 1 ? 4 : 1); KC >= 1; KC >>= 1) {
+      for (int KC = (ntaps == 1 ? 4 : 1); KC >= 1; KC >>= 1) {
         if (nchunk % KC) continue;
         if (!tc_kernel_for(MT, NC, ntaps, KC)) continue;
-        TcParams p{};
-        p.nchunk = nchunk; p.Cout = Cout; p.halo = halo;
-        p.nstage = nchunk / KC;
-        // accumulation-length bound: at most MAX_ACC_STEPS hi*hi MMA steps per TMEM accumulator before a drain
-        // (measured: 18 steps -> heatmap error 7e-5 and the keypoint gate fails, 6 -> 2.3e-5)
-        const int max_steps = env_int("PE_TC_MAXSTEPS", MAX_ACC_STEPS);
-        p.rpg = std::max(1, max_steps / (KSTEPS * ks));
-        const int rows_total = nchunk * ks;                         // stencil rows per tile
-        p.ndrain = (rows_total + p.rpg - 1) / p.rpg;
-        int R = 128 * MT + halo + halo_after;
-        p.gather = 0; p.cpp = 0;
-        if (gather) {
-          // the window is made of whole pairs of S image rows (boxes of 2*Wp rows): up to 2*Wp - 1 rows before the tile
-          if (ks != 2 || nchunk % 4 || (Hp & 1) || 2 * Wp > 256) continue;
-          p.gather = 1; p.cpp = nchunk / 4;
-          const int nboxmax = (2 * Wp - 1 + R + 2 * Wp - 1) / (2 * Wp);
-          R = nboxmax * 2 * Wp;
-        }
-        p.nbA = (R + 255) / 256;
-        p.Rpad = ((R + 8 * p.nbA - 1) / (8 * p.nbA)) * (8 * p.nbA);
-        p.RB = p.Rpad / p.nbA;
-        p.a_bytes = (uint32_t)p.Rpad * CHB;
-        const size_t b_chunk = (size_t)ntaps * NC * CHB;
-        p.stage_bytes = (uint32_t)(KC * (p.a_bytes + b_chunk));
-        if (p.stage_bytes % (8 * CHB)) continue;                    // stage bases keep the swizzle phase (pattern period: 8 rows)
-        // ring depth: as many stages as fit, at most 4.  Store-staging buffers per epilogue warp: two alternate for the output
-        // stores; residual layers land the residual chunks of the next tile in them (one buffer per 16-column group of the
-        // warp, so three or four when the warp owns that many groups).  Shrink the staging before giving up a third stage.
-        const int ngh = (MT * NC / 16 + EPI_PARTS - 1) / EPI_PARTS;
-        int cols = 32;
-        while (cols < ((MT * NC / 16 <= 6) ? 5 : 4) * MT * NC) cols <<= 1;
-        p.tmem_cols = cols;
-        p.tiles_m = (int)((Mmax + 128LL * MT - 1) / (128LL * MT));
-        p.total_work = p.tiles_m * ns;
-        const int ctas = p.total_work < num_sms ? p.total_work : num_sms;
-        const double items = (double)((p.total_work + ctas - 1) / ctas);
-        // clocks per work item.  Measured (tools/mma_bench.cu, issue_bench.cu): one M=128 SS tcgen05.mma occupies the
-        // operand-fetch path for max(N/2, 32 + N/4) clocks (below N=128 the 4 KB A-operand read paces it); TMA ingest is
-        // ~48 B/clk/SM from L2 with a few loads in flight (tools/tma_bench.cu); each stage costs the issuers ~300 clocks of
-        // barrier hand-off that overlaps only partly
-        const double n_mma = 3.0 * KSTEPS * ntaps * nchunk * MT;
-        const double mma = n_mma * std::max(NC / 2.0, 32.0 + NC / 4.0) + 300.0 * p.nstage;
-        const double bytes = (double)nchunk * (p.a_bytes + (double)b_chunk);
-        const double epi = (double)MT * (NC / 16) * 130.0 * (1 + p.ndrain * 0.5) + 1500.0;
-        // Ring depth S (2..4) against store-staging buffers per epilogue warp (1..4; residual layers land the residual chunks
-        // of a tile in them, one buffer per 16-column group of the warp): both want the same shared memory.  Measured: a
-        // store takes ~1000 clocks to read its source, so one staging buffer stalls every group of the final phase, and two
-        // stages stall the MMA warps -- which hurts more depends on the layer, so both trade-offs become candidates.
-        const int want = has_res ? std::max(3, std::min(ngh, 4)) : 3;
-        int lastS = -1, lastN = -1;
-        auto fit = [&](int nstg_) {
-          const size_t staging = (size_t)EPI_WARPS * nstg_ * 32 * CHB;
-          if (staging + 2 * (size_t)p.stage_bytes > smem_total) return 0;
-          return (int)std::min<size_t>(4, (smem_total - staging) / p.stage_bytes);
-        };
-        for (int variant = 0; variant < 2; ++variant) {
-          int S = 0, nstg = 0;
-          if (variant == 0) {                               // a third stage first, then as much staging as still fits
-            const int target = std::min(fit(1), 3);
-            for (int t = want; t >= 1 && !nstg; --t)
-              if (fit(t) >= target && target >= 2) nstg = t;
-            S = nstg ? fit(nstg) : 0;
-          } else {                                          // full staging first, the ring gets the rest
-            nstg = want; S = fit(want);
+        // window forms: contiguous always; one run per stencil row as well when the rows are far apart
+        const int nform = (!gather && g.nrows > 1 && g.row_step > 64) ? 2 : 1;
+        for (int form = 0; form < nform; ++form) {
+          TcParams p{};
+          p.nchunk = nchunk; p.Cout = Cout; p.halo = g.halo_before;
+          p.nstage = nchunk / KC;
+          // accumulation-length bound: at most MAX_ACC_STEPS hi*hi MMA steps per TMEM accumulator before a drain
+          // (measured: 18 steps -> heatmap error 7e-5 and the keypoint gate fails, 6 -> 2.3e-5)
+          const int max_steps = env_int("PE_TC_MAXSTEPS", MAX_ACC_STEPS);
+          p.rpg = std::max(1, max_steps / (KSTEPS * g.tapw));
+          const int rows_total = nchunk * g.nrows;                  // stencil rows per tile
+          p.ndrain = (rows_total + p.rpg - 1) / p.rpg;
+          p.gather = 0; p.cpp = 0;
+          if (form == 0) {
+            int R = 128 * MT + g.halo_before + g.halo_after;
+            if (gather) {
+              // the window is made of whole pairs of S image rows (boxes of 2*Wp rows): up to 2*Wp - 1 rows before the tile
+              if (kind != TC_KIND_2x2 || nchunk % 4 || (Hp & 1) || 2 * Wp > 256) continue;
+              p.gather = 1; p.cpp = nchunk / 4;
+              const int nboxmax = (2 * Wp - 1 + R + 2 * Wp - 1) / (2 * Wp);
+              R = nboxmax * 2 * Wp;
+            }
+            p.nbA = (R + 255) / 256;
+            p.Rpad = ((R + 8 * p.nbA - 1) / (8 * p.nbA)) * (8 * p.nbA);
+            p.RB = p.Rpad / p.nbA;
+            p.nseg = 1; p.nb_seg = p.nbA; p.Rseg = p.Rpad; p.seg_step = 0;
+            p.row_step = g.row_step;
+          } else {
+            const int R1 = 128 * MT + g.tapw - 1;                   // rows one stencil row needs
+            p.nseg = g.nrows; p.seg_step = g.row_step;
+            p.nb_seg = (R1 + 255) / 256;
+            p.Rseg = ((R1 + 8 * p.nb_seg - 1) / (8 * p.nb_seg)) * (8 * p.nb_seg);
+            p.RB = p.Rseg / p.nb_seg;
+            p.nbA = p.nseg * p.nb_seg;
+            p.Rpad = p.nseg * p.Rseg;
+            p.row_step = p.Rseg;
           }
-          if (S < 2 || nstg < 1 || (S == lastS && nstg == lastN)) continue;
-          lastS = S; lastN = nstg;
-          p.S = S; p.nstg = nstg;
-          const double item = std::max(std::max(mma, bytes / 40.0), epi) + (S < 3 ? 0.15 * mma : 0.0) + (nstg < 2 ? 0.1 * epi : 0.0)
-                              + ((has_res && MT * NC / 16 > 6) ? 0.5 * epi : 0.0);
-          TcCand c;
-          c.p = p; c.ns = ns; c.MT = MT; c.NC = NC; c.KC = KC;
-          c.smem = (size_t)S * p.stage_bytes + (size_t)EPI_WARPS * nstg * 32 * CHB + 2048;
-          c.cost = items * item + 4000.0;
-          out.push_back(c);
+          p.a_bytes = (uint32_t)p.Rpad * CHB;
+          const size_t b_chunk = (size_t)ntaps * NC * CHB;
+          p.stage_bytes = (uint32_t)(KC * (p.a_bytes + b_chunk));
+          if (p.stage_bytes % (8 * CHB)) continue;                    // stage bases keep the swizzle phase (pattern period: 8 rows)
+          // ring depth: as many stages as fit, at most 4.  Store-staging buffers per epilogue warp: two alternate for the output
+          // stores; residual layers land the residual chunks of the next tile in them (one buffer per 16-column group of the
+          // warp, so three or four when the warp owns that many groups).  Shrink the staging before giving up a third stage.
+          const int ngh = (MT * NC / 16 + EPI_PARTS - 1) / EPI_PARTS;
+          int cols = 32;
+          while (cols < ((MT * NC / 16 <= 6) ? 5 : 4) * MT * NC) cols <<= 1;
+          if (cols > 512) continue;
+          p.tmem_cols = cols;
+          p.tiles_m = (int)((Mmax + 128LL * MT - 1) / (128LL * MT));
+          p.total_work = p.tiles_m * ns;
+          const int ctas = p.total_work < num_sms ? p.total_work : num_sms;
+          const double items = (double)((p.total_work + ctas - 1) / ctas);
+          // clocks per work item.  Measured (tools/mma_bench.cu, issue_bench.cu): one M=128 SS tcgen05.mma occupies the
+          // operand-fetch path for max(N/2, 32 + N/4) clocks (below N=128 the 4 KB A-operand read paces it); TMA ingest is
+          // ~48 B/clk/SM from L2 with a few loads in flight (tools/tma_bench.cu); each stage costs the issuers ~300 clocks of
+          // barrier hand-off that overlaps only partly
+          const double n_mma = 3.0 * KSTEPS * ntaps * nchunk * MT;
+          const double mma = n_mma * std::max(NC / 2.0, 32.0 + NC / 4.0) + 300.0 * p.nstage;
+          const double bytes = (double)nchunk * (p.a_bytes + (double)b_chunk);
+          const double epi = (double)MT * (NC / 16) * 130.0 * (1 + p.ndrain * 0.5) + 1500.0;
+          // Ring depth S (2..4) against store-staging buffers per epilogue warp (1..4; residual layers land the residual chunks
+          // of a tile in them, one buffer per 16-column group of the warp): both want the same shared memory.  Measured: a
+          // store takes ~1000 clocks to read its source, so one staging buffer stalls every group of the final phase, and two
+          // stages stall the MMA warps -- which hurts more depends on the layer, so both trade-offs become candidates.
+          const int want = has_res ? std::max(3, std::min(ngh, 4)) : 3;
+          int lastS = -1, lastN = -1;
+          auto fit = [&](int nstg_) {
+            const size_t staging = (size_t)EPI_WARPS * nstg_ * 32 * CHB;
+            if (staging + 2 * (size_t)p.stage_bytes > smem_total) return 0;
+            return (int)std::min<size_t>(4, (smem_total - staging) / p.stage_bytes);
+          };
+          for (int variant = 0; variant < 2; ++variant) {
+            int S = 0, nstg = 0;
+            if (variant == 0) {                               // a third stage first, then as much staging as still fits
+              const int target = std::min(fit(1), 3);
+              for (int t = want; t >= 1 && !nstg; --t)
+                if (fit(t) >= target && target >= 2) nstg = t;
+              S = nstg ? fit(nstg) : 0;
+            } else {                                          // full staging first, the ring gets the rest
+              nstg = want; S = fit(want);
+            }
+            if (S < 2 || nstg < 1 || (S == lastS && nstg == lastN)) continue;
+            lastS = S; lastN = nstg;
+            p.S = S; p.nstg = nstg;
+            const double item = std::max(std::max(mma, bytes / 40.0), epi) + (S < 3 ? 0.15 * mma : 0.0) + (nstg < 2 ? 0.1 * epi : 0.0)
+                                + ((has_res && MT * NC / 16 > 6) ? 0.5 * epi : 0.0);
+            TcCand c;
+            c.p = p; c.ns = ns; c.MT = MT; c.NC = NC; c.KC = KC;
+            c.smem = (size_t)S * p.stage_bytes + (size_t)EPI_WARPS * nstg * 32 * CHB + 2048;
+            c.cost = items * item + 4000.0;
+            out.push_back(c);
+          }
         }
       }
     }
@@ -970,30 +1061,34 @@ static std::vector<TcCand> tc_enumerate(int Cin, int Cout, int ks, bool has_res,
 }
 
 // tensor maps + kernel attributes of one candidate
-static cudaError_t tc_build(TcConvPlan* pl, const TcCand& c, const float* in, float* outp, const float* res, const float* wtc,
-                            const float* bias, int Cin, int Cout, int ks, int relu, int H, int W, int max_img, int num_sms,
-                            const float* gather_src) {
-  const int Hp = H + 2, Wp = W + 2, ntaps = ks * ks, nchunk = Cin / 16;
-  const long long Mmax = (long long)max_img * Hp * Wp;
+static cudaError_t tc_build(TcConvPlan* pl, const TcCand& c, const TcConvDesc& d, int num_sms) {
+  TcGeom g;
+  tc_geom(d.kind, d.W, d.dil, &g);
+  const int Hp = d.H + 2, Wp = d.W + 2, ntaps = g.ntaps, nchunk = d.Cin / 16, Cout = d.Cout;
+  const long long Mmax = d.max_rows;
   pl->p = c.p;
   // weight blob = [per-channel scale 2^-k: Cout floats padded to 64][inverse 2^k: same][packed operand]
-  const float* wpack = wtc + 2 * (((Cout + 63) / 64) * 64);
+  const float* wpack = d.wtc + 2 * (((Cout + 63) / 64) * 64);
   pl->p.scale_pad = ((Cout + 63) / 64) * 64;
-  pl->p.res = res; pl->p.bias = bias; pl->p.scale = wtc;
-  pl->p.H = H; pl->p.W = W; pl->p.Hp = Hp; pl->p.Wp = Wp; pl->p.relu = relu;
+  pl->p.res = d.res; pl->p.bias = d.bias; pl->p.scale = d.wtc;
+  pl->p.H = d.H; pl->p.W = d.W; pl->p.Hp = Hp; pl->p.Wp = Wp; pl->p.act = d.act;
+  pl->p.no_border = g.two_d ? 0 : 1;
+  pl->p.in_coff = d.in_coff / 16; pl->p.out_coff = d.out_coff / 16; pl->p.res_coff = d.res_coff / 16;
+  pl->p.res_rowF = ps_row_floats(d.res ? d.res_total : d.out_total);
+  pl->p.res_row_off = d.res_row_off; pl->p.res_post = d.res_post;
   {
-    auto magic = [](uint32_t d, uint32_t& mul, uint32_t& sh) {
+    auto magic = [](uint32_t dd, uint32_t& mul, uint32_t& sh) {
       uint32_t l = 0;
-      while ((1u << l) < d) ++l;                       // ceil(log2 d)
+      while ((1u << l) < dd) ++l;                      // ceil(log2 d)
       sh = 31 + l;
-      mul = (uint32_t)((((uint64_t)1 << sh) + d - 1) / d);
+      mul = (uint32_t)((((uint64_t)1 << sh) + dd - 1) / dd);
     };
     magic((uint32_t)(Hp * Wp), pl->p.div_hpwp_mul, pl->p.div_hpwp_sh);
     magic((uint32_t)Wp, pl->p.div_wp_mul, pl->p.div_wp_sh);
   }
   pl->p.mma_wait_ns = env_int("PE_TC_MMA_WAIT_NS", 0);
   pl->p.poll_ns = env_int("PE_TC_POLL_NS", -1000);   // < 0: hardware-suspended waits with this time hint (ns); measured +1 % under the power cap
-  pl->rows_per_img = Hp * Wp;
+  pl->rows_per_img = g.two_d ? Hp * Wp : 1;
   pl->smem = c.smem;
   pl->ns = c.ns; pl->MT = c.MT; pl->NC = c.NC; pl->TAPS = ntaps; pl->KC = c.KC;
   pl->num_sms = num_sms;
@@ -1002,16 +1097,18 @@ static cudaError_t tc_build(TcConvPlan* pl, const TcCand& c, const float* in, fl
   if (c.p.gather) {
     // the ORIGINAL input of the stride-2 convolution: [max_img][2H+2][2W+2][C] PS rows, read with element strides (2, 2);
     // with a traversal stride the box extent is given in tensor elements: 2*Wp columns -> Wp loaded, 4 rows -> 2 loaded
-    const int Ci = Cin / 4, Hpi = 2 * H + 2, Wpi = 2 * W + 2;
-    const uint64_t rowb = (uint64_t)ps_row_floats(Ci) * 4;
-    const uint64_t dims[4] = {(uint64_t)ps_row_floats(Ci), (uint64_t)Wpi, (uint64_t)Hpi, (uint64_t)max_img};
+    const int Hpi = 2 * d.H + 2, Wpi = 2 * d.W + 2;
+    const long long nimg = Mmax / ((long long)Hp * Wp);
+    const uint64_t rowb = (uint64_t)ps_row_floats(d.gather_total) * 4;
+    const uint64_t dims[4] = {(uint64_t)ps_row_floats(d.gather_total), (uint64_t)Wpi, (uint64_t)Hpi, (uint64_t)nimg};
     const uint64_t str[3] = {rowb, rowb * Wpi, rowb * Wpi * Hpi};
     const uint32_t box[4] = {cf, (uint32_t)(2 * Wp), 4, 1}, es[4] = {1, 2, 2, 1};
-    r1 = encode_nd(&pl->tmA, gather_src, 4, dims, str, box, es);
+    pl->p.in_coff = d.gather_coff / 16;
+    r1 = encode_nd(&pl->tmA, d.gather_src, 4, dims, str, box, es);
   } else {
-    const uint64_t dims[2] = {(uint64_t)ps_row_floats(Cin), (uint64_t)Mmax}, str[1] = {(uint64_t)ps_row_floats(Cin) * 4};
+    const uint64_t dims[2] = {(uint64_t)ps_row_floats(d.in_total), (uint64_t)(Mmax + (g.two_d ? 0 : g.halo_after))}, str[1] = {(uint64_t)ps_row_floats(d.in_total) * 4};
     const uint32_t box[2] = {cf, (uint32_t)c.p.RB};
-    r1 = encode_nd(&pl->tmA, in, 2, dims, str, box);
+    r1 = encode_nd(&pl->tmA, d.in, 2, dims, str, box);
   }
   {
     // weights [tap][chunk*Cout + n][CHB bytes] as a 3-D tensor: one box = all taps of NC channels of one chunk
@@ -1020,17 +1117,19 @@ static cudaError_t tc_build(TcConvPlan* pl, const TcCand& c, const float* in, fl
     r2 = encode_nd(&pl->tmW, wpack, 3, dims, str, box);
   }
   {
-    const uint64_t dims[2] = {(uint64_t)ps_row_floats(Cout), (uint64_t)Mmax}, str[1] = {(uint64_t)ps_row_floats(Cout) * 4};
+    const uint64_t dims[2] = {(uint64_t)ps_row_floats(d.out_total), (uint64_t)Mmax}, str[1] = {(uint64_t)ps_row_floats(d.out_total) * 4};
     const uint32_t box[2] = {cf, 32};
-    r3 = encode_nd(&pl->tmO, outp, 2, dims, str, box);
+    r3 = encode_nd(&pl->tmO, d.out, 2, dims, str, box);
     pl->tmR = pl->tmO;
-    if (res) {
-      const CUresult r4 = encode_nd(&pl->tmR, res, 2, dims, str, box);
+    if (d.res) {
+      const uint64_t rdims[2] = {(uint64_t)ps_row_floats(d.res_total), (uint64_t)(Mmax + (d.res_row_off > 0 ? d.res_row_off : 0))};
+      const uint64_t rstr[1] = {(uint64_t)ps_row_floats(d.res_total) * 4};
+      const CUresult r4 = encode_nd(&pl->tmR, d.res, 2, rdims, rstr, box);
       if (r4 != CUDA_SUCCESS) r3 = r4;
     }
   }
   if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS || r3 != CUDA_SUCCESS) {
-    fprintf(stderr, "conv_tc: cuTensorMapEncodeTiled failed (%d, %d, %d) Cin=%d Cout=%d RB=%d NC=%d\n", (int)r1, (int)r2, (int)r3, Cin, Cout, c.p.RB, c.NC);
+    fprintf(stderr, "conv_tc: cuTensorMapEncodeTiled failed (%d, %d, %d) kind=%d Cin=%d Cout=%d RB=%d NC=%d\n", (int)r1, (int)r2, (int)r3, d.kind, d.Cin, Cout, c.p.RB, c.NC);
     return cudaErrorInvalidValue;
   }
   pl->kernel = tc_kernel_for(c.MT, c.NC, ntaps, c.KC);
@@ -1038,44 +1137,50 @@ static cudaError_t tc_build(TcConvPlan* pl, const TcCand& c, const float* in, fl
 }
 
 // Tiling choice.  The candidates compute bit-identical results (the accumulation order over K does not depend on the
-// N-split, the tile height or the stage size), so the choice is purely a speed matter and it is MEASURED: at model creation
-// every candidate of a not-yet-seen layer shape runs on the layer's own buffers and the fastest is kept (per process cache
-// keyed by shape).  PE_TC_AUTOTUNE=0 falls back to the cost model; PE_TC_MT / PE_TC_NS / PE_TC_KC pin a tiling.
+// N-split, the tile height, the stage size or the window form), so the choice is purely a speed matter and it is MEASURED:
+// at plan creation every candidate of a not-yet-seen layer shape runs on the layer's own buffers and the fastest is kept
+// (per process cache keyed by shape).  PE_TC_AUTOTUNE=0 falls back to the cost model; PE_TC_MT / PE_TC_NS / PE_TC_KC pin a tiling.
 #include <map>
 #include <tuple>
 #include <algorithm>
-typedef std::tuple<int, int, int, int, int, int, int> TcShapeKey;   // Cin, Cout, ks, H, W, residual, max_img
-static std::map<TcShapeKey, std::tuple<int, int, int, int>> g_tc_choice;  // -> ns, MT, KC, S*8 + nstg
+typedef std::tuple<int, int, int, int, int, int, long long, int> TcShapeKey;   // kind*1000+dil, Cin, Cout, H, W, residual/gather/act flags, rows, slice flag
+static std::map<TcShapeKey, std::tuple<int, int, int, int>>& tc_choices() {   // -> ns, MT, KC, (S*8 + nstg)*2 + segmented
+  static auto* m = new std::map<TcShapeKey, std::tuple<int, int, int, int>>();
+  return *m;
+}
+static std::tuple<int, int, int, int> tc_cand_id(const TcCand& c) { return std::make_tuple(c.ns, c.MT, c.KC, (c.p.S * 8 + c.p.nstg) * 2 + (c.p.nseg > 1 ? 1 : 0)); }
 
-cudaError_t tc_conv_plan_create(TcConvPlan** out, const float* in, float* outp, const float* res, const float* wtc,
-                                const float* bias, int Cin, int Cout, int ks, int relu, int H, int W, int max_img,
-                                const float* gather_src) {
+cudaError_t tc_conv_plan_create_ex(TcConvPlan** out, const TcConvDesc* dp) {
+  const TcConvDesc& d = *dp;
   if (env_int("PE_TC_DISABLE", 0)) return cudaErrorNotSupported;
-  if (gather_src && (ks != 2 || !env_int("PE_TC_GATHER", 1))) return cudaErrorNotSupported;
-  // ks = 3: 3x3 pad 1;  ks = 1: 1x1;  ks = 2: 2x2 stencil with taps at (+0,+1) rows/cols (no pad) -- the form a
-  // stride-2 3x3 convolution takes over the space-to-depth repack of its input (kernels_simt.cu s2d_kernel)
-  if ((ks != 1 && ks != 2 && ks != 3) || Cin % 16 || Cout % 16 || Cout > 512) return cudaErrorNotSupported;
-  if ((long long)max_img * (H + 2) * (W + 2) + 1024 >= (1LL << 31)) return cudaErrorNotSupported;   // TMA row coordinates are int32
+  if (d.gather_src && (d.kind != TC_KIND_2x2 || !env_int("PE_TC_GATHER", 1))) return cudaErrorNotSupported;
+  TcGeom g;
+  if (!tc_geom(d.kind, d.W, d.dil, &g)) return cudaErrorNotSupported;
+  if (d.Cin % 16 || d.Cout % 16 || d.Cout > 4096 || d.in_coff % 16 || d.out_coff % 16 || d.res_coff % 16 || d.in_total % 16 || d.out_total % 16)
+    return cudaErrorNotSupported;
+  if (d.max_rows + 4096 >= (1LL << 31)) return cudaErrorNotSupported;   // TMA row coordinates are int32
   int num_sms = 148;
   {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  std::vector<TcCand> cands = tc_enumerate(Cin, Cout, ks, res != nullptr, H, W, max_img, num_sms, gather_src != nullptr);
-  const int force_mt = env_int("PE_TC_MT", 0), force_ns = env_int("PE_TC_NS", 0), force_kc = env_int("PE_TC_KC", 0);
+  std::vector<TcCand> cands = tc_enumerate(d.kind, d.Cin, d.Cout, d.res != nullptr, d.H, d.W, d.dil, d.max_rows, num_sms, d.gather_src != nullptr);
+  const int force_mt = env_int("PE_TC_MT", 0), force_ns = env_int("PE_TC_NS", 0), force_kc = env_int("PE_TC_KC", 0), force_seg = env_int("PE_TC_SEG", -1);
   cands.erase(std::remove_if(cands.begin(), cands.end(), [&](const TcCand& c) {
-                return (force_mt && c.MT != force_mt) || (force_ns && c.ns != force_ns) || (force_kc && c.KC != force_kc); }),
+                return (force_mt && c.MT != force_mt) || (force_ns && c.ns != force_ns) || (force_kc && c.KC != force_kc) ||
+                       (force_seg >= 0 && (c.p.nseg > 1) != (force_seg != 0)); }),
               cands.end());
   if (cands.empty()) return cudaErrorNotSupported;
   std::sort(cands.begin(), cands.end(), [](const TcCand& a, const TcCand& b) { return a.cost < b.cost; });
-  const TcShapeKey key(Cin, Cout, ks, H, W, (res ? 1 : 0) + (gather_src ? 2 : 0), max_img);
-  const bool pinned = force_mt || force_ns || force_kc;
+  const TcShapeKey key(d.kind * 1000 + d.dil, d.Cin, d.Cout, d.H, d.W, (d.res ? 1 : 0) + (d.gather_src ? 2 : 0) + 4 * d.act + 16 * d.res_post, d.max_rows,
+                       (d.in_total != d.Cin) + 2 * (d.out_total != d.Cout));
+  const bool pinned = force_mt || force_ns || force_kc || force_seg >= 0;
   size_t pick = 0;
-  auto hit = g_tc_choice.find(key);
-  if (!pinned && hit != g_tc_choice.end()) {
+  auto hit = tc_choices().find(key);
+  if (!pinned && hit != tc_choices().end()) {
     for (size_t i = 0; i < cands.size(); ++i)
-      if (std::make_tuple(cands[i].ns, cands[i].MT, cands[i].KC, cands[i].p.S * 8 + cands[i].p.nstg) == hit->second) pick = i;
+      if (tc_cand_id(cands[i]) == hit->second) pick = i;
   } else if (!pinned && env_int("PE_TC_AUTOTUNE", 1) && cands.size() > 1) {
     cudaStream_t ts;
     cudaEvent_t e0, e1;
@@ -1085,14 +1190,15 @@ cudaError_t tc_conv_plan_create(TcConvPlan** out, const float* in, float* outp, 
     std::vector<TcConvPlan> tmp(ntry);
     std::vector<float> ms_min(ntry, 1e30f);
     std::vector<char> ok(ntry, 0);
-    for (size_t i = 0; i < ntry; ++i)
-      ok[i] = tc_build(&tmp[i], cands[i], in, outp, res, wtc, bias, Cin, Cout, ks, relu, H, W, max_img, num_sms, gather_src) == cudaSuccess;
+    for (size_t i = 0; i < ntry; ++i) ok[i] = tc_build(&tmp[i], cands[i], d, num_sms) == cudaSuccess;
     // round-robin over the candidates (clock / cache drift hits all alike), minimum of the rounds; round 0 warms up
+    unsigned int* const saved_flag = pe_range_flag();
+    pe_range_flag() = nullptr;                            // candidate runs read uninitialised buffers
     for (int rep = 0; rep < 6; ++rep) {
       for (size_t i = 0; i < ntry; ++i) {
         if (!ok[i]) continue;
         cudaEventRecord(e0, ts);
-        tc_conv_launch(&tmp[i], max_img, ts);
+        tc_conv_launch_rows(&tmp[i], d.max_rows, ts);
         cudaEventRecord(e1, ts);
         if (cudaEventSynchronize(e1) != cudaSuccess) { ok[i] = 0; continue; }
         float ms = 0.f;
@@ -1100,22 +1206,23 @@ cudaError_t tc_conv_plan_create(TcConvPlan** out, const float* in, float* outp, 
         if (rep > 0) ms_min[i] = std::min(ms_min[i], ms);
       }
     }
+    pe_range_flag() = saved_flag;
     float best_ms = 1e30f;
     for (size_t i = 0; i < ntry; ++i) {
       if (!ok[i]) continue;
       if (env_int("PE_TC_VERBOSE", 0) > 1)
-        fprintf(stderr, "conv_tc tune: Cin=%d Cout=%d ks=%d %dx%d res=%d gather=%d  NS=%d MT=%d KC=%d S=%d nstg=%d -> %.3f ms (model %.0f)\n", Cin, Cout, ks, H, W,
-                res ? 1 : 0, gather_src ? 1 : 0, cands[i].ns, cands[i].MT, cands[i].KC, cands[i].p.S, cands[i].p.nstg, ms_min[i], cands[i].cost);
+        fprintf(stderr, "conv_tc tune: kind=%d Cin=%d Cout=%d %dx%d dil=%d res=%d gather=%d  NS=%d MT=%d KC=%d S=%d nstg=%d seg=%d -> %.3f ms (model %.0f)\n", d.kind, d.Cin, d.Cout,
+                d.H, d.W, d.dil, d.res ? 1 : 0, d.gather_src ? 1 : 0, cands[i].ns, cands[i].MT, cands[i].KC, cands[i].p.S, cands[i].p.nstg, cands[i].p.nseg, ms_min[i], cands[i].cost);
       if (ms_min[i] < best_ms) { best_ms = ms_min[i]; pick = i; }
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     cudaStreamDestroy(ts);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    g_tc_choice[key] = std::make_tuple(cands[pick].ns, cands[pick].MT, cands[pick].KC, cands[pick].p.S * 8 + cands[pick].p.nstg);
+    tc_choices()[key] = tc_cand_id(cands[pick]);
   }
   TcConvPlan* pl = new TcConvPlan();
-  cudaError_t e = tc_build(pl, cands[pick], in, outp, res, wtc, bias, Cin, Cout, ks, relu, H, W, max_img, num_sms, gather_src);
+  cudaError_t e = tc_build(pl, cands[pick], d, num_sms);
   if (e != cudaSuccess) { delete pl; return e; }
   pl->p.prof = nullptr;
 #if PE_TC_PROFILE
@@ -1123,16 +1230,34 @@ cudaError_t tc_conv_plan_create(TcConvPlan** out, const float* in, float* outp, 
 #endif
   const TcCand& c = cands[pick];
   if (env_int("PE_TC_VERBOSE", 0))
-    fprintf(stderr, "conv_tc plan: Cin=%d Cout=%d ks=%d %dx%d res=%d  MT=%d NS=%d NC=%d KC=%d S=%d nstg=%d rpg=%d ndrain=%d Rpad=%d RB=%d stage=%u smem=%zu tmem=%d work=%d\n",
-            Cin, Cout, ks, H, W, res ? 1 : 0, c.MT, c.ns, c.NC, c.KC, c.p.S, c.p.nstg, c.p.rpg, c.p.ndrain, c.p.Rpad, c.p.RB, c.p.stage_bytes, c.smem, c.p.tmem_cols,
-            c.p.total_work);
+    fprintf(stderr, "conv_tc plan: kind=%d Cin=%d Cout=%d %dx%d dil=%d res=%d  MT=%d NS=%d NC=%d KC=%d S=%d nstg=%d rpg=%d ndrain=%d Rpad=%d RB=%d nseg=%d stage=%u smem=%zu tmem=%d work=%d\n",
+            d.kind, d.Cin, d.Cout, d.H, d.W, d.dil, d.res ? 1 : 0, c.MT, c.ns, c.NC, c.KC, c.p.S, c.p.nstg, c.p.rpg, c.p.ndrain, c.p.Rpad, c.p.RB, c.p.nseg, c.p.stage_bytes, c.smem,
+            c.p.tmem_cols, c.p.total_work);
   *out = pl;
   return cudaSuccess;
 }
 
+// the round-1 entry point: a whole-tensor 2-D layer (ks = 3: 3x3 pad 1; ks = 1: 1x1; ks = 2: the 2x2 form of a stride-2 3x3 layer)
+cudaError_t tc_conv_plan_create(TcConvPlan** out, const float* in, float* outp, const float* res, const float* wtc,
+                                const float* bias, int Cin, int Cout, int ks, int relu, int H, int W, int max_img,
+                                const float* gather_src) {
+  if (ks != 1 && ks != 2 && ks != 3) return cudaErrorNotSupported;
+  TcConvDesc d{};
+  d.kind = ks == 3 ? TC_KIND_3x3 : (ks == 2 ? TC_KIND_2x2 : TC_KIND_1x1);
+  d.Cin = Cin; d.Cout = Cout; d.act = relu ? 1 : 0; d.dil = 0; d.H = H; d.W = W;
+  d.max_rows = (long long)max_img * (H + 2) * (W + 2);
+  d.in = in; d.in_total = Cin; d.in_coff = 0;
+  d.out = outp; d.out_total = Cout; d.out_coff = 0;
+  d.res = res; d.res_total = Cout; d.res_coff = 0; d.res_row_off = 0; d.res_post = 0;
+  d.wtc = wtc; d.bias = bias;
+  d.gather_src = gather_src; d.gather_total = Cin / 4; d.gather_coff = 0;
+  return tc_conv_plan_create_ex(out, &d);
+}
+
 int tc_plan_candidates(int Cin, int Cout, int ks, int has_res, int H, int W, int max_img, int gather, int32_t* out, int cap) {
-  if ((ks != 1 && ks != 2 && ks != 3) || Cin % 16 || Cout % 16 || Cout > 512 || !out || cap < 0) return -1;
-  const std::vector<TcCand> c = tc_enumerate(Cin, Cout, ks, has_res != 0, H, W, max_img, 148, gather != 0);
+  if ((ks != 1 && ks != 2 && ks != 3) || Cin % 16 || Cout % 16 || Cout > 4096 || !out || cap < 0) return -1;
+  const int kind = ks == 3 ? TC_KIND_3x3 : (ks == 2 ? TC_KIND_2x2 : TC_KIND_1x1);
+  const std::vector<TcCand> c = tc_enumerate(kind, Cin, Cout, has_res != 0, H, W, 0, (long long)max_img * (H + 2) * (W + 2), 148, gather != 0);
   int n = 0;
   for (const TcCand& k : c) {
     if (n >= cap) break;
@@ -1146,10 +1271,12 @@ int tc_plan_candidates(int Cin, int Cout, int ks, int has_res, int H, int W, int
 
 void tc_conv_plan_destroy(TcConvPlan* plan, bool cuda_ok) { if (plan && plan->p.prof && cuda_ok) cudaFree(plan->p.prof); delete plan; }
 
-cudaError_t tc_conv_launch(TcConvPlan* pl, int nimg, cudaStream_t st) {
+cudaError_t tc_conv_launch(TcConvPlan* pl, int nimg, cudaStream_t st) { return tc_conv_launch_rows(pl, (long long)nimg * pl->rows_per_img, st); }
+
+cudaError_t tc_conv_launch_rows(TcConvPlan* pl, long long rows, cudaStream_t st) {
   TcParams p = pl->p;
   p.flag = pe_range_flag();
-  p.M = (long long)nimg * pl->rows_per_img;
+  p.M = rows;
   p.tiles_m = (int)((p.M + 128LL * pl->MT - 1) / (128LL * pl->MT));
   p.total_work = p.tiles_m * pl->ns;
   const unsigned grid = (unsigned)(p.total_work < pl->num_sms ? p.total_work : pl->num_sms);

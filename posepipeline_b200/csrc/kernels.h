@@ -40,6 +40,22 @@ struct TcConvPlan;
 cudaError_t tc_conv_plan_create(TcConvPlan** plan, const float* in, float* out, const float* res, const float* wtc,
                                 const float* bias, int Cin, int Cout, int ks, int relu, int H, int W, int max_img,
                                 const float* gather_src = nullptr);
+// General form: any layer kind, operands may be 16-channel-aligned slices of wider tensors.
+enum { TC_KIND_1x1 = 1, TC_KIND_2x2 = 2, TC_KIND_3x3 = 3, TC_KIND_LIN1 = 11, TC_KIND_LIN3 = 13 };
+struct TcConvDesc {
+  int kind;                // TC_KIND_*: 3x3 pad 1 / 1x1 / 2x2 (stride-2 3x3 in space-to-depth form) over padded 2-D tensors;
+                           // LIN3 = 3 taps at rows m, m+dil, m+2*dil and LIN1 = plain GEMM over flat row matrices (no zero border)
+  int Cin, Cout, act, dil; // act: 0 none, 1 ReLU, 2 SiLU
+  int H, W;                // 2-D kinds: output (= input) height / width
+  long long max_rows;      // rows of the flat output matrix (2-D kinds: max_img * (H+2) * (W+2))
+  const float* in; int in_total, in_coff;           // input tensor, its channel count, first channel of the view
+  float* out; int out_total, out_coff;
+  const float* res; int res_total, res_coff, res_row_off, res_post;   // residual view; row m + res_row_off; added after the activation if res_post
+  const float* wtc; const float* bias;
+  const float* gather_src; int gather_total, gather_coff;             // 2x2 only: TMA-gather the space-to-depth rows from this tensor
+};
+cudaError_t tc_conv_plan_create_ex(TcConvPlan** plan, const TcConvDesc* desc);
+cudaError_t tc_conv_launch_rows(TcConvPlan* plan, long long rows, cudaStream_t st);
 void tc_conv_plan_destroy(TcConvPlan* plan, bool cuda_ok = true);
 int tc_plan_candidates(int Cin, int Cout, int ks, int has_res, int H, int W, int max_img, int gather, int32_t* out, int cap);
 cudaError_t tc_conv_launch(TcConvPlan* plan, int nimg, cudaStream_t st);

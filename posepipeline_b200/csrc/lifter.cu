@@ -7,14 +7,18 @@
 // B200-first restatement: consecutive windows overlap in 242 of 243 frames, so the strided model
 // evaluated on every window equals the DILATED temporal model (same weights; dilation 1,3,9,27,81)
 // evaluated once over the whole edge-padded sequence -- ~16.9 MMAC per frame, a 10.4x cut in work
-// with the same sums of the same products.  Each layer is a tap-shifted GEMM over [time][channels]
-// rows (the same kernel family as the 2-D convolutions); BatchNorm is folded, ReLU / residual
-// (centre-cropped by `dil` rows) are fused in the epilogue.
+// with the same sums of the same products (tests/test_oracle.py::test_videopose3d_strided_equals_dilated_whole_sequence).
+//
+// Every layer but the last is a GEMM over [time][channels] rows and runs on the tcgen05 kernel of conv_tc.cu:
+//   expand_conv  (k3, dilation 1)   48(34) -> 1024   TC_KIND_LIN3  + BN + ReLU
+//   layers_conv[2i]   (k3, dilation 3^(i+1))  1024 -> 1024   TC_KIND_LIN3  + BN + ReLU        (K = 3072, N = 1024)
+//   layers_conv[2i+1] (k1)                    1024 -> 1024   TC_KIND_LIN1  + BN + ReLU, then + residual (rows m + dilation)
+//   shrink (k1, bias) 1024 -> 51: 0.4 % of the MACs, plain fp32 rows out -> the SIMT GEMM
+// BatchNorm is folded into the weights; split-precision operands as everywhere else (3 MMAs per MAC, fp32 accumulate).
+#include <algorithm>
 #include <cstdio>
 #include <string>
 #include <vector>
-
-#include <algorithm>
 
 #include "../../include/poseengine.h"
 #include "engine_internal.h"
@@ -25,11 +29,14 @@ struct pe_lifter {
   pe_engine* e = nullptr;
   int device; cudaStream_t stream;
   int channels;
+  int use_tc = 1;
   float* d_w = nullptr;
-  std::vector<int64_t> off;
+  std::vector<int64_t> off;      // per layer: simt weights, bias, tensor-core packing (or -1)
   float* d_a = nullptr; float* d_b = nullptr; float* d_c = nullptr;  // ping-pong PS activations
   float* d_in = nullptr; float* d_out = nullptr;
   size_t cap_rows = 0;
+  std::vector<TcConvPlan*> plans;   // 9 tensor-core layers x 3 buffer rotations (the residual stream rotates through a, b, c)
+  int64_t launches = 0;
 };
 
 __global__ void lifter_pack_input(const float* __restrict__ kp, int n_frames, int pad, float* __restrict__ out, int T0) {
@@ -47,11 +54,12 @@ __global__ void lifter_pack_input(const float* __restrict__ kp, int n_frames, in
 
 extern "C" int pe_lifter_create(pe_engine* e, const float* weights, int64_t n_floats, const int64_t* offsets, int32_t n_offsets,
                                 int32_t channels, pe_lifter** out) {
-  if (!e || !weights || !offsets || !out || n_offsets != 20 || channels % 48 != 0 && channels % 64 != 0)
-    return pe_set_error(PE_ERR_INVALID, "bad argument to pe_lifter_create (need 20 offsets: 10 layers x (w,b))");
+  if (!e || !weights || !offsets || !out || n_offsets != 30 || channels % 64 != 0)
+    return pe_set_error(PE_ERR_INVALID, "bad argument to pe_lifter_create (need 30 offsets: 10 layers x (w, b, w_tc))");
   if (!pe_handle_alive(PE_H_ENGINE, e)) return pe_set_error(PE_ERR_INVALID, "pe_lifter_create: engine handle is not alive");
   pe_lifter* l = new pe_lifter();
   l->e = e; l->device = e->device; l->stream = e->stream; l->channels = channels;
+  l->use_tc = !(getenv("PE_LIFTER_TC") && atoi(getenv("PE_LIFTER_TC")) == 0);
   l->off.assign(offsets, offsets + n_offsets);
   cudaSetDevice(l->device);
   if (cudaMalloc(&l->d_w, sizeof(float) * n_floats) != cudaSuccess ||
@@ -66,16 +74,60 @@ extern "C" int pe_lifter_create(pe_engine* e, const float* weights, int64_t n_fl
   return PE_OK;
 }
 
+static void lifter_drop_plans(pe_lifter* l, bool cuda_ok) {
+  for (auto* p : l->plans) if (p) tc_conv_plan_destroy(p, cuda_ok);
+  l->plans.clear();
+}
+
 extern "C" int pe_lifter_destroy(pe_lifter* l) {
   if (!l || !pe_handle_release(PE_H_LIFTER, l)) return PE_OK;     // unknown or already destroyed (e.g. with its engine)
   l->e->lifters.erase(std::remove(l->e->lifters.begin(), l->e->lifters.end(), l), l->e->lifters.end());
-  if (pe_cuda_usable(l->device)) {
+  const bool ok = pe_cuda_usable(l->device);
+  if (ok) {
     cudaStreamSynchronize(l->stream);
     cudaFree(l->d_w); cudaFree(l->d_a); cudaFree(l->d_b); cudaFree(l->d_c); cudaFree(l->d_in); cudaFree(l->d_out);
     cudaGetLastError();
   }
+  lifter_drop_plans(l, ok);
   delete l;
   return PE_OK;
+}
+
+// tensor-core plans for the current buffers: layer 0 (expand) + 4 x (dilated k3, k1 + residual).  The residual stream
+// rotates x -> z through the three buffers, so the plans are built for the concrete (in, out, res) pointers of each layer.
+static int lifter_build_plans(pe_lifter* l, long long cap_rows) {
+  lifter_drop_plans(l, true);
+  if (!l->use_tc) return PE_OK;
+  const int C = l->channels;
+  const float* W = l->d_w;
+  l->plans.assign(9, nullptr);
+  auto mk = [&](int idx, int layer, int kind, int cin, int dil, const float* in, float* outp, const float* res, int res_off) -> bool {
+    if (l->off[3 * layer + 2] < 0) return false;
+    TcConvDesc d{};
+    d.kind = kind; d.Cin = cin; d.Cout = C; d.act = 1; d.dil = dil; d.H = 0; d.W = 0;
+    d.max_rows = cap_rows;
+    d.in = in; d.in_total = cin; d.in_coff = 0;
+    d.out = outp; d.out_total = C; d.out_coff = 0;
+    d.res = res; d.res_total = C; d.res_coff = 0; d.res_row_off = res_off; d.res_post = res ? 1 : 0;
+    d.wtc = W + l->off[3 * layer + 2]; d.bias = W + l->off[3 * layer + 1];
+    return tc_conv_plan_create_ex(&l->plans[idx], &d) == cudaSuccess;
+  };
+  bool ok = mk(0, 0, TC_KIND_LIN3, 48, 1, l->d_in, l->d_a, nullptr, 0);
+  float* x = l->d_a; float* y = l->d_b; float* z = l->d_c;
+  int dil = 3;
+  for (int i = 0; i < 4 && ok; ++i) {
+    ok = ok && mk(1 + 2 * i, 1 + 2 * i, TC_KIND_LIN3, C, dil, x, y, nullptr, 0);
+    ok = ok && mk(2 + 2 * i, 2 + 2 * i, TC_KIND_LIN1, C, 0, y, z, x, dil);
+    float* t = x; x = z; z = t;
+    dil *= 3;
+  }
+  if (!ok) { lifter_drop_plans(l, true); cudaGetLastError(); }   // this build / shape is not covered: SIMT GEMMs
+  return PE_OK;
+}
+
+extern "C" int pe_lifter_uses_tensor_cores(pe_lifter* l) {
+  if (!l || !pe_handle_alive(PE_H_LIFTER, l)) return 0;
+  return l->plans.empty() ? 0 : 1;
 }
 
 extern "C" int pe_lift3d(pe_lifter* l, const float* kp2d_norm, int32_t n_frames, float* out3d) {
@@ -85,47 +137,72 @@ extern "C" int pe_lift3d(pe_lifter* l, const float* kp2d_norm, int32_t n_frames,
   cudaStream_t st = l->stream;
   const int pad = 121, C = l->channels;
   const long long T0 = (long long)n_frames + 2 * pad;
+  pe_range_flag() = nullptr;
   if ((size_t)T0 > l->cap_rows) {
     cudaStreamSynchronize(st);
     cudaFree(l->d_a); cudaFree(l->d_b); cudaFree(l->d_c); cudaFree(l->d_in); cudaFree(l->d_out);
     l->d_a = l->d_b = l->d_c = l->d_in = l->d_out = nullptr;
-    const size_t rows = (size_t)T0 + 64;
+    const size_t cap = (((size_t)T0 + 4095) / 4096) * 4096;            // grow in 4096-row steps: plans (and their tuning) are per capacity
+    const size_t rows = cap + 512;
     if (cudaMalloc(&l->d_a, rows * ps_row_floats(C) * sizeof(float)) != cudaSuccess || cudaMalloc(&l->d_b, rows * ps_row_floats(C) * sizeof(float)) != cudaSuccess ||
         cudaMalloc(&l->d_c, rows * ps_row_floats(C) * sizeof(float)) != cudaSuccess || cudaMalloc(&l->d_in, rows * ps_row_floats(48) * sizeof(float)) != cudaSuccess ||
         cudaMalloc(&l->d_out, rows * 51 * sizeof(float)) != cudaSuccess) {
       l->cap_rows = 0;
       return pe_set_error(PE_ERR_CUDA, "pe_lift3d: out of device memory");
     }
-    l->cap_rows = (size_t)T0;
+    cudaMemsetAsync(l->d_a, 0, rows * ps_row_floats(C) * sizeof(float), st);
+    cudaMemsetAsync(l->d_b, 0, rows * ps_row_floats(C) * sizeof(float), st);
+    cudaMemsetAsync(l->d_c, 0, rows * ps_row_floats(C) * sizeof(float), st);
+    cudaMemsetAsync(l->d_in, 0, rows * ps_row_floats(48) * sizeof(float), st);
+    cudaStreamSynchronize(st);
+    l->cap_rows = cap;
+    int rc = lifter_build_plans(l, (long long)cap);
+    if (rc) return rc;
   }
+  const bool tc = !l->plans.empty();
   float* d_kp = l->d_out;  // reuse the output buffer as input staging (n_frames*34 <= rows*51)
   if (cudaMemcpyAsync(d_kp, kp2d_norm, sizeof(float) * 34 * (size_t)n_frames, cudaMemcpyHostToDevice, st) != cudaSuccess)
     return pe_set_error(PE_ERR_CUDA, "pe_lift3d: H2D failed");
   lifter_pack_input<<<(unsigned)((T0 * 48 + 255) / 256), 256, 0, st>>>(d_kp, n_frames, pad, l->d_in, (int)T0);
+  ++l->launches;
   const float* W = l->d_w;
-  auto w = [&](int layer) { return W + l->off[2 * layer]; };
-  auto b = [&](int layer) { return W + l->off[2 * layer + 1]; };
+  auto w = [&](int layer) { return W + l->off[3 * layer]; };
+  auto b = [&](int layer) { return W + l->off[3 * layer + 1]; };
+  auto run_tc = [&](int idx, long long rows) -> bool { ++l->launches; return tc_conv_launch_rows(l->plans[idx], rows, st) == cudaSuccess; };
   // layer 0: expand_conv (k3, dil 1) 48(34)->C + expand_bn + ReLU
   long long T = T0 - 2;
-  launch_conv_linear(l->d_in, l->d_a, nullptr, w(0), b(0), 48, C, 3, 1, 1, T, 0, 0, C, st);
+  if (tc) { if (!run_tc(0, T)) return pe_set_error(PE_ERR_CUDA, "lifter tensor-core layer 0 failed"); }
+  else { launch_conv_linear(l->d_in, l->d_a, nullptr, w(0), b(0), 48, C, 3, 1, 1, T, 0, 0, C, st); ++l->launches; }
   float* x = l->d_a; float* y = l->d_b; float* z = l->d_c;
   int dil = 3;
   for (int i = 0; i < 4; ++i) {
     const long long T2 = T - 2 * dil;
-    // layers_conv[2i] (k3, dilation dil) + layers_bn[2i] + ReLU
-    launch_conv_linear(x, y, nullptr, w(1 + 2 * i), b(1 + 2 * i), C, C, 3, dil, 1, T2, 0, 0, C, st);
-    // layers_conv[2i+1] (1x1) + layers_bn[2i+1] + ReLU, then + res (x centre-cropped by dil rows; negative
-    // res_off selects 'residual added after the ReLU, read at row m + |res_off|')
-    launch_conv_linear(y, z, x, w(2 + 2 * i), b(2 + 2 * i), C, C, 1, 0, 1, T2, /*res_off=*/-dil, 0, C, st);
+    if (tc) {
+      if (!run_tc(1 + 2 * i, T2) || !run_tc(2 + 2 * i, T2)) return pe_set_error(PE_ERR_CUDA, "lifter tensor-core layer failed");
+    } else {
+      // layers_conv[2i] (k3, dilation dil) + layers_bn[2i] + ReLU
+      launch_conv_linear(x, y, nullptr, w(1 + 2 * i), b(1 + 2 * i), C, C, 3, dil, 1, T2, 0, 0, C, st);
+      // layers_conv[2i+1] (1x1) + layers_bn[2i+1] + ReLU, then + res (x centre-cropped by dil rows; negative
+      // res_off selects 'residual added after the ReLU, read at row m + |res_off|')
+      launch_conv_linear(y, z, x, w(2 + 2 * i), b(2 + 2 * i), C, C, 1, 0, 1, T2, /*res_off=*/-dil, 0, C, st);
+      l->launches += 2;
+    }
     float* t = x; x = z; z = t;
     T = T2;
     dil *= 3;
   }
   // shrink: 1x1 C->51 with bias, plain fp32 output rows
   launch_conv_linear(x, l->d_out, nullptr, w(9), b(9), C, 64, 1, 0, 0, T, 0, 1, 51, st);
+  ++l->launches;
   if (T != n_frames) return pe_set_error(PE_ERR_STATE, "lifter geometry error");
   if (cudaMemcpyAsync(out3d, l->d_out, sizeof(float) * 51 * (size_t)n_frames, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
       cudaStreamSynchronize(st) != cudaSuccess)
     return pe_set_error(PE_ERR_CUDA, cudaGetErrorString(cudaGetLastError()));
+  return PE_OK;
+}
+
+extern "C" int pe_lifter_launch_count(pe_lifter* l, int64_t* count) {
+  if (!l || !count || !pe_handle_alive(PE_H_LIFTER, l)) return pe_set_error(PE_ERR_INVALID, "bad argument");
+  *count = l->launches;
   return PE_OK;
 }

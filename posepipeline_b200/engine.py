@@ -185,7 +185,9 @@ def pack_tc_weights(w: np.ndarray) -> np.ndarray:
     Each output channel's weights are multiplied by a power of two so the largest is in [8,16): exact, and it keeps the
     small `lo` halves out of the FP16 subnormal range (a 0.05 weight would otherwise carry only ~20 significant bits);
     the epilogue multiplies the accumulators by `scale` = the inverse power of two (exact again)."""
-    cout, cin, k, _ = w.shape
+    if w.ndim == 3:                                # 1-D temporal convolution (Cout, Cin, taps)
+        w = w[:, :, :, None]
+    cout, cin, k, kw = w.shape
     mx = np.abs(w.reshape(cout, -1)).max(axis=1)
     e = np.where(mx > 0, np.floor(np.log2(16.0 / np.maximum(mx, 1e-30))), 0.0)
     e = np.clip(e, -20, 40)
@@ -199,7 +201,7 @@ def pack_tc_weights(w: np.ndarray) -> np.ndarray:
     scale = np.ones(2 * (((cout + 63) // 64) * 64), np.float32)
     scale[:cout] = np.exp2(-e).astype(np.float32)
     scale[len(scale) // 2: len(scale) // 2 + cout] = up
-    t = ws.transpose(2, 3, 1, 0).reshape(k * k, cin // 16, 16, cout).transpose(0, 1, 3, 2)   # tap, chunk, cout, 16
+    t = ws.transpose(2, 3, 1, 0).reshape(k * kw, cin // 16, 16, cout).transpose(0, 1, 3, 2)   # tap, chunk, cout, 16
     if _lib.load().pe_precision_mode() == 1:
         h, l = fp16_split(t)
         op = np.ascontiguousarray(np.concatenate([h, l], axis=3)).view(np.float32)
@@ -443,7 +445,7 @@ class Lifter:
         blob = WeightBlob()
         offs: List[int] = []
 
-        def add(wname, bnname, pad_in=None, pad_out=None, bias=None):
+        def add(wname, bnname, pad_in=None, pad_out=None, bias=None, tc=True):
             w = state_dict[wname]                                        # (Cout, Cin, k)
             wf, bf = fold_bn(w, bn_of(state_dict, bnname) if bnname else None, bias)
             cout, cin, k = wf.shape
@@ -453,18 +455,32 @@ class Lifter:
             bp = np.zeros(co, np.float32)
             bp[:cout] = bf
             offs.extend([blob.add(wp), blob.add(bp)])
+            if tc:                                                      # tensor-core packing [tap][Cin/16][Cout][h16|l16]
+                wt = np.zeros((co, ci, k), np.float32)
+                wt[:cout, :cin] = wf
+                offs.append(blob.add(pack_tc_weights(wt)))
+            else:
+                offs.append(-1)
 
         add("expand_conv.weight", "expand_bn", pad_in=48)
         for i in range(4):
             add(f"layers_conv.{2 * i}.weight", f"layers_bn.{2 * i}")
             add(f"layers_conv.{2 * i + 1}.weight", f"layers_bn.{2 * i + 1}")
-        add("shrink.weight", None, pad_out=64, bias=state_dict["shrink.bias"])
+        add("shrink.weight", None, pad_out=64, bias=state_dict["shrink.bias"], tc=False)     # 0.4 % of the MACs, fp32 rows out: SIMT
         w = blob.array()
         offs_a = np.asarray(offs, np.int64)
         h = C.c_void_p()
         check(self.lib.pe_lifter_create(engine.h, ptr(w), w.size, ptr(offs_a), len(offs), channels, C.byref(h)))
         self.h = h
         _lib.track(self)
+
+    def uses_tensor_cores(self) -> bool:
+        return bool(self.lib.pe_lifter_uses_tensor_cores(self.h))
+
+    def launch_count(self) -> int:
+        v = C.c_int64()
+        check(self.lib.pe_lifter_launch_count(self.h, C.byref(v)))
+        return v.value
 
     def lift(self, kp2d_norm: np.ndarray) -> np.ndarray:
         """(N,17,2) normalised screen coordinates -> (N,17,3) float32."""

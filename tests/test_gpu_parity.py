@@ -322,6 +322,7 @@ def test_unstaged_frame_is_an_error(eng, model48):
 
 # ------------------------------------------------------------------ a10 lifter
 def test_lifter_matches_oracle(eng):
+    """a10: the tcgen05 temporal-convolution stack against the reference's own windowed evaluation (fp32 oracle)."""
     sd = synthetic_videopose3d_state_dict()
     lf = E.Lifter(eng, sd)
     net = OV.load_lifter(sd)
@@ -331,9 +332,33 @@ def test_lifter_matches_oracle(eng):
         x = OV.normalize_screen_coordinates(kp[:, :, :2], 1920, 1080)
         got = lf.lift(x)
         assert got.shape == (n, 17, 3)
-        assert np.abs(got - ref).max() <= 1e-3, np.abs(got - ref).max()
-        assert np.abs(got - ref).max() <= 5e-5 * np.abs(ref).max()
+        err = np.abs(got - ref).max()
+        print(f"lifter N={n}: max abs err {err:.2e} (max |ref| {np.abs(ref).max():.2f}), tensor cores: {lf.uses_tensor_cores()}")
+        assert err <= 1e-3 and err <= 5e-5 * np.abs(ref).max(), err
+    assert lf.uses_tensor_cores()                          # the contraction must be on tcgen05, not the SIMT fallback
     lf.close()
+
+
+def test_lifter_long_sequence_config5(eng):
+    """BASELINE configs[4] size: N = 16384 frames against the float64 dilated whole-sequence form of
+    the oracle network; also: the tensor-core and the fp32 SIMT paths of the library agree."""
+    sd = synthetic_videopose3d_state_dict()
+    n = 16384
+    kp = synthetic_keypoints_2d(n, seed=7)
+    x = OV.normalize_screen_coordinates(kp[:, :, :2], 1920, 1080)
+    ref = OV.dilated_whole_sequence(OV.load_lifter(sd, torch.float64), x)
+    lf = E.Lifter(eng, sd)
+    got = lf.lift(x)
+    assert lf.uses_tensor_cores()
+    err = np.abs(got - ref).max()
+    print(f"lifter N={n}: max abs err vs fp64 {err:.2e} (max |ref| {np.abs(ref).max():.2f})")
+    assert got.shape == (n, 17, 3) and err <= 1e-3 and err <= 3e-5 * np.abs(ref).max(), err
+    lf.close()
+    simt = _with_env(lambda: E.Lifter(eng, sd), PE_LIFTER_TC=0)
+    got2 = simt.lift(x[:700])                            # the last 121 frames see the edge padding instead of later frames
+    assert not simt.uses_tensor_cores()
+    assert np.abs(got2[:500] - ref[:500]).max() <= 3e-5 * np.abs(ref).max()
+    simt.close()
 
 
 def test_topdown_halpe136_and_wholebody133(eng):

@@ -164,18 +164,7 @@ def test_videopose3d_strided_equals_dilated_whole_sequence():
     kp = synthetic_keypoints_2d(40)
     ref = OV.process_videopose3d(kp, 1080, 1920, net)["keypoints_3d"]
     x = OV.normalize_screen_coordinates(kp[:, :, :2], 1920, 1080)
-    xp = np.pad(x, ((121, 121), (0, 0), (0, 0)), "edge").reshape(1, -1, 34).transpose(0, 2, 1)
-    t = torch.from_numpy(xp)
-    F = torch.nn.functional
-    with torch.no_grad():
-        y = F.relu(net.expand_bn(F.conv1d(t, net.expand_conv.weight)))
-        dil = 3
-        for i in range(4):
-            res = y[:, :, dil:-dil]
-            y = F.relu(net.layers_bn[2 * i](F.conv1d(y, net.layers_conv[2 * i].weight, dilation=dil)))
-            y = res + F.relu(net.layers_bn[2 * i + 1](F.conv1d(y, net.layers_conv[2 * i + 1].weight)))
-            dil *= 3
-        out = net.shrink(y)[0].T.reshape(-1, 17, 3).numpy()
+    out = OV.dilated_whole_sequence(net, x)
     assert out.shape == ref.shape and np.abs(out - ref).max() < 2e-6      # wrapper rounds its windows to float32
 
 

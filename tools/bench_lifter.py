@@ -22,4 +22,4 @@ for _ in range(reps):
     out = lf.lift(x)
 dt = (time.perf_counter() - t0) / reps
 print(f"lifter: {n} frames in {dt * 1e3:.2f} ms -> {n / dt:.0f} frames/s; reference-accounting {n * 2 * 176.3e6 / dt / 1e12:.1f} TFLOP/s, "
-      f"executed (dilated form) {n * 2 * 16.9e6 / dt / 1e12:.2f} TFLOP/s (fp32 SIMT)")
+      f"executed (dilated form) {n * 2 * 16.9e6 / dt / 1e12:.2f} TFLOP/s ({'tcgen05' if lf.uses_tensor_cores() else 'fp32 SIMT'})")
