@@ -37,6 +37,7 @@ typedef struct pe_engine pe_engine;
 typedef struct pe_model pe_model;
 typedef struct pe_lifter pe_lifter;
 typedef struct pe_bytetrack pe_bytetrack;
+typedef struct pe_detector pe_detector;
 
 /* layer program handed over by the host graph builder (posepipeline_b200/hrnet_spec.py) */
 enum { PE_OP_STEM = 0, PE_OP_CONV = 1, PE_OP_FUSE = 2, PE_OP_HEAD = 3 };
@@ -181,6 +182,36 @@ int pe_lifter_uses_tensor_cores(pe_lifter* l);
 int pe_lifter_launch_count(pe_lifter* l, int64_t* count);
 /* kp2d_norm: N*17*2 normalised screen coords; out: N*17*3.  Windows are edge-replicated (pad 121). */
 int pe_lift3d(pe_lifter* l, const float* kp2d_norm, int32_t n_frames, float* out3d);
+
+/* ---- person detector (YOLOX-X, the detector half of mmtrack.apis.inference_mot, pose_pipeline/wrappers/mmtrack.py:45;
+ * architecture 3rdparty/mmtracking/_base_/models/yolox_x_8x8.py:5-26, test pipeline and thresholds
+ * mot/bytetrack/bytetrack_yolox_x_crowdhuman_mot17-private-half.py:6,9-20,60-81).  The layer program comes from the host
+ * graph builder (posepipeline_b200/yolox_spec.py); operands may be 16-channel-aligned slices of wider tensors. ---- */
+enum { PE_GOP_INPUT = 0, PE_GOP_CONV = 1, PE_GOP_MAXPOOL = 2, PE_GOP_UPSAMPLE = 3, PE_GOP_DETHEAD = 4 };
+typedef struct pe_gop_desc {
+  int32_t kind;                     /* PE_GOP_* */
+  int32_t in, out, res;             /* tensor ids (-1 = none); DETHEAD: in = cls tower output, res = reg tower output */
+  int32_t in_coff, out_coff, res_coff; /* first channel of each view; DETHEAD: out_coff = index of the level's first prior */
+  int32_t cin, cout;                /* channels of the views */
+  int32_t ksize, stride;            /* CONV: 1|3, 1|2; MAXPOOL: window; DETHEAD: stride = the level's stride (8/16/32) */
+  int32_t act;                      /* 0 none, 1 ReLU, 2 SiLU */
+  int64_t w_off, b_off, wtc_off;    /* float offsets into the weight blob (DETHEAD: w = [6][cin] cls,reg x4,obj; b = [6]) */
+} pe_gop_desc;
+typedef struct pe_det_desc {
+  int32_t frame_h, frame_w;         /* staged frame size this detector is built for */
+  int32_t resized_h, resized_w;     /* mmcv.imrescale(keep ratio, (800,1440)) size */
+  int32_t net_h, net_w;             /* padded to a multiple of 32 (Pad size_divisor) */
+  int32_t n_ops, n_tensors, n_slots, max_frames, max_candidates, reserved;
+  float score_thr, nms_iou, pad_val, reserved_f;
+} pe_det_desc;
+int pe_detector_create(pe_engine* e, const pe_det_desc* desc, const pe_gop_desc* ops, const pe_tensor_desc* tensors,
+                       const int64_t* slot_elems, const float* weights, int64_t n_weight_floats, pe_detector** out);
+int pe_detector_destroy(pe_detector* d);
+/* frames = indices of staged frames (pe_stage_frames).  out_dets: n_frames * max_det rows [x1,y1,x2,y2,score] float32 in
+ * original-image pixels (rescale=True), score-descending after NMS; out_counts[i] = rows of frame i. */
+int pe_detect(pe_detector* d, const int32_t* frame_idx, int32_t n_frames, float* out_dets, int32_t* out_counts, int32_t max_det);
+int pe_detector_debug_tensor(pe_detector* d, int32_t tensor_id, int32_t coff, int32_t C, int32_t img, float* out_chw);
+int pe_detector_launch_count(pe_detector* d, int64_t* count);
 
 /* ---- ByteTrack association (host only; the per-frame `ByteTracker.track` mmtrack runs inside inference_mot,
  * pose_pipeline/wrappers/mmtrack.py:45; configuration 3rdparty/mmtracking/mot/bytetrack/

@@ -45,6 +45,19 @@ class ModelDesc(C.Structure):
                 ("pixel_std", C.c_float)]
 
 
+class GopDesc(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("inp", C.c_int32), ("out", C.c_int32), ("res", C.c_int32), ("in_coff", C.c_int32),
+                ("out_coff", C.c_int32), ("res_coff", C.c_int32), ("cin", C.c_int32), ("cout", C.c_int32), ("ksize", C.c_int32),
+                ("stride", C.c_int32), ("act", C.c_int32), ("w_off", C.c_int64), ("b_off", C.c_int64), ("wtc_off", C.c_int64)]
+
+
+class DetDesc(C.Structure):
+    _fields_ = [("frame_h", C.c_int32), ("frame_w", C.c_int32), ("resized_h", C.c_int32), ("resized_w", C.c_int32),
+                ("net_h", C.c_int32), ("net_w", C.c_int32), ("n_ops", C.c_int32), ("n_tensors", C.c_int32), ("n_slots", C.c_int32),
+                ("max_frames", C.c_int32), ("max_candidates", C.c_int32), ("reserved", C.c_int32), ("score_thr", C.c_float),
+                ("nms_iou", C.c_float), ("pad_val", C.c_float), ("reserved_f", C.c_float)]
+
+
 _lib = None
 
 
@@ -96,6 +109,11 @@ def load():
         "pe_lift3d": (C.c_int, [vp, vp, i32, vp]),
         "pe_lifter_uses_tensor_cores": (C.c_int, [vp]),
         "pe_lifter_launch_count": (C.c_int, [vp, P(i64)]),
+        "pe_detector_create": (C.c_int, [vp, P(DetDesc), P(GopDesc), P(TensorDesc), vp, vp, i64, P(vp)]),
+        "pe_detector_destroy": (C.c_int, [vp]),
+        "pe_detect": (C.c_int, [vp, vp, i32, vp, vp, i32]),
+        "pe_detector_debug_tensor": (C.c_int, [vp, i32, i32, i32, i32, vp]),
+        "pe_detector_launch_count": (C.c_int, [vp, P(i64)]),
         "pe_bytetrack_create": (C.c_int, [vp, i32, P(vp)]),
         "pe_bytetrack_destroy": (C.c_int, [vp]),
         "pe_bytetrack_reset": (C.c_int, [vp]),

@@ -121,6 +121,7 @@ extern "C" int pe_engine_destroy(pe_engine* e) {
   // children first (copies: the destroy calls edit the lists)
   { const std::vector<pe_model*> c = e->models; for (pe_model* m : c) pe_model_destroy(m); }
   { const std::vector<pe_lifter*> c = e->lifters; for (pe_lifter* l : c) pe_lifter_destroy(l); }
+  { const std::vector<pe_detector*> c = e->detectors; for (pe_detector* d : c) pe_detector_destroy(d); }
   if (!pe_handle_release(PE_H_ENGINE, e)) return PE_OK;
   if (pe_cuda_usable(e->device)) {
     cudaStreamSynchronize(e->stream);

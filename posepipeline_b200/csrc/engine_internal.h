@@ -18,6 +18,7 @@ struct pe_engine {
   // released after its engine (garbage-collection order is arbitrary on the Python side) is a no-op, never a dangling `e`
   std::vector<pe_model*> models;
   std::vector<pe_lifter*> lifters;
+  std::vector<pe_detector*> detectors;
 };
 
 // Live-handle registry (engine.cu).  Every pe_*_destroy first asks pe_handle_release(): false = the handle is not (or no

@@ -20,6 +20,14 @@ void launch_head(const float* in, int Cin, int H, int W, int nimg, const float* 
 void launch_ps_to_chw(const float* in, int C, int H, int W, int img, float* out, cudaStream_t st);
 
 void launch_s2d(const float* in, int C, int Hin, int Win, int nimg, float* out, int Hout, int Wout, cudaStream_t st);
+// detector (YOLOX) kernels: slices of wider tensors are given as (total channels, first channel)
+void launch_s2d_slice(const float* in, int C, int Ctot, int coff, int Hin, int Win, int nimg, float* out, int Hout, int Wout, cudaStream_t st);
+void launch_upsample2(const float* in, int C, int in_tot, int in_coff, int H, int W, int nimg, float* out, int out_tot, int out_coff, cudaStream_t st);
+void launch_maxpool(const float* in, int C, int tot, int in_coff, int H, int W, int nimg, int k, float* out, int out_coff, cudaStream_t st);
+void launch_det_input(const uint8_t* frames, const int32_t* frame_idx, int fh, int fw, int rh, int rw, int H2, int W2, const int32_t* xofs,
+                      const int16_t* alpha, const int32_t* yofs, const int16_t* beta, float pad_val, int nimg, float* out, cudaStream_t st);
+void launch_det_head(const float* cls_feat, const float* reg_feat, int C, int H, int W, int nimg, const float* w, const float* b, float stride,
+                     const float* scale_factor4, float score_thr, int prior_base, float* cand, int* count, int cap, float* raw, cudaStream_t st);
 void launch_chw_to_ps(const float* in, int C, int H, int W, int nimg, float* out, cudaStream_t st);
 
 // Range flag of the forward being launched on this thread (device word; nullptr = no checking).  The launchers below pass

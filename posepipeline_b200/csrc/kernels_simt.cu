@@ -583,3 +583,226 @@ void launch_s2d(const float* in, int C, int Hin, int Win, int nimg, float* out, 
   long long total = (long long)nimg * (Hout + 2) * (Wout + 2) * C;
   s2d_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, C, Hin, Win, nimg, out, Hout, Wout);
 }
+
+// =============================================================================================
+// Detector (YOLOX) data-movement kernels.  All work on 16-channel chunks of PS rows; `Ctot` / `coff` select a channel
+// slice of a wider tensor (concatenations are never materialised: producers write into slices of the concat tensor).
+// =============================================================================================
+// space-to-depth of a channel slice (stride-2 3x3 convolutions whose input cannot be TMA-gathered)
+__global__ void __launch_bounds__(256) s2d_slice_kernel(const float* __restrict__ in, int C, int Ctot, int coff, int Hin, int Win, int nimg,
+                                                        float* __restrict__ out, int Hout, int Wout) {
+  const int C4 = 4 * C, g4 = C4 >> 2;
+  const int Hp = Hout + 2, Wp = Wout + 2, HpI = Hin + 2, WpI = Win + 2;
+  const long long total = (long long)nimg * Hp * Wp * g4;
+  const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (t >= total) return;
+  const int ce = (int)(t % g4) * 4;
+  const long long m = t / g4;
+  const int img = (int)(m / (Hp * Wp));
+  const int r = (int)(m % (Hp * Wp));
+  const int ap = r / Wp, bp = r % Wp;
+  const int par = ce / C, c = ce % C;
+  const int py = par >> 1, px = par & 1;
+  const int sy = 2 * (ap - 1) + py, sx = 2 * (bp - 1) + px;
+  float* drow = out + m * ps_row_floats(C4);
+  if (ap >= 1 && bp >= 1 && sy < HpI && sx < WpI)
+    ps_copy4(drow, ce, in + (((long long)img * HpI + sy) * WpI + sx) * ps_row_floats(Ctot), coff + c);
+  else
+    ps_zero4(drow, ce);
+}
+
+void launch_s2d_slice(const float* in, int C, int Ctot, int coff, int Hin, int Win, int nimg, float* out, int Hout, int Wout, cudaStream_t st) {
+  long long total = (long long)nimg * (Hout + 2) * (Wout + 2) * C;
+  s2d_slice_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, C, Ctot, coff, Hin, Win, nimg, out, Hout, Wout);
+}
+
+// nearest-neighbour x2 upsampling (F.interpolate(scale_factor=2, mode='nearest')): pure copy of chunks, slice -> slice
+__global__ void __launch_bounds__(256) upsample2_kernel(const float* __restrict__ in, int C, int in_tot, int in_coff, int H, int W, int nimg,
+                                                        float* __restrict__ out, int out_tot, int out_coff) {
+  const int nch = C >> 4, Ho = 2 * H, Wo = 2 * W, Hp = Ho + 2, Wp = Wo + 2;
+  const long long total = (long long)nimg * Hp * Wp * nch;
+  const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (t >= total) return;
+  const int chunk = (int)(t % nch);
+  const long long m = t / nch;
+  const int img = (int)(m / (Hp * Wp)), r = (int)(m % (Hp * Wp)), py = r / Wp, px = r % Wp;
+  uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<char*>(out + m * ps_row_floats(out_tot)) + (size_t)(out_coff / 16 + chunk) * PS_CHUNK_BYTES);
+  if (py < 1 || py > Ho || px < 1 || px > Wo) {
+#pragma unroll
+    for (int i = 0; i < PS_CHUNK_BYTES / 16; ++i) op[i] = make_uint4(0u, 0u, 0u, 0u);
+    return;
+  }
+  const long long srow = ((long long)img * (H + 2) + (py - 1) / 2 + 1) * (W + 2) + (px - 1) / 2 + 1;
+  const uint4* ip = reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(in + srow * ps_row_floats(in_tot)) + (size_t)(in_coff / 16 + chunk) * PS_CHUNK_BYTES);
+#pragma unroll
+  for (int i = 0; i < PS_CHUNK_BYTES / 16; ++i) op[i] = __ldg(ip + i);
+}
+
+void launch_upsample2(const float* in, int C, int in_tot, int in_coff, int H, int W, int nimg, float* out, int out_tot, int out_coff, cudaStream_t st) {
+  const long long total = (long long)nimg * (2 * H + 2) * (2 * W + 2) * (C / 16);
+  upsample2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, C, in_tot, in_coff, H, W, nimg, out, out_tot, out_coff);
+}
+
+// MaxPool2d(k, stride 1, padding k/2) (SPPBottleneck): out-of-image taps are -inf, i.e. ignored; slice -> slice
+__global__ void __launch_bounds__(256) maxpool_kernel(const float* __restrict__ in, int C, int tot, int in_coff, int H, int W, int nimg, int k,
+                                                      float* __restrict__ out, int out_coff) {
+  const int nch = C >> 4, Hp = H + 2, Wp = W + 2;
+  const long long total = (long long)nimg * Hp * Wp * nch;
+  const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (t >= total) return;
+  const int chunk = (int)(t % nch);
+  const long long m = t / nch;
+  const int img = (int)(m / (Hp * Wp)), r = (int)(m % (Hp * Wp)), py = r / Wp, px = r % Wp;
+  float* orow = out + m * ps_row_floats(tot);
+  if (py < 1 || py > H || px < 1 || px > W) {
+    uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<char*>(orow) + (size_t)(out_coff / 16 + chunk) * PS_CHUNK_BYTES);
+#pragma unroll
+    for (int i = 0; i < PS_CHUNK_BYTES / 16; ++i) op[i] = make_uint4(0u, 0u, 0u, 0u);
+    return;
+  }
+  float best[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) best[i] = -INFINITY;
+  const int R = k / 2;
+  for (int dy = -R; dy <= R; ++dy) {
+    const int y = py + dy;
+    if (y < 1 || y > H) continue;
+    for (int dx = -R; dx <= R; ++dx) {
+      const int x = px + dx;
+      if (x < 1 || x > W) continue;
+      float v[16];
+      chunk_load16(in + (((long long)img * Hp + y) * Wp + x) * ps_row_floats(tot), in_coff / 16 + chunk, v);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) best[i] = fmaxf(best[i], v[i]);
+    }
+  }
+  chunk_store16(orow, out_coff / 16 + chunk, best);      // re-splitting an exactly representable value reproduces it
+}
+
+void launch_maxpool(const float* in, int C, int tot, int in_coff, int H, int W, int nimg, int k, float* out, int out_coff, cudaStream_t st) {
+  const long long total = (long long)nimg * (H + 2) * (W + 2) * (C / 16);
+  maxpool_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, C, tot, in_coff, H, W, nimg, k, out, out_coff);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Detector input: cv2.resize(INTER_LINEAR, uint8 fixed point) + Pad(114) + Normalize(0,1) + Focus space-to-depth, fused.
+// One thread = one position of the padded (H/2+2) x (W/2+2) Focus grid = 12 values (4 pixels x 3 channels) -> one
+// 16-channel PS chunk (channels 12..15 zero).  Channel order of the Focus concat: (top-left, bottom-left, top-right,
+// bottom-right) x (R, G, B) where R,G,B are the planes the reference's wrapper hands over (it swaps the BGR frame once,
+// pose_pipeline/wrappers/mmtrack.py:43), i.e. BGR frame channel 2 - c.
+// xofs/yofs: source index pairs, alpha/beta: 11-bit coefficient pairs (host tables, same arithmetic as OpenCV).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) det_input_kernel(const uint8_t* __restrict__ frames, const int32_t* __restrict__ frame_idx, int fh, int fw,
+                                                        int rh, int rw,   // resized size (un-padded)
+                                                        int H2, int W2,   // Focus grid = padded size / 2
+                                                        const int32_t* __restrict__ xofs, const int16_t* __restrict__ alpha,
+                                                        const int32_t* __restrict__ yofs, const int16_t* __restrict__ beta, float pad_val,
+                                                        int nimg, float* __restrict__ out) {
+  const int Hp = H2 + 2, Wp = W2 + 2;
+  const long long total = (long long)nimg * Hp * Wp;
+  const long long m = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (m >= total) return;
+  const int img = (int)(m / (Hp * Wp)), r = (int)(m % (Hp * Wp)), py = r / Wp, px = r % Wp;
+  float* orow = out + m * ps_row_floats(16);
+  if (py < 1 || py > H2 || px < 1 || px > W2) {
+#pragma unroll
+    for (int c = 0; c < 16; c += 4) ps_zero4(orow, c);
+    return;
+  }
+  const uint8_t* f = frames + (size_t)frame_idx[img] * fh * fw * 3;
+  float v[16];
+#pragma unroll
+  for (int i = 12; i < 16; ++i) v[i] = 0.f;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {                       // Focus order: top-left, bottom-left, top-right, bottom-right
+    const int dy = q & 1, dx = q >> 1;
+    const int y = 2 * (py - 1) + dy, x = 2 * (px - 1) + dx;
+    if (y >= rh || x >= rw) {
+      v[3 * q] = v[3 * q + 1] = v[3 * q + 2] = pad_val;
+      continue;
+    }
+    const int sy0 = yofs[2 * y], sy1 = yofs[2 * y + 1], sx0 = xofs[2 * x], sx1 = xofs[2 * x + 1];
+    const int b0 = beta[2 * y], b1 = beta[2 * y + 1], a0 = alpha[2 * x], a1 = alpha[2 * x + 1];
+    const uint8_t* r0 = f + (size_t)sy0 * fw * 3;
+    const uint8_t* r1 = f + (size_t)sy1 * fw * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int cs = 2 - c;                             // R,G,B planes of the BGR frame
+      const int S0 = r0[sx0 * 3 + cs] * a0 + r0[sx1 * 3 + cs] * a1;
+      const int S1 = r1[sx0 * 3 + cs] * a0 + r1[sx1 * 3 + cs] * a1;
+      int pix = (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2;
+      pix = pix < 0 ? 0 : (pix > 255 ? 255 : pix);
+      v[3 * q + c] = (float)pix;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 16; c += 4) ps_store4(orow, c, make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]));
+}
+
+void launch_det_input(const uint8_t* frames, const int32_t* frame_idx, int fh, int fw, int rh, int rw, int H2, int W2, const int32_t* xofs,
+                      const int16_t* alpha, const int32_t* yofs, const int16_t* beta, float pad_val, int nimg, float* out, cudaStream_t st) {
+  const long long total = (long long)nimg * (H2 + 2) * (W2 + 2);
+  det_input_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(frames, frame_idx, fh, fw, rh, rw, H2, W2, xofs, alpha, yofs, beta, pad_val, nimg, out);
+}
+
+// ---------------------------------------------------------------------------------------------
+// YOLOXHead output convolutions (1x1: cls 1, reg 4, obj 1 channel) + get_bboxes decode of one level, fused:
+//   box = ((reg_xy * stride + prior) -/+ exp(reg_wh) * stride / 2) / scale_factor,  score = sigmoid(cls) * sigmoid(obj)
+// and every candidate with score >= score_thr is appended to the image's candidate list (prior index kept for a
+// deterministic order).  One warp per position: lanes split the input channels, shuffle-reduce the 6 dot products.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) det_head_kernel(const float* __restrict__ cls_feat, const float* __restrict__ reg_feat, int C, int H, int W,
+                                                       int nimg, const float* __restrict__ w /*[6][C]: cls, reg x4, obj*/,
+                                                       const float* __restrict__ b /*[6]*/, float stride, float4 scale_factor, float score_thr,
+                                                       int prior_base, float* __restrict__ cand /*[nimg][cap][6]*/, int* __restrict__ count, int cap,
+                                                       float* __restrict__ raw /*optional [nimg][H*W][6] logits*/) {
+  const int warp = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const long long total = (long long)nimg * H * W;
+  if (warp >= total) return;
+  const int img = warp / (H * W), pos = warp % (H * W), y = pos / W, x = pos % W;
+  const long long row = ((long long)img * (H + 2) + y + 1) * (W + 2) + x + 1;
+  const float* cr = cls_feat + row * ps_row_floats(C);
+  const float* rr = reg_feat + row * ps_row_floats(C);
+  float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int c = lane * 4; c < C; c += 128) {
+    const float4 cv = ps_load4(cr, c), rv = ps_load4(rr, c);
+    const float cvv[4] = {cv.x, cv.y, cv.z, cv.w}, rvv[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      acc[0] = fmaf(cvv[i], w[c + i], acc[0]);
+#pragma unroll
+      for (int k = 1; k < 6; ++k) acc[k] = fmaf(rvv[i], w[k * C + c + i], acc[k]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 6; ++k)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+  if (lane != 0) return;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) acc[k] += b[k];
+  if (raw) {
+    float* o = raw + ((size_t)img * H * W + pos) * 6;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) o[k] = acc[k];
+  }
+  const float sc = __fmul_rn(__fdiv_rn(1.0f, 1.0f + expf(-acc[0])), __fdiv_rn(1.0f, 1.0f + expf(-acc[5])));
+  if (!(sc >= score_thr)) return;
+  const float cx = __fadd_rn(__fmul_rn(acc[1], stride), (float)x * stride), cy = __fadd_rn(__fmul_rn(acc[2], stride), (float)y * stride);
+  const float bw = __fmul_rn(expf(acc[3]), stride), bh = __fmul_rn(expf(acc[4]), stride);
+  const float hw = __fdiv_rn(bw, 2.0f), hh = __fdiv_rn(bh, 2.0f);
+  const int slot = atomicAdd(count + img, 1);
+  if (slot >= cap) return;
+  float* o = cand + ((size_t)img * cap + slot) * 6;
+  o[0] = __fdiv_rn(__fsub_rn(cx, hw), scale_factor.x); o[1] = __fdiv_rn(__fsub_rn(cy, hh), scale_factor.y);
+  o[2] = __fdiv_rn(__fadd_rn(cx, hw), scale_factor.z); o[3] = __fdiv_rn(__fadd_rn(cy, hh), scale_factor.w);
+  o[4] = sc; o[5] = __int_as_float(prior_base + pos);
+}
+
+void launch_det_head(const float* cls_feat, const float* reg_feat, int C, int H, int W, int nimg, const float* w, const float* b, float stride,
+                     const float* scale_factor4, float score_thr, int prior_base, float* cand, int* count, int cap, float* raw, cudaStream_t st) {
+  const long long warps = (long long)nimg * H * W;
+  det_head_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(cls_feat, reg_feat, C, H, W, nimg, w, b, stride,
+                                                                         make_float4(scale_factor4[0], scale_factor4[1], scale_factor4[2], scale_factor4[3]),
+                                                                         score_thr, prior_base, cand, count, cap, raw);
+}

@@ -80,8 +80,8 @@ def test_mmtrack_interface():
     from posepipeline_b200.wrappers import mmtrack as T
     with pytest.raises(Exception, match="Unknown config file for MMTrack method nope"):
         T.mmtrack_bounding_boxes("x.mp4", "nope")
-    with pytest.raises(NotImplementedError):
-        T.mmtrack_bounding_boxes("x.mp4", "bytetrack")
+    with pytest.raises(NotImplementedError):          # Faster R-CNN trackers: the reference's own install or nothing
+        T.mmtrack_bounding_boxes("x.mp4", "tracktor")
     rows = np.array([[3, 10, 20, 50, 80, 0.9]], np.float32)
     d = T.tracks_from_rows(rows)[0]
     assert d["track_id"] == 3 and np.allclose(d["tlhw"], [10, 20, 40, 60]) and np.allclose(d["tlbr"], [10, 20, 50, 80])   # Q2
