@@ -39,87 +39,50 @@ class TopDownSpec:
     std: Tuple[float, float, float] = (0.229, 0.224, 0.225)
     wrapper_double_swap: bool = True
     checkpoint: Optional[str] = None               # path under MODEL_DATA_DIR (reference wrappers/mmpose.py:33-52)
+    config: Optional[str] = None                   # mmcv config path under MODEL_DATA_DIR (same lines)
 
 
-# Halpe-136 left/right pairs, derived from the `swap` fields of the reference's dataset_info
-# (3rdparty/mmpose/config/_base_/halpe.py, passed to the model at halpe/hrnet_w48_halpe_384x288_dark_plus.py:152)
-HALPE_FLIP_PAIRS = [[1, 2],
-                    [3, 4],
-                    [5, 6],
-                    [7, 8],
-                    [9, 10],
-                    [11, 12],
-                    [13, 14],
-                    [15, 16],
-                    [20, 21],
-                    [22, 23],
-                    [24, 25],
-                    [26, 42],
-                    [27, 41],
-                    [28, 40],
-                    [29, 39],
-                    [30, 38],
-                    [31, 37],
-                    [32, 36],
-                    [33, 35],
-                    [43, 52],
-                    [44, 51],
-                    [45, 50],
-                    [46, 49],
-                    [47, 48],
-                    [57, 61],
-                    [58, 60],
-                    [62, 71],
-                    [63, 70],
-                    [64, 69],
-                    [65, 68],
-                    [66, 73],
-                    [67, 72],
-                    [74, 80],
-                    [75, 79],
-                    [76, 78],
-                    [81, 85],
-                    [82, 84],
-                    [86, 90],
-                    [87, 89],
-                    [91, 93],
-                    [94, 115],
-                    [95, 116],
-                    [96, 117],
-                    [97, 118],
-                    [98, 119],
-                    [99, 120],
-                    [100, 121],
-                    [101, 122],
-                    [102, 123],
-                    [103, 124],
-                    [104, 125],
-                    [105, 126],
-                    [106, 127],
-                    [107, 128],
-                    [108, 129],
-                    [109, 130],
-                    [110, 131],
-                    [111, 132],
-                    [112, 133],
-                    [113, 134],
-                    [114, 135]]
+# Halpe-136 left/right pairs = the `swap` fields of the reference's dataset_info (3rdparty/mmpose/config/_base_/halpe.py, passed
+# to the model at halpe/hrnet_w48_halpe_384x288_dark_plus.py:152).  Built-in copy for runs without the config tree; with
+# $MODEL_DATA_DIR/mmpose/config present the pairs are read from the file (mmcv_config.flip_pairs_from_dataset_info), and
+# tests/test_config.py checks the two agree.
+HALPE_FLIP_PAIRS = [[a, b] for a, b in zip(
+    [1, 3, 5, 7, 9, 11, 13, 15, 20, 22, 24, 26, 27, 28, 29, 30, 31, 32, 33, 43, 44, 45, 46, 47, 57, 58, 62, 63, 64, 65, 66, 67, 74, 75, 76,
+     81, 82, 86, 87, 91] + list(range(94, 115)),
+    [2, 4, 6, 8, 10, 12, 14, 16, 21, 23, 25, 42, 41, 40, 39, 38, 37, 36, 35, 52, 51, 50, 49, 48, 61, 60, 71, 70, 69, 68, 73, 72, 80, 79, 78,
+     85, 84, 90, 89, 93] + list(range(115, 136)))]
 
 
 METHODS: Dict[str, TopDownSpec] = {
     # reference wrappers/mmpose.py:33-36
-    "HRNet_W48_COCO": TopDownSpec(checkpoint="mmpose/checkpoints/hrnet_w48_coco_384x288_dark-e881a4b6_20210203.pth"),
+    "HRNet_W48_COCO": TopDownSpec(config="mmpose/config/top_down/darkpose/coco/hrnet_w48_coco_384x288_dark.py",
+                                  checkpoint="mmpose/checkpoints/hrnet_w48_coco_384x288_dark-e881a4b6_20210203.pth"),
     # reference wrappers/mmpose.py:41-44; old-style config without dataset_info => mmpose falls back to the COCO-17 body
     # pairs when flipping all 133 channels -- reproduced
-    "HRNet_W48_COCOWholeBody": TopDownSpec(num_joints=133,
+    "HRNet_W48_COCOWholeBody": TopDownSpec(num_joints=133, config="mmpose/config/coco-wholebody/hrnet_w48_coco_wholebody_384x288_dark_plus.py",
                                            checkpoint="mmpose/checkpoints/hrnet_w48_coco_wholebody_384x288_dark-f5726563_20200918.pth"),
     # reference wrappers/mmpose.py:49-52 (PosePipe's production default, scripts/process_h36m.py:15)
     "HRNet_W48_HALPE": TopDownSpec(num_joints=136, flip_pairs=[list(p) for p in HALPE_FLIP_PAIRS],
+                                   config="mmpose/config/halpe/hrnet_w48_halpe_384x288_dark_plus.py",
                                    checkpoint="mmpose/checkpoints/hrnet_w48_halpe_384x288_dark_plus-d13c2588_20211021.pth"),
     # BASELINE config 1 (upstream hrnet_w32_coco_256x192.py; not configured in the reference)
     "HRNet_W32_COCO": TopDownSpec(variant="w32", image_size=(192, 256), heatmap_size=(48, 64), post_process="default",
-                                  modulate_kernel=11, checkpoint="mmpose/checkpoints/hrnet_w32_coco_256x192-c78dce93_20200708.pth"),
+                                  modulate_kernel=11, config="mmpose/config/top_down/hrnet/coco/hrnet_w32_coco_256x192.py",
+                                  checkpoint="mmpose/checkpoints/hrnet_w32_coco_256x192-c78dce93_20200708.pth"),
 }
+
+
+def spec_for(method: str, model_data_dir: str = "") -> TopDownSpec:
+    """The method's settings as the reference would see them: read from its mmcv config file under
+    ``model_data_dir`` (the path ``wrappers/mmpose.py:33-52`` passes to ``init_pose_model``) when that file exists -- so an
+    edited ``test_cfg`` / ``data_cfg`` is honoured -- else the built-in copy of the shipped values."""
+    import dataclasses
+    base = METHODS[method]
+    path = os.path.join(model_data_dir or "", base.config or "")
+    if base.config and os.path.isfile(path):
+        from .mmcv_config import load_config, topdown_settings
+        return dataclasses.replace(base, **topdown_settings(load_config(path)))
+    return base
 
 
 def tf32_split(x: np.ndarray):

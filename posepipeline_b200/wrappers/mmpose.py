@@ -66,7 +66,7 @@ def get_engine() -> "E.PoseEngine":
 def get_model(method: str):
     """Process-level cache keyed by method tag (the reference reloads weights for every video, Q8)."""
     if method not in _models:
-        spec = E.METHODS[method]
+        spec = E.spec_for(method, _model_data_dir())      # honours an edited $MODEL_DATA_DIR/mmpose/config/**
         ckpt = os.path.join(_model_data_dir(), spec.checkpoint)
         if os.path.exists(ckpt):
             from ..weights import load_checkpoint
