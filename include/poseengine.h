@@ -110,6 +110,25 @@ int pe_stage_frames(pe_engine* e, const uint8_t* frames, int32_t n, int32_t heig
 /* As above but the frames are already in device memory (benchmark "resident" leg). */
 int pe_stage_frames_device(pe_engine* e, const uint8_t* d_frames, int32_t n, int32_t height, int32_t width);
 
+/* Frame source (replaces the synchronous cap.read() -> H2D sequence of wrappers/mmpose.py:60-76 and
+ * wrappers/mmtrack.py:37-45): two device slots.  pe_frames_upload copies a block on the engine's own copy stream and may be
+ * called from a decode thread while the engine stream computes on the other slot; pe_frames_select makes a slot the staged
+ * frames (the engine stream waits for that slot's upload only).  The caller must not upload into a slot while a compute call
+ * that selected it is still running (the compute entry points are synchronous, so "it has returned" suffices). */
+int pe_frames_upload(pe_engine* e, int32_t slot, const uint8_t* frames, int32_t n, int32_t height, int32_t width,
+                     int64_t frame_stride_bytes);
+/* same, but the block lands in caller-owned device memory (e.g. a frame cache resident in HBM) instead of the engine's buffer */
+int pe_frames_upload_to(pe_engine* e, int32_t slot, void* d_dst, const uint8_t* frames, int32_t n, int32_t height, int32_t width,
+                        int64_t frame_stride_bytes);
+int pe_frames_select(pe_engine* e, int32_t slot);
+int pe_frames_slot_ptr(pe_engine* e, int32_t slot, void** out);
+
+/* cv2.warpAffine(frame, trans, (out_w, out_h), INTER_LINEAR, border 0) for n (staged frame, forward 2x3 matrix) pairs ->
+ * uint8 HWC crops n*out_h*out_w*3 on the host: the crop primitive of pose_pipeline/utils/bounding_box.py:32-53
+ * (crop_image_bbox / get_person_dataloader), bit-exact against cv2.  swap_rb = 1 swaps channels 0 and 2. */
+int pe_warp_affine(pe_engine* e, const int32_t* frame_idx, const double* trans, int32_t n, int32_t out_h, int32_t out_w,
+                   int32_t swap_rb, uint8_t* out_crops);
+
 /* PersonBbox.make (pose_pipeline/pipeline.py:656-687): per frame keep the dicts whose track_id is in
  * keep_tracks; exactly one -> present, bbox = its tlhw; then NaN-mask, bfill(limit 2), ffill(limit 2).
  * Host-only, bit-exact.  counts[f] = #tracks in frame f; track_ids/tlhw are concatenated over frames. */

@@ -88,6 +88,11 @@ def load():
         "pe_shutdown": (C.c_int, []),
         "pe_stage_frames": (C.c_int, [vp, vp, i32, i32, i32, i64]),
         "pe_stage_frames_device": (C.c_int, [vp, vp, i32, i32, i32]),
+        "pe_frames_upload": (C.c_int, [vp, i32, vp, i32, i32, i32, i64]),
+        "pe_frames_upload_to": (C.c_int, [vp, i32, vp, vp, i32, i32, i32, i64]),
+        "pe_frames_select": (C.c_int, [vp, i32]),
+        "pe_frames_slot_ptr": (C.c_int, [vp, i32, P(vp)]),
+        "pe_warp_affine": (C.c_int, [vp, vp, vp, i32, i32, i32, i32, vp]),
         "pe_person_bbox": (C.c_int, [vp, i32, vp, vp, vp, i32, vp, vp]),
         "pe_model_create": (C.c_int, [vp, P(ModelDesc), P(OpDesc), P(TensorDesc), vp, vp, i64, vp, vp, P(vp)]),
         "pe_model_destroy": (C.c_int, [vp]),

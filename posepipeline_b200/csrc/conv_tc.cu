@@ -775,10 +775,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (p.act == 1) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
-          } else if (p.act == 2) {                           // SiLU (YOLOX ConvModule): x * sigmoid(x) = x / (1 + exp(-x))
+          }
+#ifndef PE_TC_NO_SILU
+          else if (p.act == 2) {                           // SiLU (YOLOX ConvModule): x * sigmoid(x) = x / (1 + exp(-x))
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = __fdiv_rn(v[i], 1.0f + expf(-v[i]));
           }
+#endif
+#ifndef PE_TC_NO_RESPOST
           if (p.res && p.res_post) {                         // residual after the activation (VideoPose3D: x = res + ReLU(bn(conv)))
             uint4 rv[NV];
             res_fetch(gi, g, rv);
@@ -789,13 +793,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] += one[i];
           }
+#endif
 #if PE_FP16
+#ifndef PE_TC_NO_RANGECHECK
           {                                                  // a value beyond the fp16x2 range is an error, not a silent clamp
             float amax = fabsf(v[0]);
 #pragma unroll
             for (int i = 1; i < 16; ++i) amax = fmaxf(amax, fabsf(v[i]));
             if (amax > PS_ABS_MAX && p.flag) atomicOr(p.flag, 1u);
           }
+#endif
           uint2 h[4], l[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) split4_h(make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]), h[i], l[i]);
@@ -961,7 +968,7 @@ static std::vector<TcCand> tc_enumerate(int kind, int Cin, int Cout, bool has_re
         if (nchunk % KC) continue;
         if (!tc_kernel_for(MT, NC, ntaps, KC)) continue;
         // window forms: contiguous always; one run per stencil row as well when the rows are far apart
-        const int nform = (!gather && g.nrows > 1 && g.row_step > 64) ? 2 : 1;
+        const int nform = (!gather && g.nrows > 1 && g.halo_before + g.halo_after > 128 * MT) ? 2 : 1;
         for (int form = 0; form < nform; ++form) {
           TcParams p{};
           p.nchunk = nchunk; p.Cout = Cout; p.halo = g.halo_before;

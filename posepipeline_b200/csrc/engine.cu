@@ -126,6 +126,8 @@ extern "C" int pe_engine_destroy(pe_engine* e) {
   if (pe_cuda_usable(e->device)) {
     cudaStreamSynchronize(e->stream);
     if (e->d_frames) cudaFree(e->d_frames);
+    if (e->copy_stream) { cudaStreamSynchronize(e->copy_stream); cudaStreamDestroy(e->copy_stream); }
+    for (int s = 0; s < 2; ++s) { if (e->d_slot_own[s]) cudaFree(e->d_slot_own[s]); if (e->slot_ready[s]) cudaEventDestroy(e->slot_ready[s]); }
     if (e->own_stream) cudaStreamDestroy(e->stream);
     cudaGetLastError();
   }
@@ -175,6 +177,67 @@ extern "C" int pe_stage_frames(pe_engine* e, const uint8_t* frames, int32_t n, i
   CU(cudaMemcpy2DAsync(e->d_frames, fb, frames, (size_t)frame_stride_bytes, fb, n, cudaMemcpyHostToDevice, e->stream));
   e->frames = e->d_frames;
   e->n_frames = n; e->fh = height; e->fw = width;
+  return PE_OK;
+}
+
+// f2 frame source: upload of one block into device slot `slot` on the engine's copy stream.  Meant to be called from the
+// decode thread while the engine stream computes on the other slot; the caller guarantees (host-side) that no compute call
+// still reads this slot (pe_topdown / pe_detect are synchronous, so "the call that used it has returned" is enough).
+static int frames_upload(pe_engine* e, int32_t slot, uint8_t* d_dst, const uint8_t* frames, int32_t n, int32_t height, int32_t width,
+                         int64_t frame_stride_bytes) {
+  ENGINE_ALIVE(e);
+  if (slot < 0 || slot > 1 || !frames || n <= 0 || height <= 0 || width <= 0) return fail(PE_ERR_INVALID, "bad argument to pe_frames_upload");
+  CU(cudaSetDevice(e->device));
+  const size_t fb = (size_t)height * width * 3;
+  if (frame_stride_bytes == 0) frame_stride_bytes = (int64_t)fb;
+  if ((size_t)frame_stride_bytes < fb) return fail(PE_ERR_INVALID, "frame stride smaller than a frame");
+  if (!e->copy_stream) CU(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+  if (!e->slot_ready[slot]) CU(cudaEventCreateWithFlags(&e->slot_ready[slot], cudaEventDisableTiming));
+  if (!d_dst) {
+    if (fb * n > e->slot_cap[slot]) {
+      CU(cudaStreamSynchronize(e->copy_stream));
+      if (e->d_slot_own[slot]) CU(cudaFree(e->d_slot_own[slot]));
+      e->d_slot_own[slot] = nullptr; e->slot_cap[slot] = 0;
+      CU(cudaMalloc(&e->d_slot_own[slot], fb * n));
+      e->slot_cap[slot] = fb * n;
+    }
+    d_dst = e->d_slot_own[slot];
+  }
+  CU(cudaMemcpy2DAsync(d_dst, fb, frames, (size_t)frame_stride_bytes, fb, n, cudaMemcpyHostToDevice, e->copy_stream));
+  CU(cudaEventRecord(e->slot_ready[slot], e->copy_stream));
+  e->d_slot[slot] = d_dst;
+  e->slot_n[slot] = n; e->slot_h[slot] = height; e->slot_w[slot] = width;
+  return PE_OK;
+}
+
+extern "C" int pe_frames_upload(pe_engine* e, int32_t slot, const uint8_t* frames, int32_t n, int32_t height, int32_t width,
+                                int64_t frame_stride_bytes) {
+  return frames_upload(e, slot, nullptr, frames, n, height, width, frame_stride_bytes);
+}
+
+// same, into caller-owned device memory (a resident frame cache): the block is uploaded once and stays where it will be re-used
+extern "C" int pe_frames_upload_to(pe_engine* e, int32_t slot, void* d_dst, const uint8_t* frames, int32_t n, int32_t height, int32_t width,
+                                   int64_t frame_stride_bytes) {
+  if (!d_dst) return fail(PE_ERR_INVALID, "pe_frames_upload_to: destination is NULL");
+  return frames_upload(e, slot, (uint8_t*)d_dst, frames, n, height, width, frame_stride_bytes);
+}
+
+// makes the block in `slot` the staged frames: the engine stream waits for its upload, nothing else
+extern "C" int pe_frames_select(pe_engine* e, int32_t slot) {
+  ENGINE_ALIVE(e);
+  if (slot < 0 || slot > 1 || !e->d_slot[slot] || !e->slot_ready[slot]) return fail(PE_ERR_STATE, "pe_frames_select: slot %d holds no upload", slot);
+  CU(cudaSetDevice(e->device));
+  CU(cudaStreamWaitEvent(e->stream, e->slot_ready[slot], 0));
+  e->frames = e->d_slot[slot];
+  e->n_frames = e->slot_n[slot]; e->fh = e->slot_h[slot]; e->fw = e->slot_w[slot];
+  return PE_OK;
+}
+
+// device address of a slot (so a resident frame cache can copy the block device-to-device)
+extern "C" int pe_frames_slot_ptr(pe_engine* e, int32_t slot, void** out) {
+  ENGINE_ALIVE(e);
+  if (slot < 0 || slot > 1 || !out) return fail(PE_ERR_INVALID, "bad argument to pe_frames_slot_ptr");
+  *out = e->d_slot[slot];
   return PE_OK;
 }
 
@@ -311,6 +374,40 @@ extern "C" int pe_box_to_affine(const pe_model_desc* desc, const double* bbox_xy
   if (!desc || !bbox_xywh || !center || !scale || !trans) return fail(PE_ERR_INVALID, "bad argument to pe_box_to_affine");
   box_to_affine(desc, bbox_xywh, center, scale, trans);
   return PE_OK;
+}
+
+// ------------------------------------------------------------------------------------------ f4: generic affine crops
+// cv2.warpAffine(frame, trans, (out_w, out_h), flags=INTER_LINEAR) for n (frame, 2x3 matrix) pairs on staged frames: the crop
+// primitive of pose_pipeline/utils/bounding_box.py:32-53 (crop_image_bbox, used by get_person_dataloader :101-194 for the SMPL
+// wrappers) on the same fixed-point kernel as the pose path's crops.  Bit-exact against cv2.
+extern "C" int pe_warp_affine(pe_engine* e, const int32_t* frame_idx, const double* trans, int32_t n, int32_t out_h, int32_t out_w,
+                              int32_t swap_rb, uint8_t* out_crops) {
+  ENGINE_ALIVE(e);
+  if (!frame_idx || !trans || !out_crops || n <= 0 || out_h <= 0 || out_w <= 0) return fail(PE_ERR_INVALID, "bad argument to pe_warp_affine");
+  if (!e->frames) return fail(PE_ERR_STATE, "no frames staged: call pe_stage_frames first");
+  for (int i = 0; i < n; ++i)
+    if (frame_idx[i] < 0 || frame_idx[i] >= e->n_frames) return fail(PE_ERR_STATE, "frame_idx[%d]=%d is not a staged frame (%d staged)", i, frame_idx[i], e->n_frames);
+  CU(cudaSetDevice(e->device));
+  cudaStream_t st = e->stream;
+  std::vector<double> minv((size_t)6 * n);
+  for (int i = 0; i < n; ++i) invert_affine(trans + 6 * i, minv.data() + 6 * i);
+  double* d_minv = nullptr; int32_t* d_fidx = nullptr; uint8_t* d_out = nullptr;
+  const size_t cb = (size_t)out_h * out_w * 3;
+  int rc = PE_OK;
+  cudaError_t ce = cudaMalloc(&d_minv, sizeof(double) * 6 * n);
+  if (ce == cudaSuccess) ce = cudaMalloc(&d_fidx, sizeof(int32_t) * n);
+  if (ce == cudaSuccess) ce = cudaMalloc(&d_out, cb * n);
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_minv, minv.data(), sizeof(double) * 6 * n, cudaMemcpyHostToDevice, st);
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_fidx, frame_idx, sizeof(int32_t) * n, cudaMemcpyHostToDevice, st);
+  if (ce == cudaSuccess) {
+    launch_warp_crop(e->frames, e->fh, e->fw, d_fidx, d_minv, d_out, n, out_h, out_w, swap_rb, st);
+    ce = cudaGetLastError();
+  }
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(out_crops, d_out, cb * n, cudaMemcpyDeviceToHost, st);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+  if (ce != cudaSuccess) rc = fail(PE_ERR_CUDA, "pe_warp_affine: %s", cudaGetErrorString(ce));
+  cudaFree(d_minv); cudaFree(d_fidx); cudaFree(d_out);
+  return rc;
 }
 
 // ------------------------------------------------------------------------------------------ model

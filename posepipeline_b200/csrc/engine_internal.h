@@ -14,6 +14,14 @@ struct pe_engine {
   const uint8_t* frames = nullptr;   // current frames (owned store or caller's device memory)
   size_t frames_cap = 0;
   int n_frames = 0, fh = 0, fw = 0;
+  // double-buffered upload slots (pe_frames_upload / pe_frames_select): a decode thread copies block k+1 on copy_stream while
+  // the engine stream computes on block k
+  cudaStream_t copy_stream = nullptr;
+  uint8_t* d_slot[2] = {nullptr, nullptr};       // current block of each slot: engine-owned buffer or caller memory
+  uint8_t* d_slot_own[2] = {nullptr, nullptr};   // the engine-owned buffers
+  size_t slot_cap[2] = {0, 0};
+  int slot_n[2] = {0, 0}, slot_h[2] = {0, 0}, slot_w[2] = {0, 0};
+  cudaEvent_t slot_ready[2] = {nullptr, nullptr};
   // handles created on this engine and still alive: pe_engine_destroy destroys them first, so a model / lifter handle
   // released after its engine (garbage-collection order is arbitrary on the Python side) is a no-op, never a dangling `e`
   std::vector<pe_model*> models;

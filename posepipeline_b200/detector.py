@@ -38,7 +38,8 @@ class Detector:
     """YOLOX-X for one frame size (the network input size follows from it: Resize keep-ratio to (800,1440), Pad to /32)."""
 
     def __init__(self, engine: PoseEngine, state_dict: Dict[str, np.ndarray], frame_h: int, frame_w: int, max_frames: int = 8,
-                 score_thr: float = SCORE_THR, nms_iou: float = NMS_IOU, max_candidates: int = 4096, max_det: int = 1024):
+                 score_thr: float = SCORE_THR, nms_iou: float = NMS_IOU, max_candidates: int = 4096, max_det: int = 1024,
+                 unique_slots: bool = False):
         self.engine, self.lib = engine, engine.lib
         self.frame_h, self.frame_w, self.max_frames, self.max_det = frame_h, frame_w, max_frames, max_det
         sd = {(k[len("detector."):] if k.startswith("detector.") else k): v for k, v in state_dict.items()}
@@ -77,7 +78,11 @@ class Detector:
                     raise ValueError("the engine's detector head is single-class (bbox_head.num_classes=1, bytetrack config :14)")
                 o.w_off = blob.add(w)
                 o.b_off = blob.add(np.concatenate([sd[f"{cls}.bias"], sd[f"{reg}.bias"], sd[f"{obj}.bias"]]))
-        slot_of, slot_elems = prog.assign_slots()
+        if unique_slots:                                    # parity hook: debug_tensor needs every tensor in its own buffer
+            slot_of = list(range(len(prog.tensors)))
+            slot_elems = [(t.H + 2) * (t.W + 2) * t.C for t in prog.tensors]
+        else:
+            slot_of, slot_elems = prog.assign_slots()
         tens = (_lib.TensorDesc * len(prog.tensors))()
         for t in prog.tensors:
             tens[t.tid].C, tens[t.tid].H, tens[t.tid].W, tens[t.tid].slot = t.C, t.H, t.W, slot_of[t.tid]
@@ -144,6 +149,14 @@ class DetectorPool:
         if key not in self._by_size:
             self._by_size[key] = Detector(self.engine, self.sd, key[0], key[1], self.max_frames)
         return self._by_size[key].detect(frames)
+
+    def detect_block(self, reader, blk) -> List[np.ndarray]:
+        """A block the frame source has already uploaded (frames.BlockReader): select it, no extra staging copy."""
+        key = blk.frames.shape[1:3]
+        if key not in self._by_size:
+            self._by_size[key] = Detector(self.engine, self.sd, key[0], key[1], self.max_frames)
+        reader.select(blk)
+        return self._by_size[key].detect_staged(np.arange(blk.n))
 
     def close(self):
         for d in self._by_size.values():

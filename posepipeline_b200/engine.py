@@ -197,6 +197,35 @@ class PoseEngine:
         check(self.lib.pe_stage_frames(self.h, ptr(frames), n, H, W, 0))
         self.n_frames = n
 
+    def upload_block(self, slot: int, frames: np.ndarray):
+        """Asynchronous H2D of a block into device slot 0/1 on the copy stream (callable from a decode thread)."""
+        n, H, W, _ = frames.shape
+        check(self.lib.pe_frames_upload(self.h, int(slot), ptr(frames), n, H, W, 0))
+
+    def upload_block_to(self, slot: int, dev_ptr: int, frames: np.ndarray):
+        """As upload_block, but into caller-owned device memory (the resident frame cache)."""
+        n, H, W, _ = frames.shape
+        check(self.lib.pe_frames_upload_to(self.h, int(slot), C.c_void_p(dev_ptr), ptr(frames), n, H, W, 0))
+
+    def select_block(self, slot: int, n: int):
+        check(self.lib.pe_frames_select(self.h, int(slot)))
+        self.n_frames = n
+
+    def slot_ptr(self, slot: int) -> int:
+        p = C.c_void_p()
+        check(self.lib.pe_frames_slot_ptr(self.h, int(slot), C.byref(p)))
+        return p.value or 0
+
+    def warp_affine(self, frame_idx, trans: np.ndarray, out_size, swap_rb: bool = False) -> np.ndarray:
+        """cv2.warpAffine(frame, trans_i, out_size=(w, h), INTER_LINEAR) of staged frames -> (n,h,w,3) uint8, bit-exact."""
+        fi = np.ascontiguousarray(frame_idx, np.int32)
+        t = np.ascontiguousarray(trans, np.float64).reshape(-1, 6)
+        w, h = int(out_size[0]), int(out_size[1])
+        out = np.empty((len(fi), h, w, 3), np.uint8)
+        if len(fi):
+            check(self.lib.pe_warp_affine(self.h, ptr(fi), ptr(t), len(fi), h, w, int(swap_rb), ptr(out)))
+        return out
+
     def stage_frames_device(self, dev_ptr: int, n: int, H: int, W: int):
         check(self.lib.pe_stage_frames_device(self.h, C.c_void_p(dev_ptr), n, H, W))
         self.n_frames = n

@@ -64,12 +64,17 @@ def _patch_module(name: str):
     return ref, "patched"
 
 
-def install(patch_person_bbox: bool = True):
+def install(patch_person_bbox: bool = True, patch_robust_reader: bool = True):
     """Returns {module name: 'patched' | 'replaced'}."""
     status = {}
     for name in PROVIDED:
         _, status[name] = _patch_module(name)
+    import pose_pipeline.pipeline as P
     if patch_person_bbox:
-        import pose_pipeline.pipeline as P
         P.PersonBbox.make = person_bbox_make
+    if patch_robust_reader:
+        # same contract as pipeline.py:47-87; the whole-file validation decode is skipped for content this process has
+        # already decoded completely (frames.robust_reader) -- one decode per video instead of four
+        from . import frames
+        P.Video.get_robust_reader = staticmethod(lambda key, return_cap=True: frames.robust_reader(P.Video, key, return_cap))
     return status

@@ -48,3 +48,16 @@ def gather_rows(local: np.ndarray, n_total: int, device=None) -> np.ndarray:
     dist.all_gather(outs, t)
     full = np.concatenate([o.cpu().numpy() for o in outs], axis=0)[:n_total]
     return full
+
+
+def max_over_ranks(value: int) -> int:
+    """max of an integer over the ranks (1 rank: the value itself)."""
+    rank, world = dist_info()
+    if world == 1:
+        return int(value)
+    import torch
+    import torch.distributed as dist
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    t = torch.tensor([int(value)], dtype=torch.int64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return int(t.item())

@@ -22,6 +22,7 @@ import cv2
 import numpy as np
 
 from .. import engine as E
+from .. import frames as F
 from ..sharding import dist_info, gather_rows, shard_range
 
 # reference wrappers/mmpose.py:8-24 (label strings consumed by TopDownPerson.joint_names, pipeline.py:1139-1141)
@@ -93,7 +94,7 @@ def mmpose_top_down_person(key, method='HRNet_W48_COCO'):
 
     bboxes = (PersonBbox & key).fetch1("bbox")
     video = Video.get_robust_reader(key, return_cap=False)  # returning video allows deleting it
-    cap = cv2.VideoCapture(video)
+    reader = None
     try:
         model = get_model(method)
         engine = model.engine
@@ -101,35 +102,40 @@ def mmpose_top_down_person(key, method='HRNet_W48_COCO'):
         rank, world = dist_info()
         start, stop = shard_range(n, rank, world)
         results = []
-        # frames before this rank's range are decoded and dropped (cap.grab: no colour conversion / copy)
-        for _ in range(start):
-            assert cap.grab()
-        block = None
-        i = start
-        while i < stop:
-            nb = min(FRAME_BLOCK, stop - i)
-            present, frames_idx = [], []
-            for j in range(nb):
-                # should match the length of identified person tracks
-                ret, frame = cap.read()
-                assert ret and frame is not None
-                if block is None or block.shape[1:] != frame.shape:
-                    block = _pinned((FRAME_BLOCK,) + frame.shape)
-                block[j] = frame
-                # handle the case where person is not tracked in frame
-                if not np.any(np.isnan(bboxes[i + j])):
-                    present.append(i + j)
-                    frames_idx.append(j)
+
+        def run_block(first, nb):
+            # handle the case where person is not tracked in frame
+            present = [first + j for j in range(nb) if not np.any(np.isnan(bboxes[first + j]))]
             out_block = [np.zeros((num_keypoints, 3)) for _ in range(nb)]
             if present:
-                engine.stage_frames(block[:nb])
-                kp = model.topdown(np.asarray(frames_idx, np.int32), np.asarray([bboxes[p] for p in present], np.float64))
+                kp = model.topdown(np.asarray([p - first for p in present], np.int32), np.asarray([bboxes[p] for p in present], np.float64))
                 for r, p in enumerate(present):
-                    out_block[p - i] = kp[r]
+                    out_block[p - first] = kp[r]
             results.extend(out_block)
-            i += nb
+
+        fp = F.fingerprint(video) if hasattr(engine, "stage_frames_device") else None
+        cached = F.CACHE.get(fp, start, stop) if fp and stop > start else None
+        if cached is not None:
+            # this rank's frames are resident in HBM (the tracker pass decoded them): no decode, no host->device copy
+            ptr, fh, fw = cached
+            i = start
+            while i < stop:
+                nb = min(FRAME_BLOCK, stop - i)
+                engine.stage_frames_device(ptr + (i - start) * fh * fw * 3, nb, fh, fw)
+                run_block(i, nb)
+                i += nb
+        else:
+            # the decode thread reads this rank's frame range (seek, not decode-and-drop) one block ahead of the GPU
+            reader = F.BlockReader(video, engine, FRAME_BLOCK, start, stop)
+            for blk in reader:
+                # should match the length of identified person tracks
+                assert blk.complete and blk.n > 0
+                reader.select(blk)
+                run_block(blk.first, blk.n)
+            assert len(results) == stop - start
     finally:
-        cap.release()
+        if reader is not None:
+            reader.close()
         os.remove(video)
 
     if world > 1:
@@ -139,14 +145,3 @@ def mmpose_top_down_person(key, method='HRNet_W48_COCO'):
         absent = np.asarray([bool(np.any(np.isnan(b))) for b in bboxes])
         return full.astype(np.float64) if absent.any() else full
     return np.asarray(results)
-
-
-def _pinned(shape):
-    """uint8 staging block in page-locked host memory when torch+CUDA are present (plumbing only), else pageable."""
-    try:
-        import torch
-        if torch.cuda.is_available():
-            return torch.empty(shape, dtype=torch.uint8, pin_memory=True).numpy()
-    except Exception:
-        pass
-    return np.empty(shape, np.uint8)

@@ -22,6 +22,9 @@ from typing import Optional
 import cv2
 import numpy as np
 
+from .. import frames as F
+from ..sharding import dist_info, gather_rows, max_over_ranks, shard_range
+
 METHODS = ("tracktor", "deepsort", "bytetrack", "qdtrack")
 FRAME_BLOCK = int(os.environ.get("PE_DET_FRAME_BLOCK", "8"))
 _reference_impl = None                 # set by posepipeline_b200.install when the reference's mmtrack wrapper is importable
@@ -58,27 +61,54 @@ def mmtrack_bounding_boxes(file_path, method="tracktor"):
 
     cap = cv2.VideoCapture(file_path)
     video_length = int(cap.get(cv2.CAP_PROP_FRAME_COUNT))
+    fh, fw = int(cap.get(cv2.CAP_PROP_FRAME_HEIGHT)), int(cap.get(cv2.CAP_PROP_FRAME_WIDTH))
+    cap.release()
+
+    engine = getattr(detector, "engine", None)
+    rank, world = dist_info()
+    start, stop = shard_range(video_length, rank, world)
+    # decoded frames go straight into the HBM-resident cache: the pose pass of this video then needs no second decode
+    fp = F.fingerprint(file_path) if engine is not None and hasattr(engine, "upload_block_to") else None
+    writer = F.CACHE.begin(fp, stop - start, fh, fw, getattr(engine, "device", 0), first=start) if fp else None
+    reader = F.BlockReader(file_path, engine, FRAME_BLOCK, start, stop, cache_writer=writer)
+    per_frame = []                                 # detections of this rank's frames, in order
+    try:
+        for blk in reader:
+            if blk.n == 0:                         # read failure: the reference breaks out of its loop (:40-41)
+                break
+            if hasattr(detector, "detect_block"):
+                per_frame.extend(detector.detect_block(reader, blk))
+            else:
+                per_frame.extend(detector.detect(blk.frames))
+            if not blk.complete:
+                break
+    finally:
+        reader.close()
+    if fp and world == 1 and len(per_frame) == video_length:
+        F.mark_valid(fp)                           # every frame decoded: a later get_robust_reader need not test-decode again
+
+    if world > 1:
+        # the detector shards by frame; the association is sequential in time and costs microseconds per frame, so every
+        # rank gathers all detections and runs the same tracker: identical tracks everywhere, no broadcast
+        cap_det = max(1, max_over_ranks(max([len(d) for d in per_frame], default=0)))
+        local = np.zeros((stop - start, cap_det * 5 + 1), np.float32)
+        local[:, -1] = -1.0                        # -1 = this frame could not be read
+        for i, d in enumerate(per_frame):
+            local[i, : len(d) * 5] = np.asarray(d, np.float32).ravel()
+            local[i, -1] = len(d)
+        full = gather_rows(local, video_length)
+        per_frame = []
+        for row in full:
+            if row[-1] < 0:
+                break
+            per_frame.append(row[: int(row[-1]) * 5].reshape(-1, 5))
 
     tracks = []
     try:
-        frame_id = 0
-        done = False
-        while frame_id < video_length and not done:
-            block = []
-            for _ in range(min(FRAME_BLOCK, video_length - frame_id)):
-                ret, frame = cap.read()
-                if ret != True or frame is None:
-                    done = True
-                    break
-                block.append(frame)
-            if not block:
-                break
-            for dets in detector.detect(np.stack(block)):
-                track_results = tracker.update(frame_id, dets)
-                tracks.append(tracks_from_rows(track_results))
-                frame_id += 1
+        for frame_id, dets in enumerate(per_frame):
+            track_results = tracker.update(frame_id, dets)
+            tracks.append(tracks_from_rows(track_results))
     finally:
-        cap.release()
         tracker.close()
 
     return tracks

@@ -63,9 +63,10 @@ def _match(ours, ref):
     return pairs
 
 
-def test_detector_input_and_every_layer_match_oracle(eng, det1080, oracle_net):
+def test_detector_input_and_every_layer_match_oracle(eng, sd, oracle_net):
     """Fixed-point resize + pad + Focus bit-exact; every ConvModule output of backbone / neck / head towers vs torch fp32."""
     frames = np.stack([synthetic_frame(0), synthetic_frame(1)])
+    det1080 = D.Detector(eng, sd, 1080, 1920, max_frames=2, unique_slots=True)
     det1080.detect(frames)
     for img in (0, 1):
         x, sf = OY.preprocess(cv2.cvtColor(frames[img], cv2.COLOR_BGR2RGB))
@@ -92,6 +93,7 @@ def test_detector_input_and_every_layer_match_oracle(eng, det1080, oracle_net):
         print(f"detector worst layers img {img} (max-abs-err / max-abs):", errs[:4], "median", errs[len(errs) // 2][0])
         assert len(errs) > 150
         assert errs[0][0] < 5e-5, errs[:5]
+    det1080.close()
 
 
 def test_detections_match_oracle(eng, det1080, oracle_net, sd):

@@ -175,3 +175,47 @@ def test_real_person_bbox_make_matches_reference_golden(ref_pipeline):
         assert np.array_equal(present, np.array(c["present"], bool))
         assert np.array_equal(np.isnan(bbox), np.isnan(gold)) and np.array_equal(np.nan_to_num(bbox), np.nan_to_num(gold))
     dj.reset()
+
+
+def test_overlay_video_equals_reference_renderer(ref_pipeline, tmp_path):
+    """f4: our video_overlay / draw_keypoints against the reference's own functions (utils/visualization.py:12-90) on the
+    same clip and callback: the written videos decode to identical frames."""
+    import cv2
+    ref_vis = importlib.import_module("pose_pipeline.utils.visualization")
+    from posepipeline_b200.utils import visualization as ours
+    path = str(tmp_path / "in.mp4")
+    _video(path, 20)
+    rng = np.random.default_rng(3)
+    kp = np.concatenate([rng.uniform(0, 160, (20, 17, 1)), rng.uniform(0, 120, (20, 17, 1)), rng.uniform(0, 1, (20, 17, 1))], axis=2)
+
+    def cb_factory(mod):
+        def cb(image, idx):
+            image = mod.draw_keypoints(image, kp[idx], radius=6)
+            cv2.rectangle(image, (10, 10 + idx), (60, 70 + idx), (255, 255, 255), 3)
+            return image
+        return cb
+    a, b = str(tmp_path / "ref.mp4"), str(tmp_path / "ours.mp4")
+    ref_vis.video_overlay(path, a, cb_factory(ref_vis), downsample=2, compress=False)
+    ours.video_overlay(path, b, cb_factory(ours), downsample=2, compress=False)
+    fa, fb = fakes.read_video(a), fakes.read_video(b)
+    assert len(fa) == len(fb) == 20 and fa[0].shape == (60, 80, 3)
+    assert all(np.array_equal(x, y) for x, y in zip(fa, fb))
+    img = rng.integers(0, 255, (120, 160, 3), dtype=np.uint8)
+    assert np.array_equal(ref_vis.draw_keypoints(img, kp[0]), ours.draw_keypoints(img, kp[0]))
+
+
+def test_crop_helpers_equal_reference(ref_pipeline):
+    """f4 host maths: fix_bb_aspect_ratio and the crop transform against the reference's utils/bounding_box.py:7-53."""
+    import cv2
+    ref_bb = importlib.import_module("pose_pipeline.utils.bounding_box")
+    from posepipeline_b200.utils import bounding_box as ours
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 255, (240, 320, 3), dtype=np.uint8)
+    for _ in range(8):
+        bbox = np.array([rng.uniform(-20, 200), rng.uniform(-20, 120), rng.uniform(20, 150), rng.uniform(30, 200)])
+        for ts, dil in (((224, 224), 1.0), ((288, 384), 1.2)):
+            assert np.array_equal(ref_bb.fix_bb_aspect_ratio(bbox, ratio=ts[0] / ts[1], dilate=dil), ours.fix_bb_aspect_ratio(bbox, ratio=ts[0] / ts[1], dilate=dil))
+            trans, b2 = ours.crop_transform(bbox, ts, dil)
+            ref_img, ref_b = ref_bb.crop_image_bbox(img, bbox, target_size=ts, dilate=dil)
+            assert np.array_equal(b2, ref_b)
+            assert np.array_equal(cv2.warpAffine(img, trans, ts, flags=cv2.INTER_LINEAR), ref_img)     # what the GPU kernel reproduces bit for bit

@@ -142,3 +142,64 @@ def test_frame_sharding_world2_gloo_matches_single_rank(tmp_path, monkeypatch):
     for rank, out, calls in got:
         assert out.dtype == single.dtype and np.array_equal(out, single), rank     # every rank holds the full result
         assert calls >= 1
+
+
+# ------------------------------------------------------------------ mmtrack wrapper: detector sharded by frame, replicated tracker
+class StubDetector:
+    """detections = f(frame content): one box whose position follows the bright square drawn into the frame."""
+
+    def detect(self, frames):
+        out = []
+        for f in frames:
+            ys, xs = np.nonzero(f[..., 1] > 200)
+            out.append(np.zeros((0, 5), np.float32) if len(xs) == 0 else
+                       np.array([[xs.min(), ys.min(), xs.max() + 1, ys.max() + 1, 0.9], [1, 2, 9, 12, 0.3]], np.float32))
+        return out
+
+
+def _track_video(tmp, n=13):
+    frames = []
+    for i in range(n):
+        f = np.full((96, 128, 3), 30, np.uint8)
+        if i != 6:
+            f[10 + i:50 + i, 20 + 3 * i:45 + 3 * i] = 255
+        frames.append(f)
+    path = os.path.join(tmp, "t.mp4")
+    fakes.write_video(path, frames)
+    return path
+
+
+def _track_worker(rank, world, port, tmp, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from posepipeline_b200.wrappers import mmtrack as T
+    T.get_detector = lambda: StubDetector()
+    tracks = T.mmtrack_bounding_boxes(os.path.join(tmp, "t.mp4"), "bytetrack")
+    q.put((rank, [[(t["track_id"], t["tlbr"].tolist(), float(t["confidence"])) for t in fr] for fr in tracks]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_mmtrack_sharded_detector_world2_matches_single_rank(tmp_path, monkeypatch):
+    from posepipeline_b200.wrappers import mmtrack as T
+    path = _track_video(str(tmp_path))
+    monkeypatch.setattr(T, "get_detector", lambda: StubDetector())
+    single = T.mmtrack_bounding_boxes(path, "bytetrack")
+    assert len(single) == 13 and len(single[6]) <= 1 and single[0][0]["track_id"] == 0
+    ref = [[(t["track_id"], t["tlbr"].tolist(), float(t["confidence"])) for t in fr] for fr in single]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    import socket
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    procs = [ctx.Process(target=_track_worker, args=(r, 2, port, str(tmp_path), q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, tr in got:
+        assert tr == ref, rank                      # every rank holds the full, identical track list
