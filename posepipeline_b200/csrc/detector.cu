@@ -163,7 +163,8 @@ extern "C" int pe_detector_create(pe_engine* e, const pe_det_desc* desc, const p
     c.Cin = s2 ? 4 * op.cin : op.cin; c.Cout = op.cout; c.act = op.act; c.dil = 0; c.H = to.H; c.W = to.W;
     c.max_rows = (long long)maximg * (to.H + 2) * (to.W + 2);
     c.out = act(d, op.out); c.out_total = to.C; c.out_coff = op.out_coff;
-    if (op.res >= 0) { c.res = act(d, op.res); c.res_total = d->tensors[op.res].C; c.res_coff = op.res_coff; }
+    // DarknetBottleneck: out = SiLU(bn(conv2(.))) + identity -- the residual joins AFTER the activation
+    if (op.res >= 0) { c.res = act(d, op.res); c.res_total = d->tensors[op.res].C; c.res_coff = op.res_coff; c.res_post = 1; }
     c.wtc = d->d_w + op.wtc_off; c.bias = d->d_w + op.b_off;
     cudaError_t ce = cudaErrorNotSupported;
     if (s2) {
