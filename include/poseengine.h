@@ -40,8 +40,17 @@ typedef struct pe_bytetrack pe_bytetrack;
 typedef struct pe_detector pe_detector;
 
 /* layer program handed over by the host graph builder (posepipeline_b200/hrnet_spec.py) */
-enum { PE_OP_STEM = 0, PE_OP_CONV = 1, PE_OP_FUSE = 2, PE_OP_HEAD = 3 };
-enum { PE_POST_NONE = 0, PE_POST_DEFAULT = 1, PE_POST_UNBIASED = 2 };
+enum { PE_OP_STEM = 0, PE_OP_CONV = 1, PE_OP_FUSE = 2, PE_OP_HEAD = 3,
+       /* ViTPose (posepipeline_b200/vit_spec.py): token tensors are flat rows, described with W = 0 and H = tokens per image */
+       PE_OP_PATCH = 4,   /* crop -> patch rows [tokens][3*ksize*ksize]; ksize = patch size, stride = padding */
+       PE_OP_GEMM = 5,    /* Linear: in[0] -> out, bias b_off, weights wtc_off; relu = activation (0 none, 1 ReLU, 3 GELU);
+                             residual = tensor id, or reserved = 1: a [tokens][cout] fp32 table at w_off added to every image */
+       PE_OP_LN = 6,      /* LayerNorm over cout channels: gamma w_off, beta b_off, eps = 10^-up[1]; up[0] = 1 writes the padded
+                             2-D grid of the output tensor (tokens -> H x W) instead of flat rows */
+       PE_OP_ATTN = 7,    /* multi-head self-attention: in[0] = qkv rows [3][cin heads][64], out rows [heads][64] */
+       PE_OP_D2S = 8 };   /* depth-to-space x2: in[0] [H x W][4*cout] -> out [2H x 2W][cout] (deconvolution head) */
+enum { PE_POST_NONE = 0, PE_POST_DEFAULT = 1, PE_POST_UNBIASED = 2, PE_POST_UDP = 3 /* mmpose post_dark_udp + UDP back-projection */ };
+#define PE_MODEL_FLAG_UDP 1   /* pe_model_desc.reserved bit 0: TopDownAffine(use_udp=True) warp matrix */
 
 typedef struct pe_op_desc {
   int32_t kind;        /* PE_OP_* */
@@ -75,7 +84,7 @@ typedef struct pe_model_desc {
   int32_t blur_kernel;         /* cfg test_cfg.modulate_kernel (17) */
   int32_t swap_rb;             /* 0 = reproduce the wrapper's double BGR<->RGB swap */
   int32_t use_tensor_cores;    /* 1 = tcgen05 path for eligible convs, 0 = fp32 SIMT everywhere */
-  int32_t reserved;
+  int32_t reserved;            /* PE_MODEL_FLAG_* */
   float padding;               /* bbox padding 1.25 */
   float pixel_std;             /* 200 */
 } pe_model_desc;

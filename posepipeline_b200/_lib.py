@@ -16,7 +16,7 @@ HEADER_PATH = os.path.join(os.path.dirname(_PKG), "include", "poseengine.h")
 
 PE_OK, PE_ERR_INVALID, PE_ERR_CUDA, PE_ERR_STATE, PE_ERR_NOGPU, PE_ERR_RANGE = 0, -1, -2, -3, -4, -5
 PE_OP_STEM, PE_OP_CONV, PE_OP_FUSE, PE_OP_HEAD = 0, 1, 2, 3
-PE_POST = {None: 0, "none": 0, "default": 1, "unbiased": 2}
+PE_POST = {None: 0, "none": 0, "default": 1, "unbiased": 2, "udp": 3}
 
 
 class PoseEngineError(RuntimeError):

@@ -9,7 +9,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
-SOURCES = ["engine.cu", "kernels_simt.cu", "decode.cu", "lifter.cu", "conv_tc.cu", "bytetrack.cu", "detector.cu"]
+SOURCES = ["engine.cu", "kernels_simt.cu", "decode.cu", "lifter.cu", "conv_tc.cu", "bytetrack.cu", "detector.cu", "vit.cu"]
 HEADERS = ["kernels.h", "pe_common.cuh", "engine_internal.h", os.path.join("..", "..", "include", "poseengine.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 # PE_PRECISION=tf32 builds the wide-range TF32x3 variant (8 B/element); default fp16x2 (4 B/element, half the MMAs)

@@ -69,7 +69,7 @@ struct TcParams {
   int res_row_off;           // residual row = output row + res_row_off (1-D temporal layers read a centre-cropped residual)
   int res_post;              // 1 = residual added AFTER the activation (VideoPose3D blocks), 0 = before (HRNet / Darknet blocks)
   int no_border;             // 1 = every row < M is an output row (1-D / GEMM layers); 0 = rows on the zero border are written as zeros
-  int act;                   // 0 none, 1 ReLU, 2 SiLU
+  int act;                   // 0 none, 1 ReLU, 2 SiLU, 3 GELU
   int S;                     // pipeline stages
   int nstage;                // stages per tile = nchunk / KC
   int rpg;                   // stencil rows per drain group
@@ -780,6 +780,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           else if (p.act == 2) {                           // SiLU (YOLOX ConvModule): x * sigmoid(x) = x / (1 + exp(-x))
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = __fdiv_rn(v[i], 1.0f + expf(-v[i]));
+          } else if (p.act == 3) {                         // GELU (ViT MLP): x * 0.5 * (1 + erf(x / sqrt(2)))
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = v[i] * 0.5f * (1.0f + erff(v[i] * 0.70710678118654752440f));
           }
 #endif
 #ifndef PE_TC_NO_RESPOST

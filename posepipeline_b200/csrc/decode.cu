@@ -134,6 +134,47 @@ __global__ void __launch_bounds__(256) decode_kernel(DecodeArgs a) {
         offy = -(-dxy * dx + dxx * dy) / det;
       }
     }
+  } else if (a.post == 3) {
+    // mmpose post_dark_udp (use_udp + GaussianHeatmap, ViTPose configs): cv2.GaussianBlur in place with the default
+    // BORDER_REFLECT_101, clip to [0.001, 50], log, second-order step on edge-replicated neighbours; the 2x2 system is solved
+    // in float64 (hessian + float64 eps * I), the rest is float32 like the numpy arrays
+    const int R = (a.ksize - 1) / 2;
+    auto refl = [](int i, int n) { return i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i); };
+    for (int i = threadIdx.x; i < HW; i += 256) {
+      const int y = i / a.W, x = i % a.W;
+      const float* row = s_m + y * a.W;
+      float s = c_gauss[R] * row[x];
+      for (int d = 1; d <= R; ++d) s = fmaf(c_gauss[R + d], row[refl(x - d, a.W)] + row[refl(x + d, a.W)], s);
+      s_t[i] = s;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < HW; i += 256) {
+      const int y = i / a.W, x = i % a.W;
+      float s = c_gauss[R] * s_t[i];
+      for (int d = 1; d <= R; ++d) s = fmaf(c_gauss[R + d], s_t[refl(y - d, a.H) * a.W + x] + s_t[refl(y + d, a.H) * a.W + x], s);
+      s_b[i] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && px >= 0 && py >= 0) {
+      auto L = [&](int yy, int xx) -> float {
+        yy = min(max(yy, 0), a.H - 1); xx = min(max(xx, 0), a.W - 1);           // np.pad(mode='edge')
+        return logf(fminf(fmaxf(s_b[yy * a.W + xx], 0.001f), 50.f));
+      };
+      const float i_ = L(py, px), ix1 = L(py, px + 1), iy1 = L(py + 1, px), ix1y1 = L(py + 1, px + 1);
+      const float ix1_y1_ = L(py - 1, px - 1), ix1_ = L(py, px - 1), iy1_ = L(py - 1, px);
+      const float dx = __fmul_rn(0.5f, __fsub_rn(ix1, ix1_)), dy = __fmul_rn(0.5f, __fsub_rn(iy1, iy1_));
+      const float dxx = __fadd_rn(__fsub_rn(ix1, __fmul_rn(2.f, i_)), ix1_), dyy = __fadd_rn(__fsub_rn(iy1, __fmul_rn(2.f, i_)), iy1_);
+      float t = __fsub_rn(ix1y1, ix1);
+      t = __fsub_rn(t, iy1); t = __fadd_rn(t, i_); t = __fadd_rn(t, i_); t = __fsub_rn(t, ix1_); t = __fsub_rn(t, iy1_); t = __fadd_rn(t, ix1_y1_);
+      const float dxy = __fmul_rn(0.5f, t);
+      const double eps = 1.1920928955078125e-07;
+      const double h00 = (double)dxx + eps, h01 = (double)dxy, h11 = (double)dyy + eps;
+      const double det = h00 * h11 - h01 * h01;
+      if (det != 0.0) {
+        offx = -((h11 * (double)dx - h01 * (double)dy) / det);      // coords -= H^-1 g
+        offy = -((-h01 * (double)dx + h00 * (double)dy) / det);
+      }
+    }
   } else if (a.post == 1) {
     if (threadIdx.x == 0 && 1 < px && px < a.W - 1 && 1 < py && py < a.H - 1) {
       const float ddx = __fsub_rn(s_m[py * a.W + px + 1], s_m[py * a.W + px - 1]);
@@ -144,7 +185,7 @@ __global__ void __launch_bounds__(256) decode_kernel(DecodeArgs a) {
   }
   if (threadIdx.x == 0) {
     float fx = cx, fy = cy;
-    if (a.post == 2) {
+    if (a.post == 2 || a.post == 3) {
       fx = (float)((double)cx + offx);
       fy = (float)((double)cy + offy);
     } else if (a.post == 1) {
@@ -153,7 +194,8 @@ __global__ void __launch_bounds__(256) decode_kernel(DecodeArgs a) {
     }
     // transform_preds: float32 arithmetic, one rounding per numpy operation
     const float sx = __fmul_rn(a.scale[n * 2 + 0], 200.0f), sy = __fmul_rn(a.scale[n * 2 + 1], 200.0f);
-    const float scx = __fdiv_rn(sx, (float)a.W), scy = __fdiv_rn(sy, (float)a.H);
+    // transform_preds: scale / output_size, or scale / (output_size - 1) with use_udp
+    const float scx = __fdiv_rn(sx, (float)(a.post == 3 ? a.W - 1 : a.W)), scy = __fdiv_rn(sy, (float)(a.post == 3 ? a.H - 1 : a.H));
     const float ox = __fsub_rn(__fadd_rn(__fmul_rn(fx, scx), a.center[n * 2 + 0]), __fmul_rn(sx, 0.5f));
     const float oy = __fsub_rn(__fadd_rn(__fmul_rn(fy, scy), a.center[n * 2 + 1]), __fmul_rn(sy, 0.5f));
     float* o = a.out + ((size_t)n * a.K + k) * 3;
@@ -168,7 +210,7 @@ cudaError_t launch_decode(const float* hm, const float* hm_flip, const int* flip
                           const float* gauss, cudaStream_t st) {
   const int smem = decode_smem_bytes(H, W);
   if (smem > 220 * 1024) return cudaErrorInvalidValue;
-  if (post == 2 && !gauss) return cudaErrorInvalidValue;
+  if ((post == 2 || post == 3) && !gauss) return cudaErrorInvalidValue;
   cudaError_t e = pe_smem_optin((const void*)decode_kernel, smem);
   if (e != cudaSuccess) return e;
   DecodeArgs a{hm, hm_flip, flip_perm, center, scale, out, gauss, K, H, W, shift, post, ksize};

@@ -328,6 +328,17 @@ static void box_to_affine(const pe_model_desc* d, const double* bbox, float* cen
   else if (w < aspect * h) w = h * aspect;
   scale[0] = ((float)w / d->pixel_std) * d->padding;
   scale[1] = ((float)h / d->pixel_std) * d->padding;
+  if (d->reserved & PE_MODEL_FLAG_UDP) {
+    // TopDownAffine(use_udp=True): get_warp_matrix(0, center * 2.0, image_size - 1.0, scale * 200.0) -> float32 2x3 (A.4)
+    const double in0 = (double)(center[0] * 2.0f), in1 = (double)(center[1] * 2.0f);
+    const double dst0 = (double)d->in_w - 1.0, dst1 = (double)d->in_h - 1.0;
+    const double tg0 = (double)(scale[0] * 200.0f), tg1 = (double)(scale[1] * 200.0f);
+    const double sx = dst0 / tg0, sy = dst1 / tg1;
+    const float m[6] = {(float)(1.0 * sx), (float)(-0.0 * sx), (float)(sx * (-0.5 * in0 * 1.0 + 0.5 * in1 * 0.0 + 0.5 * tg0)),
+                        (float)(0.0 * sy), (float)(1.0 * sy), (float)(sy * (-0.5 * in0 * 0.0 - 0.5 * in1 * 1.0 + 0.5 * tg1))};
+    for (int i = 0; i < 6; ++i) trans[i] = (double)m[i];
+    return;
+  }
   // mmpose get_affine_transform(center, scale, rot=0, image_size) (A.1 step 4)
   const float src_w = scale[0] * 200.0f;
   float src[3][2], dst[3][2];
@@ -430,6 +441,7 @@ struct pe_model {
   float* d_hm = nullptr;        // [2*max][K][hh][hw]
   float* d_out = nullptr;       // [max][K][3]
   float* d_gauss = nullptr;     // [64] 1-D Gaussian taps of this model's modulate_kernel
+  std::vector<float*> const_res;    // per op: tiled per-token constant added through the GEMM residual path (position embedding)
   unsigned int* d_flag = nullptr;   // range flag: kernels OR 1 into it when an activation does not fit the operand format
   unsigned int* h_flag = nullptr;   // pinned copy, read with every result
   // pinned staging
@@ -450,6 +462,8 @@ struct pe_model {
 };
 
 static float* act_ptr(pe_model* m, int tid) { return m->slots[m->tensors[tid].slot]; }
+// rows per image of a tensor: padded 2-D grid, or (W == 0) a flat token matrix of H rows
+static long long rows_per_img(const pe_tensor_desc& t) { return t.W ? (long long)(t.H + 2) * (t.W + 2) : (long long)t.H; }
 
 static void gauss_taps(int k, float* out) {
   // cv2.getGaussianKernel(k, sigma<=0 -> 0.3*((k-1)*0.5-1)+0.8, CV_32F): computed in double, normalised, cast
@@ -468,6 +482,7 @@ static void model_free(pe_model* m, bool cuda_ok) {
     cudaStreamSynchronize(m->e->stream);
     for (auto& g : m->graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
     for (auto* p : m->slots) if (p) cudaFree(p);
+    for (auto* p : m->const_res) if (p) cudaFree(p);
     cudaFree(m->d_w); cudaFree(m->d_s2d); cudaFree(m->d_lut); cudaFree(m->d_perm); cudaFree(m->d_crops); cudaFree(m->d_minv);
     cudaFree(m->d_fidx); cudaFree(m->d_cs); cudaFree(m->d_hm); cudaFree(m->d_out); cudaFree(m->d_gauss); cudaFree(m->d_flag);
     cudaFreeHost(m->h_flag); cudaFreeHost(m->h_minv); cudaFreeHost(m->h_fidx); cudaFreeHost(m->h_cs); cudaFreeHost(m->h_out);
@@ -496,7 +511,7 @@ extern "C" int pe_model_create(pe_engine* e, const pe_model_desc* desc, const pe
   ENGINE_ALIVE(e);
   pe_range_flag() = nullptr;      // plan creation launches candidate tilings on uninitialised buffers
   if (desc->max_crops <= 0 || desc->n_ops <= 0) return fail(PE_ERR_INVALID, "bad model description");
-  if (desc->post_process == PE_POST_UNBIASED && (desc->blur_kernel < 3 || desc->blur_kernel > 63 || desc->blur_kernel % 2 == 0))
+  if ((desc->post_process == PE_POST_UNBIASED || desc->post_process == PE_POST_UDP) && (desc->blur_kernel < 3 || desc->blur_kernel > 63 || desc->blur_kernel % 2 == 0))
     return fail(PE_ERR_INVALID, "blur kernel must be odd and in [3,63]");
   CU(cudaSetDevice(e->device));
   pe_model* m = new pe_model();
@@ -537,7 +552,7 @@ extern "C" int pe_model_create(pe_engine* e, const pe_model_desc* desc, const pe
   {
     // Gaussian taps of THIS model's modulate_kernel (a device buffer per model: two models with different kernels coexist)
     float taps[64] = {0};
-    if (desc->post_process == PE_POST_UNBIASED) gauss_taps(desc->blur_kernel, taps);
+    if (desc->post_process == PE_POST_UNBIASED || desc->post_process == PE_POST_UDP) gauss_taps(desc->blur_kernel, taps);
     CUM(cudaMalloc(&m->d_gauss, sizeof taps));
     CUM(cudaMemcpyAsync(m->d_gauss, taps, sizeof taps, cudaMemcpyHostToDevice, e->stream));
     CUM(cudaStreamSynchronize(e->stream));       // `taps` is a stack buffer
@@ -556,8 +571,36 @@ extern "C" int pe_model_create(pe_engine* e, const pe_model_desc* desc, const pe
     }
     if (s2d_floats) { CUM(cudaMalloc(&m->d_s2d, s2d_floats * sizeof(float))); CUM(cudaMemsetAsync(m->d_s2d, 0, s2d_floats * sizeof(float), e->stream)); }
     CUM(cudaStreamSynchronize(e->stream));   // weights and zeroed slots are in place: plan creation times candidate tilings on them
+    m->const_res.assign(desc->n_ops, nullptr);
     for (int i = 0; i < desc->n_ops; ++i) {
       const pe_op_desc& op = m->ops[i];
+      if (op.kind == PE_OP_GEMM) {
+        if (op.wtc_off < 0) { int rc = fail(PE_ERR_INVALID, "GEMM op %d has no tensor-core weights", i); model_free(m, true); return rc; }
+        const pe_tensor_desc& to = m->tensors[op.out];
+        const pe_tensor_desc& ti = m->tensors[op.in[0]];
+        const long long rows = rows_per_img(to) * maximg;
+        const float* res = op.residual >= 0 ? act_ptr(m, op.residual) : nullptr;
+        if (op.reserved == 1) {           // per-token constant (position embedding), tiled once for the largest batch
+          CUM(cudaMalloc(&m->const_res[i], (size_t)rows * ps_row_floats(op.cout) * sizeof(float)));
+          launch_tile_rows(m->d_w + op.w_off, (int)rows_per_img(to), op.cout, maximg, m->const_res[i], e->stream);
+          CUM(cudaStreamSynchronize(e->stream));
+          res = m->const_res[i];
+        }
+        TcConvDesc c{};
+        c.kind = TC_KIND_LIN1; c.Cin = op.cin; c.Cout = op.cout; c.act = op.relu; c.max_rows = rows;
+        c.in = act_ptr(m, op.in[0]); c.in_total = ti.C; c.in_coff = 0;
+        c.out = act_ptr(m, op.out); c.out_total = to.C; c.out_coff = 0;
+        c.res = res; c.res_total = op.cout; c.res_coff = 0;
+        c.wtc = m->d_w + op.wtc_off; c.bias = m->d_w + op.b_off;
+        const cudaError_t ce = tc_conv_plan_create_ex(&m->tc[i], &c);
+        if (ce != cudaSuccess) {
+          int rc = fail(PE_ERR_CUDA, "tensor-core plan for GEMM op %d (%d -> %d) failed: %s", i, op.cin, op.cout, cudaGetErrorString(ce));
+          cudaGetLastError();
+          model_free(m, true);
+          return rc;
+        }
+        continue;
+      }
       if (op.kind != PE_OP_CONV || op.wtc_off < 0) continue;
       if (op.stride == 2 && op.ksize != 3) continue;
       const pe_tensor_desc& to = m->tensors[op.out];
@@ -634,7 +677,7 @@ static int forward_eager(pe_model* m, int ncrop, int nimg) {
   for (size_t i = 0; i < m->ops.size(); ++i) {
     const pe_op_desc& op = m->ops[i];
     const pe_tensor_desc& to = m->tensors[op.out];
-    const bool is_conv = (op.kind == PE_OP_CONV);
+    const bool is_conv = (op.kind == PE_OP_CONV || op.kind == PE_OP_GEMM);
     const bool timed = m->profile && (is_conv || m->profile > 1);
     if (timed) {
       if (m->ev_used == m->ev_conv.size()) {
@@ -676,6 +719,33 @@ static int forward_eager(pe_model* m, int ncrop, int nimg) {
         launch_head(act_ptr(m, op.in[0]), op.cin, ti.H, ti.W, nimg, m->d_w + op.w_off, m->d_w + op.b_off, op.cout, m->d_hm, st);
         break;
       }
+      case PE_OP_PATCH:
+        launch_patchify(m->d_crops, ncrop, nimg, d.in_h, d.in_w, m->d_lut, op.ksize, op.stride, d.in_h / op.ksize, d.in_w / op.ksize, act_ptr(m, op.out), st);
+        break;
+      case PE_OP_GEMM: {
+        if (!m->tc[i]) return fail(PE_ERR_STATE, "GEMM op %zu has no tensor-core plan (models with Linear layers need use_tensor_cores = 1)", i);
+        const cudaError_t ce = tc_conv_launch_rows(m->tc[i], rows_per_img(to) * nimg, st);
+        if (ce != cudaSuccess) return fail(PE_ERR_CUDA, "GEMM op %zu: %s", i, cudaGetErrorString(ce));
+        break;
+      }
+      case PE_OP_LN: {
+        const pe_tensor_desc& ti = m->tensors[op.in[0]];
+        const cudaError_t ce = launch_layernorm(act_ptr(m, op.in[0]), m->d_w + op.w_off, m->d_w + op.b_off, powf(10.f, -(float)op.up[1]), op.cout, nimg, ti.H,
+                                                to.H, to.W, op.up[0], act_ptr(m, op.out), st);
+        if (ce != cudaSuccess) return fail(PE_ERR_CUDA, "LayerNorm op %zu: %s", i, cudaGetErrorString(ce));
+        break;
+      }
+      case PE_OP_ATTN: {
+        const pe_tensor_desc& ti = m->tensors[op.in[0]];
+        const cudaError_t ce = launch_attention(act_ptr(m, op.in[0]), nimg, ti.H, op.cin, 1.0f / sqrtf((float)(op.cout / op.cin)), act_ptr(m, op.out), st);
+        if (ce != cudaSuccess) return fail(PE_ERR_CUDA, "attention op %zu: %s", i, cudaGetErrorString(ce));
+        break;
+      }
+      case PE_OP_D2S: {
+        const pe_tensor_desc& ti = m->tensors[op.in[0]];
+        launch_d2s(act_ptr(m, op.in[0]), op.cout, ti.H, ti.W, nimg, act_ptr(m, op.out), st);
+        break;
+      }
       default:
         return fail(PE_ERR_INVALID, "unknown op kind %d", op.kind);
     }
@@ -696,7 +766,7 @@ static int profile_collect(pe_model* m) {
     CU(cudaEventElapsedTime(&ms, m->ev_conv[i].first, m->ev_conv[i].second));
     if (m->op_ms.size() < m->ops.size()) m->op_ms.assign(m->ops.size(), 0.0);
     m->op_ms[m->ev_op[i]] += ms;
-    if (m->ops[m->ev_op[i]].kind == PE_OP_CONV) { m->acc_conv_ms += ms; ++m->acc_conv_launches; }
+    if (m->ops[m->ev_op[i]].kind == PE_OP_CONV || m->ops[m->ev_op[i]].kind == PE_OP_GEMM) { m->acc_conv_ms += ms; ++m->acc_conv_launches; }
   }
   CU(cudaEventElapsedTime(&ms, m->ev_fwd0, m->ev_fwd1));
   m->acc_total_ms += ms;
@@ -869,6 +939,24 @@ extern "C" int pe_debug_tensor(pe_model* m, int32_t tensor_id, int32_t img, floa
   if (img < 0 || img >= m->nimg_last) return fail(PE_ERR_STATE, "image %d not in the last forward batch (%d images)", img, m->nimg_last);
   CU(cudaSetDevice(m->e->device));
   const pe_tensor_desc& t = m->tensors[tensor_id];
+  if (t.W == 0) {                       // flat token matrix: -> [H tokens][C] row-major
+    const int rowF = ps_row_floats(t.C);
+    std::vector<float> host((size_t)t.H * rowF);
+    CU(cudaMemcpyAsync(host.data(), act_ptr(m, tensor_id) + (size_t)img * t.H * rowF, host.size() * sizeof(float), cudaMemcpyDeviceToHost, m->e->stream));
+    CU(cudaStreamSynchronize(m->e->stream));
+    for (int r = 0; r < t.H; ++r)
+      for (int c = 0; c < t.C; ++c) {
+        const float* row = host.data() + (size_t)r * rowF;
+#if PE_FP16
+        const __half* hp = reinterpret_cast<const __half*>(reinterpret_cast<const char*>(row) + (c >> 4) * 64);
+        out_chw[(size_t)r * t.C + c] = __half2float(hp[c & 15]) + __half2float(hp[16 + (c & 15)]) * PS_LO_INV;
+#else
+        const float* fp = row + (c >> 4) * 32;
+        out_chw[(size_t)r * t.C + c] = fp[c & 15] + fp[16 + (c & 15)];
+#endif
+      }
+    return PE_OK;
+  }
   float* tmp = nullptr;
   const size_t nel = (size_t)t.C * t.H * t.W;
   CU(cudaMalloc(&tmp, nel * sizeof(float)));

@@ -28,6 +28,14 @@ void launch_det_input(const uint8_t* frames, const int32_t* frame_idx, int fh, i
                       const int16_t* alpha, const int32_t* yofs, const int16_t* beta, float pad_val, int nimg, float* out, cudaStream_t st);
 void launch_det_head(const float* cls_feat, const float* reg_feat, int C, int H, int W, int nimg, const float* w, const float* b, float stride,
                      const float* scale_factor4, float score_thr, int prior_base, float* cand, int* count, int cap, float* raw, cudaStream_t st);
+// ViTPose (vit.cu)
+void launch_patchify(const uint8_t* crops, int ncrop, int nimg, int ih, int iw, const float* lut, int patch, int pad, int th, int tw, float* out,
+                     cudaStream_t st);
+void launch_tile_rows(const float* table, int tokens, int C, int nimg, float* out, cudaStream_t st);
+cudaError_t launch_layernorm(const float* in, const float* gamma, const float* beta, float eps, int C, int nimg, int tokens, int H, int W, int grid2d,
+                             float* out, cudaStream_t st);
+cudaError_t launch_attention(const float* qkv, int nimg, int T, int heads, float scale, float* out, cudaStream_t st);
+void launch_d2s(const float* in, int C, int H, int W, int nimg, float* out, cudaStream_t st);
 void launch_chw_to_ps(const float* in, int C, int H, int W, int nimg, float* out, cudaStream_t st);
 
 // Range flag of the forward being launched on this thread (device word; nullptr = no checking).  The launchers below pass
@@ -53,7 +61,7 @@ enum { TC_KIND_1x1 = 1, TC_KIND_2x2 = 2, TC_KIND_3x3 = 3, TC_KIND_LIN1 = 11, TC_
 struct TcConvDesc {
   int kind;                // TC_KIND_*: 3x3 pad 1 / 1x1 / 2x2 (stride-2 3x3 in space-to-depth form) over padded 2-D tensors;
                            // LIN3 = 3 taps at rows m, m+dil, m+2*dil and LIN1 = plain GEMM over flat row matrices (no zero border)
-  int Cin, Cout, act, dil; // act: 0 none, 1 ReLU, 2 SiLU
+  int Cin, Cout, act, dil; // act: 0 none, 1 ReLU, 2 SiLU, 3 GELU (erf)
   int H, W;                // 2-D kinds: output (= input) height / width
   long long max_rows;      // rows of the flat output matrix (2-D kinds: max_img * (H+2) * (W+2))
   const float* in; int in_total, in_coff;           // input tensor, its channel count, first channel of the view

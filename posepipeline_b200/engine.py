@@ -16,6 +16,7 @@ import numpy as np
 from . import _lib
 from ._lib import ModelDesc, OpDesc, TensorDesc, check, ptr
 from .hrnet_spec import OP_CONV, OP_FUSE, OP_HEAD, OP_STEM, Program, build_program
+from .vit_spec import OP_ATTN, OP_D2S, OP_GEMM, OP_LN, OP_PATCH, build_vitpose_program
 from .weights import bn_of, fold_bn
 
 COCO_FLIP_PAIRS = [[1, 2], [3, 4], [5, 6], [7, 8], [9, 10], [11, 12], [13, 14], [15, 16]]
@@ -38,6 +39,7 @@ class TopDownSpec:
     mean: Tuple[float, float, float] = (0.485, 0.456, 0.406)
     std: Tuple[float, float, float] = (0.229, 0.224, 0.225)
     wrapper_double_swap: bool = True
+    use_udp: bool = False                          # TopDownAffine(use_udp=True) + post_dark_udp decode (ViTPose configs)
     checkpoint: Optional[str] = None               # path under MODEL_DATA_DIR (reference wrappers/mmpose.py:33-52)
     config: Optional[str] = None                   # mmcv config path under MODEL_DATA_DIR (same lines)
 
@@ -66,6 +68,11 @@ METHODS: Dict[str, TopDownSpec] = {
                                    config="mmpose/config/halpe/hrnet_w48_halpe_384x288_dark_plus.py",
                                    checkpoint="mmpose/checkpoints/hrnet_w48_halpe_384x288_dark_plus-d13c2588_20211021.pth"),
     # BASELINE config 1 (upstream hrnet_w32_coco_256x192.py; not configured in the reference)
+    # BASELINE configs[2] (upstream ViTPose_base_coco_256x192.py; not configured in the reference)
+    "ViTPose_B_COCO": TopDownSpec(variant="vitpose_b", image_size=(192, 256), heatmap_size=(48, 64), post_process="udp",
+                                  shift_heatmap=False, modulate_kernel=11, use_udp=True,
+                                  config="mmpose/config/top_down/vitpose/coco/ViTPose_base_coco_256x192.py",
+                                  checkpoint="mmpose/checkpoints/vitpose-b.pth"),
     "HRNet_W32_COCO": TopDownSpec(variant="w32", image_size=(192, 256), heatmap_size=(48, 64), post_process="default",
                                   modulate_kernel=11, config="mmpose/config/top_down/hrnet/coco/hrnet_w32_coco_256x192.py",
                                   checkpoint="mmpose/checkpoints/hrnet_w32_coco_256x192-c78dce93_20200708.pth"),
@@ -83,6 +90,27 @@ def spec_for(method: str, model_data_dir: str = "") -> TopDownSpec:
         from .mmcv_config import load_config, topdown_settings
         return dataclasses.replace(base, **topdown_settings(load_config(path)))
     return base
+
+
+def program_for(spec: "TopDownSpec") -> Program:
+    if spec.variant == "vitpose_b":
+        return build_vitpose_program(spec.image_size[1], spec.image_size[0], spec.num_joints)
+    return build_program(spec.variant, spec.image_size[1], spec.image_size[0], spec.num_joints)
+
+
+def deconv_as_conv_weights(w: np.ndarray) -> np.ndarray:
+    """ConvTranspose2d(k4, s2, p1) weights (Cin, Cout, 4, 4) -> the equivalent 3x3 stride-1 convolution (4*Cout, Cin, 3, 3) whose
+    output channel block (py*2+px) holds output pixels (2a+py, 2b+px): out[2a+py] takes taps ky with (2a+py+1-ky) even,
+    i.e. py=0: ky=1 (input row a), ky=3 (row a-1); py=1: ky=0 (row a+1), ky=2 (row a).  csrc/vit.cu d2s_kernel interleaves."""
+    cin, cout = w.shape[:2]
+    out = np.zeros((4, cout, cin, 3, 3), w.dtype)
+    taps = {0: ((1, 1), (3, 0)), 1: ((0, 2), (2, 1))}          # parity -> ((k, 3x3 tap index) ...): tap index = input offset + 1
+    for py in range(2):
+        for px in range(2):
+            for ky, ty in taps[py]:
+                for kx, tx in taps[px]:
+                    out[py * 2 + px, :, :, ty, tx] = w[:, :, ky, kx].T
+    return out.reshape(4 * cout, cin, 3, 3)
 
 
 def tf32_split(x: np.ndarray):
@@ -269,7 +297,7 @@ def model_desc(spec: TopDownSpec, n_ops=0, n_tensors=0, n_slots=0, max_crops=1, 
                      num_joints=spec.num_joints, n_ops=n_ops, n_tensors=n_tensors, n_slots=n_slots, max_crops=max_crops,
                      flip_test=int(spec.flip_test), shift_heatmap=int(spec.shift_heatmap),
                      post_process=_lib.PE_POST[spec.post_process], blur_kernel=spec.modulate_kernel,
-                     swap_rb=0 if spec.wrapper_double_swap else 1, use_tensor_cores=int(use_tc), reserved=0,
+                     swap_rb=0 if spec.wrapper_double_swap else 1, use_tensor_cores=int(use_tc), reserved=int(spec.use_udp),
                      padding=spec.padding, pixel_std=200.0)
 
 
@@ -290,9 +318,9 @@ class TopDownModel:
                  use_tensor_cores: bool = True, unique_slots: bool = False):
         self.engine, self.spec, self.lib = engine, spec, engine.lib
         self.max_crops = max_crops
-        prog = build_program(spec.variant, spec.image_size[1], spec.image_size[0], spec.num_joints)
+        prog = program_for(spec)
         self.program = prog
-        missing = [k for k in prog.params if k not in state_dict]
+        missing = [k for k in prog.params if k not in state_dict and not k.endswith("num_batches_tracked")]
         if missing:
             raise KeyError(f"checkpoint is missing {len(missing)} tensors, e.g. {missing[:3]}")
         blob = WeightBlob()
@@ -308,8 +336,32 @@ class TopDownModel:
             o.relu, o.residual, o.reserved = int(op.relu), op.residual, 0
             o.w_off = o.b_off = 0
             o.wtc_off = -1
+            if op.kind == OP_GEMM:                                   # Linear (or the patch-embedding conv as a GEMM)
+                w = np.asarray(state_dict[f"{op.conv}.weight"], np.float32).reshape(op.cout, op.cin)
+                o.b_off = blob.add(np.asarray(state_dict[f"{op.conv}.bias"], np.float32))
+                o.wtc_off = blob.add(pack_tc_weights(w[:, :, None]))
+                if getattr(op, "const_table", None):                 # x + pos_embed[:, 1:] + pos_embed[:, :1]
+                    pos = np.asarray(state_dict[op.const_table], np.float32)
+                    o.w_off = blob.add((pos[0, 1:] + pos[0, :1]).astype(np.float32))
+                    o.reserved = 1
+                continue
+            if op.kind == OP_LN:
+                o.w_off = blob.add(np.asarray(state_dict[f"{op.conv}.weight"], np.float32))
+                o.b_off = blob.add(np.asarray(state_dict[f"{op.conv}.bias"], np.float32))
+                continue
+            if op.kind in (OP_PATCH, OP_ATTN, OP_D2S):
+                continue
             if op.kind in (OP_STEM, OP_CONV, OP_HEAD):
                 w = state_dict[f"{op.conv}.weight"]
+                if getattr(op, "deconv", False):
+                    w = deconv_as_conv_weights(np.asarray(w, np.float32))
+                    bn = bn_of(state_dict, op.bn)
+                    bn = {k: np.tile(v, 4) for k, v in bn.items()}                   # the same BN for each of the 4 parity blocks
+                    wf, bf = fold_bn(w, bn, None)
+                    o.b_off = blob.add(bf)
+                    o.w_off = 0
+                    o.wtc_off = blob.add(pack_tc_weights(wf))
+                    continue
                 cb = state_dict.get(f"{op.conv}.bias") if op.has_bias else None
                 wf, bf = fold_bn(w, bn_of(state_dict, op.bn) if op.bn else None, cb)
                 k = op.ksize
@@ -325,7 +377,7 @@ class TopDownModel:
                         o.wtc_off = blob.add(pack_tc_weights(space_to_depth_weights(wf)))
         if unique_slots:
             slot_of = list(range(len(prog.tensors)))
-            slot_elems = [(t.H + 2) * (t.W + 2) * t.C for t in prog.tensors]
+            slot_elems = [((t.H + 2) * (t.W + 2) if t.W else t.H) * t.C for t in prog.tensors]
         else:
             slot_of, slot_elems = prog.assign_slots()
         tens = (TensorDesc * len(prog.tensors))()
@@ -393,7 +445,7 @@ class TopDownModel:
 
     def debug_tensor(self, tensor_id: int, img: int = 0) -> np.ndarray:
         t = self.program.tensors[tensor_id]
-        out = np.empty((t.C, t.H, t.W), np.float32)
+        out = np.empty((t.C, t.H, t.W) if t.W else (t.H, t.C), np.float32)      # W == 0: token matrix [tokens][C]
         check(self.lib.pe_debug_tensor(self.h, tensor_id, img, ptr(out)))
         return out
 

@@ -106,7 +106,7 @@ class Program:
     def assign_slots(self):
         """Returns (slot_of_tensor, slot_elems_per_image) where elems counts padded pixels * C."""
         def elems(t):
-            return (t.H + 2) * (t.W + 2) * t.C
+            return ((t.H + 2) * (t.W + 2) if t.W else t.H) * t.C      # W == 0: flat token matrix of H rows
         slots: List[Tuple[int, int]] = []       # (free_after_op, size)
         slot_of = [-1] * len(self.tensors)
         order = sorted(self.tensors, key=lambda t: t.first_def)

@@ -149,3 +149,44 @@ def synthetic_videopose3d_state_dict(seed: int = 0, channels: int = 1024) -> Dic
         elif leaf == "running_var":
             sd[name] = (r.random(shape) * 0.5 + 0.75).astype(np.float32)
     return sd
+
+
+# ------------------------------------------------------------------ ViTPose-B (App. A.4)
+def synthetic_vitpose_state_dict(program: Program, seed: int = 0, calibrated: bool = True) -> Dict[str, np.ndarray]:
+    """Seeded ViTPose-B tensors under the upstream key names (there is no checkpoint offline).  Linear layers get
+    a ViT-style N(0, s^2) initialisation scaled so the residual stream stays O(1) over the 12 blocks; LayerNorm affine
+    parameters are perturbed around (1, 0) so they are exercised.  With ``calibrated`` the 1x1 final layer comes from the
+    committed fixture (tests/golden/make_synth_calibration.py) that turns the head features into sparse, peaky heatmaps."""
+    sd: Dict[str, np.ndarray] = {}
+    for name, shape in program.params.items():
+        parent, leaf = name.rsplit(".", 1)
+        r = _rng(name, seed)
+        if leaf == "num_batches_tracked":
+            sd[name] = np.zeros((), np.int64)
+        elif name.endswith("pos_embed"):
+            sd[name] = (r.standard_normal(shape) * 0.2).astype(np.float32)
+        elif "deconv_layers" in parent and len(shape) == 4:
+            fan_in = shape[0] * 4                                    # ConvTranspose k4 s2: 4 taps of every input channel per output pixel
+            sd[name] = (r.standard_normal(shape) * math.sqrt(2.0 / fan_in)).astype(np.float32)
+        elif len(shape) in (2, 4):
+            fan_in = int(np.prod(shape[1:]))
+            gain = 0.5 if (parent.endswith("attn.proj") or parent.endswith("mlp.fc2")) else 1.0    # damp the residual branches
+            sd[name] = (r.standard_normal(shape) * gain / math.sqrt(fan_in)).astype(np.float32)
+        elif leaf == "weight":
+            sd[name] = (r.random(shape) * 0.4 + 0.8).astype(np.float32)
+        elif leaf == "bias":
+            sd[name] = ((r.random(shape) - 0.5) * 0.2).astype(np.float32)
+        elif leaf == "running_mean":
+            sd[name] = ((r.random(shape) - 0.5) * 0.2).astype(np.float32)
+        elif leaf == "running_var":
+            sd[name] = (r.random(shape) * 0.5 + 0.75).astype(np.float32)
+        else:
+            raise KeyError(name)
+    if calibrated:
+        key = f"vitpose_b_{program.in_h}x{program.in_w}_k{program.num_joints}_s{seed}"
+        z = np.load(_CALIB)
+        if f"{key}/head_weight" not in z.files:
+            raise KeyError(f"no synthetic head calibration for {key}; run tests/golden/make_synth_calibration.py")
+        sd["keypoint_head.final_layer.weight"] = z[f"{key}/head_weight"].astype(np.float32)
+        sd["keypoint_head.final_layer.bias"] = z[f"{key}/head_bias"].astype(np.float32)
+    return sd

@@ -74,8 +74,42 @@ def calibrate(variant, in_h, in_w, K, seed, cfg, n_crops=10, q=0.995):
             "head_bias": hb}
 
 
+def calibrate_vitpose(seed=0, K=17, n_crops=10, q=0.995):
+    """ViTPose-B: the head features are ReLU outputs (256 channels at 64x48); a sparse positive 1x1 final layer over 8 of them
+    per joint, biased by the 99.5 % quantile of its own output so only the tips of the blobs are positive, scaled to O(1)."""
+    from posepipeline_b200.vit_spec import build_vitpose_program
+    from oracle.vitpose import load_net as load_vit
+    prog = build_vitpose_program(256, 192, K)
+    sd = W.synthetic_vitpose_state_dict(prog, seed, calibrated=False)
+    net = load_vit(sd)
+    cfg = T.VITPOSE_B_COCO
+    frames = synthetic_frames(3, seed0=100)
+    bbs = synthetic_bboxes(n_crops, seed=4321)
+    xs = []
+    for i in range(n_crops):
+        x, _, _, _ = T.preprocess(cv2.cvtColor(frames[i % 3], cv2.COLOR_BGR2RGB), bbs[i], cfg)
+        xs += [torch.from_numpy(x), torch.from_numpy(x).flip(2)]
+    with torch.no_grad():
+        feat = net.keypoint_head.deconv_layers(net.backbone(torch.stack(xs)))
+    C = feat.shape[1]
+    rng = np.random.default_rng(seed + K)
+    hw = np.zeros((K, C), np.float32)
+    for k in range(K):
+        hw[k, rng.choice(C, 8, replace=False)] = rng.uniform(0.5, 1.0, 8)
+    raw = torch.einsum("kc,bchw->bkhw", torch.from_numpy(hw), feat)
+    thr = torch.quantile(raw.permute(1, 0, 2, 3).reshape(K, -1)[:, ::3], q, dim=1)
+    hm = raw - thr[None, :, None, None]
+    mx = hm.flatten(2).max(dim=2).values.median(dim=0).values.numpy()
+    mx = np.where(mx > 0, mx, 1.0)
+    s = 0.85 / mx
+    return {"head_weight": (hw * s[:, None]).reshape(K, C, 1, 1).astype(np.float32), "head_bias": (-thr.numpy() * s).astype(np.float32)}
+
+
 if __name__ == "__main__":
     out = {}
+    for k, v in calibrate_vitpose().items():
+        out[f"vitpose_b_256x192_k17_s0/{k}"] = v
+    print("vitpose_b", {k: v.shape for k, v in out.items()})
     for variant, h, w, K, seed, cfg in [("w48", 384, 288, 17, 0, T.HRNET_W48_COCO),
                                         ("w48", 384, 288, 133, 0, T.HRNET_W48_COCO),
                                         ("w48", 384, 288, 136, 0, T.HRNET_W48_COCO),
