@@ -174,6 +174,7 @@ def test_topdown_end_to_end_keypoints(eng, model, sd):
     d = np.abs(got[..., :2] - ref["float32"][..., :2]).max(-1)
     print(f"vitpose keypoint |dx| px: UNCONDITIONAL max {d.max():.2e} | max over well-conditioned {d[good].max():.2e} well-conditioned {good.mean():.3f} "
           f"oracle fp32-vs-fp64 max {cond.max():.2e}")
+    assert (ref["float32"][..., 2] > 0.05).all()                    # real peaks: no keypoint sits at the degenerate (-1, -1)
     assert good.mean() >= 0.9 and d[good].max() <= 1e-3
     assert np.all(d[~good] <= 10 * cond[~good] + 1e-3)
     assert np.abs(got[..., 2] - ref["float32"][..., 2]).max() <= 1e-4 * max(1.0, np.abs(ref["float32"][..., 2]).max())
