@@ -73,9 +73,9 @@ def get_model(method: str):
             from ..weights import load_checkpoint
             sd = load_checkpoint(ckpt)
         elif os.environ.get("PE_SYNTHETIC_WEIGHTS") == "1":
-            from ..hrnet_spec import build_program
-            from ..weights import synthetic_hrnet_state_dict
-            sd = synthetic_hrnet_state_dict(build_program(spec.variant, spec.image_size[1], spec.image_size[0], spec.num_joints), 0)
+            from ..weights import synthetic_hrnet_state_dict, synthetic_vitpose_state_dict
+            prog = E.program_for(spec)
+            sd = synthetic_vitpose_state_dict(prog, 0) if spec.variant == "vitpose_b" else synthetic_hrnet_state_dict(prog, 0)
         else:
             raise FileNotFoundError(f"{ckpt} not found (set PE_SYNTHETIC_WEIGHTS=1 to run with seeded synthetic weights)")
         _models[method] = E.TopDownModel(get_engine(), sd, spec, max_crops=int(os.environ.get("PE_MAX_CROPS", "32")))
@@ -86,7 +86,7 @@ def mmpose_top_down_person(key, method='HRNet_W48_COCO'):
     from pose_pipeline import Video, PersonBbox      # the reference's own tables (pipeline.py:24, :648)
 
     if method in _REFERENCE_ONLY:
-        raise NotImplementedError(f"top-down method {method} is not built in this engine yet (HRNet_W48_COCO / _COCOWholeBody / _HALPE and HRNet_W32_COCO are)")
+        raise NotImplementedError(f"top-down method {method} is not built in this engine yet (HRNet_W48_COCO / _COCOWholeBody / _HALPE, HRNet_W32_COCO and ViTPose_B_COCO are)")
     if method not in E.METHODS:
         # the reference falls through its if/elif chain and dies on an unbound `pose_cfg`
         raise UnboundLocalError(f"cannot access local variable 'pose_cfg': unknown top-down method {method!r}")
