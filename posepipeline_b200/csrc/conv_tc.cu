@@ -85,6 +85,12 @@ struct TcParams {
   uint32_t a_bytes, stage_bytes;
   unsigned int* flag;        // range flag of the forward (kernels.h pe_range_flag), or nullptr
   long long* prof;
+  // 2x2 layers (stride-2 3x3 convolutions in space-to-depth form): 7 of the 16 (tap, input parity) weight blocks are
+  // structurally zero (W'[(py,px,c)][dy][dx] = w[c][2dy+py][2dx+px] exists only for 2dy+py < 3 and 2dx+px < 3).  zmask holds
+  // 4 bits per 16-channel chunk, bit (dy*2+dx) set = that tap's weights of the chunk are all zero (found by READING the
+  // packed weights at plan creation, so any channel order / pruned block is handled): the MMA warps skip those steps.
+  // Adding an exact zero product leaves an accumulator unchanged, so the results are bit-identical.
+  uint32_t zmask[32];
 };
 
 // ------------------------------------------------------------------------------------------ PTX helpers
@@ -405,6 +411,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (roleX) {
       // ---------------- X: hi*hi into the rotating `main` accumulators
       uint32_t dg = 0, dgp = 0;             // drain-group buffer / phase
+      uint32_t fresh = 1u;                  // the current drain group's accumulator has not been written yet
       const int total_rows = p.nstage * KC * ROWS;
       int tile = blockIdx.x % p.tiles_m;
       for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
@@ -430,6 +437,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t empty_bar = bar_empty + 8 * r.idx;
 #pragma unroll
           for (int kc = 0; kc < KC; ++kc) {
+            const int jz = st * KC + kc;
+            const uint32_t zm = (TAPS == 4) ? ((p.zmask[(jz >> 3) & 31] >> ((jz & 7) * 4)) & 15u) : 0u;
 #pragma unroll
             for (int row = 0; row < ROWS; ++row) {
               if (rig == 0) {
@@ -443,12 +452,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #endif
               }
               const uint32_t d_main = tmem_base + dg * GC;
-              const uint32_t acc0 = (rig == 0) ? 0u : 1u;
+              if (rig == 0) fresh = 1u;         // no MMA has written this drain group's accumulator yet
               ++row_no;
               const bool close = (++rig == p.rpg) || (row_no == total_rows);
+              // 2x2 form: taps of this stencil row whose weights are all zero for this chunk are skipped -- except that a
+              // drain group must not close without a single MMA (its accumulator would hold stale sums)
+              uint32_t skip = 0u;
+              if (TAPS == 4) {
+                skip = (zm >> (row * TAPW)) & ((1u << TAPW) - 1u);
+                if (close && fresh && skip == ((1u << TAPW) - 1u)) skip &= ~1u;
+              }
               if (elect_one()) {
+                uint32_t fr = fresh;
 #pragma unroll
                 for (int t = 0; t < TAPW; ++t) {
+                  if (TAPS == 4 && ((skip >> t) & 1u)) continue;
 #pragma unroll
                   for (int mt = 0; mt < MT; ++mt) {
                     const uint32_t a = a_st + (uint32_t)kc * a16 + (uint32_t)row * wp16 + (uint32_t)(t * ROW16 + mt * 128 * ROW16);
@@ -456,13 +474,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                     for (int ks = 0; ks < KSTEPS; ++ks)
                       tc_mma_tf32(d_main + (uint32_t)(mt * NC), desc64(desc_hi, a + 2 * ks), desc64(desc_hi, b + 2 * ks), idesc,
-                                  (t == 0 && ks == 0) ? acc0 : 1u);   // hi * hi
+                                  (fr && ks == 0) ? 0u : 1u);   // hi * hi
                   }
+                  fr = 0u;
                 }
                 if (close) tc_commit(bar_main_full + 8 * dg);          // this drain group's partial sums are complete
                 if (kc == KC - 1 && row == ROWS - 1) tc_commit(empty_bar);   // stage free once these MMAs (and warp Y's) retire
               }
               __syncwarp();
+              if (skip != ((1u << TAPW) - 1u)) fresh = 0u;
               if (close) { rig = 0; if (++dg == NMAIN) { dg = 0; dgp ^= 1u; } }
             }
           }
@@ -485,6 +505,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           while (tile >= p.tiles_m) tile -= p.tiles_m;
         }
         const uint32_t cbuf = tl & 1u;
+        uint32_t freshY = 1u;               // nothing has been written to this tile's corr accumulator yet
 #if PE_TC_PROFILE
         { const long long cc = clock64();
 #endif
@@ -505,14 +526,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #endif
           const uint32_t a_st = ring_lo0 + r.idx * stage16 + a_off16;
           const uint32_t b_st = ring_lo0 + r.idx * stage16 + (uint32_t)KC * a16;
-          const uint32_t acc0 = (st == 0) ? 0u : 1u;
+          // 2x2 form: all-zero (tap, chunk) weight blocks are skipped (see TcParams::zmask); the first MMA that is issued for
+          // a tile overwrites the accumulator, and the tile's last step is never skipped while nothing has been issued
+          uint32_t zmst = 0u;
+          if (TAPS == 4) {
+#pragma unroll
+            for (int kc = 0; kc < KC; ++kc) {
+              const int jz = st * KC + kc;
+              zmst |= ((p.zmask[(jz >> 3) & 31] >> ((jz & 7) * 4)) & 15u) << (4 * kc);
+            }
+            if (st == p.nstage - 1 && freshY) zmst &= ~(1u << (4 * (KC - 1) + TAPS - 1));
+          }
           if (elect_one()) {
+            uint32_t fr = freshY;
 #pragma unroll
             for (int kc = 0; kc < KC; ++kc) {
 #pragma unroll
               for (int row = 0; row < ROWS; ++row) {
 #pragma unroll
                 for (int t = 0; t < TAPW; ++t) {
+                  if (TAPS == 4 && ((zmst >> (4 * kc + row * TAPW + t)) & 1u)) continue;
 #pragma unroll
                   for (int mt = 0; mt < MT; ++mt) {
                     const uint32_t a = a_st + (uint32_t)kc * a16 + (uint32_t)row * wp16 + (uint32_t)(t * ROW16 + mt * 128 * ROW16);
@@ -522,10 +555,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int ks = 0; ks < KSTEPS; ++ks) {
                       const uint32_t ak = a + 2 * ks, bk = b + 2 * ks;
                       tc_mma_tf32(d_corr + (uint32_t)(mt * NC), desc64(desc_hi, ak), desc64(desc_hi, bk + LO16), idesc,
-                                  (kc == 0 && row == 0 && t == 0 && ks == 0) ? acc0 : 1u);                                             // hi * lo
+                                  (fr && ks == 0) ? 0u : 1u);                                                                          // hi * lo
                       tc_mma_tf32(d_corr + (uint32_t)(mt * NC), desc64(desc_hi, ak + LO16), desc64(desc_hi, bk), idesc, 1u);            // lo * hi
                     }
                   }
+                  fr = 0u;
                 }
               }
             }
@@ -533,6 +567,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (st == p.nstage - 1) tc_commit(bar_corr_full + 8 * cbuf);   // every cross-term MMA of this tile has retired
           }
           __syncwarp();
+          if (TAPS != 4 || zmst != ((KC == 1) ? 0xFu : (KC == 2) ? 0xFFu : 0xFFFFu)) freshY = 0u;
           r.advance(p.S);
 #if PE_TC_PROFILE
           c_is += clock64() - c0;
@@ -1079,12 +1114,13 @@ static std::vector<TcCand> tc_enumerate(int kind, int Cin, int Cout, bool has_re
 }
 
 // tensor maps + kernel attributes of one candidate
-static cudaError_t tc_build(TcConvPlan* pl, const TcCand& c, const TcConvDesc& d, int num_sms) {
+static cudaError_t tc_build(TcConvPlan* pl, const TcCand& c, const TcConvDesc& d, int num_sms, const uint32_t* zmask = nullptr) {
   TcGeom g;
   tc_geom(d.kind, d.W, d.dil, &g);
   const int Hp = d.H + 2, Wp = d.W + 2, ntaps = g.ntaps, nchunk = d.Cin / 16, Cout = d.Cout;
   const long long Mmax = d.max_rows;
   pl->p = c.p;
+  for (int i = 0; i < 32; ++i) pl->p.zmask[i] = zmask ? zmask[i] : 0u;
   // weight blob = [per-channel scale 2^-k: Cout floats padded to 64][inverse 2^k: same][packed operand]
   const float* wpack = d.wtc + 2 * (((Cout + 63) / 64) * 64);
   pl->p.scale_pad = ((Cout + 63) / 64) * 64;
@@ -1183,6 +1219,24 @@ cudaError_t tc_conv_plan_create_ex(TcConvPlan** out, const TcConvDesc* dp) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
+  // 2x2 form: which (tap, 16-channel chunk) weight blocks are all zero (TcParams::zmask) -- read from the packed operand itself
+  uint32_t zmask[32] = {0};
+  if (d.kind == TC_KIND_2x2 && d.Cin / 16 <= 256 && env_int("PE_TC_ZSKIP", 1)) {
+    const int nchunk = d.Cin / 16;
+    const size_t blk = (size_t)d.Cout * CHB, total = 4 * (size_t)nchunk * blk;
+    std::vector<uint8_t> h(total);
+    cudaDeviceSynchronize();                                  // the weight upload may still be in flight on another stream
+    if (cudaMemcpy(h.data(), d.wtc + 2 * (((d.Cout + 63) / 64) * 64), total, cudaMemcpyDeviceToHost) != cudaSuccess) return cudaGetLastError();
+    int nz = 0;
+    for (int tap = 0; tap < 4; ++tap)
+      for (int j = 0; j < nchunk; ++j) {
+        const uint8_t* b = h.data() + ((size_t)tap * nchunk + j) * blk;
+        bool zero = true;
+        for (size_t i = 0; i < blk && zero; i += 8) zero = *reinterpret_cast<const uint64_t*>(b + i) == 0;
+        if (zero) { zmask[j >> 3] |= 1u << ((j & 7) * 4 + tap); ++nz; }
+      }
+    if (env_int("PE_TC_VERBOSE", 0)) fprintf(stderr, "conv_tc 2x2 Cin=%d Cout=%d: %d of %d (tap, chunk) weight blocks are zero and skipped\n", d.Cin, d.Cout, nz, 4 * nchunk);
+  }
   std::vector<TcCand> cands = tc_enumerate(d.kind, d.Cin, d.Cout, d.res != nullptr, d.H, d.W, d.dil, d.max_rows, num_sms, d.gather_src != nullptr);
   const int force_mt = env_int("PE_TC_MT", 0), force_ns = env_int("PE_TC_NS", 0), force_kc = env_int("PE_TC_KC", 0), force_seg = env_int("PE_TC_SEG", -1);
   cands.erase(std::remove_if(cands.begin(), cands.end(), [&](const TcCand& c) {
@@ -1208,7 +1262,7 @@ cudaError_t tc_conv_plan_create_ex(TcConvPlan** out, const TcConvDesc* dp) {
     std::vector<TcConvPlan> tmp(ntry);
     std::vector<float> ms_min(ntry, 1e30f);
     std::vector<char> ok(ntry, 0);
-    for (size_t i = 0; i < ntry; ++i) ok[i] = tc_build(&tmp[i], cands[i], d, num_sms) == cudaSuccess;
+    for (size_t i = 0; i < ntry; ++i) ok[i] = tc_build(&tmp[i], cands[i], d, num_sms, zmask) == cudaSuccess;
     // round-robin over the candidates (clock / cache drift hits all alike), minimum of the rounds; round 0 warms up
     unsigned int* const saved_flag = pe_range_flag();
     pe_range_flag() = nullptr;                            // candidate runs read uninitialised buffers
@@ -1240,7 +1294,7 @@ cudaError_t tc_conv_plan_create_ex(TcConvPlan** out, const TcConvDesc* dp) {
     tc_choices()[key] = tc_cand_id(cands[pick]);
   }
   TcConvPlan* pl = new TcConvPlan();
-  cudaError_t e = tc_build(pl, cands[pick], d, num_sms);
+  cudaError_t e = tc_build(pl, cands[pick], d, num_sms, zmask);
   if (e != cudaSuccess) { delete pl; return e; }
   pl->p.prof = nullptr;
 #if PE_TC_PROFILE
