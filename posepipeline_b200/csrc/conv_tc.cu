@@ -42,9 +42,16 @@
 constexpr uint32_t ROW16 = CHB / 16;          // 8 (tf32) / 4 (fp16)
 constexpr uint32_t LO16 = CHB / 32;           // 16-byte units from hi to lo: 4 / 2
 constexpr int KSTEPS = PE_FP16 ? 1 : 2;       // 16 x f16 = one K=16 MMA; 16 x tf32 = two K=8 MMAs
-constexpr int TC_THREADS = 512;
-constexpr int EPI_WARPS = 12;
-constexpr int EPI_PARTS = EPI_WARPS / 4;      // epilogue warps per TMEM lane quarter: they split the 16-column groups round-robin
+// Epilogue organisation (template parameter SETS):
+//   SETS = 1: 12 epilogue warps (three per TMEM lane quarter, splitting the 16-column groups) work on every tile; 16 warps / CTA.
+//   SETS = 2: two sets of 8 epilogue warps (two per quarter) take ALTERNATE tiles, 20 warps / CTA at 96 registers.  Measured with
+//             the cycle counters (profiles/r02_conv_tc_notes.md): a tile's final phase (bias / activation / split / TMA stores,
+//             ~3600-4500 clocks) kept the one set away from the next tile's drains, warp X ran out of `main` accumulators after two
+//             drain groups (~2000 clocks) and stalled 30-40 % of the time; with two sets one finishes tile t while the other
+//             drains tile t+1.
+__host__ __device__ constexpr int tc_threads(int sets) { return sets == 2 ? 640 : 512; }
+__host__ __device__ constexpr int epi_parts(int sets) { return sets == 2 ? 2 : 3; }      // epilogue warps per TMEM lane quarter within one set: they split the 16-column groups round-robin
+__host__ __device__ constexpr int epi_warps(int sets) { return 4 * epi_parts(sets) * sets; }
 constexpr int MAX_ACC_STEPS = 6;              // hi*hi MMA steps one TMEM accumulator may take before it is drained (see kernel)
 #ifndef PE_TC_PROFILE
 #define PE_TC_PROFILE 0                       // 1: per-CTA cycle counters of the two MMA warps (build flag; costs issue slots)
@@ -175,6 +182,62 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
       ::"r"(dst), "l"((uint64_t)tm), "r"(c0), "r"(c1), "r"(bar)
       : "memory");
 }
+// ---- CTA-pair (cta_group::2) variants.  A pair = a cluster of two CTAs on the two SMs of one TPC; the leader (cluster rank 0)
+// issues every MMA for both, each CTA supplies its own 128 A rows and HALF of the B tile (the weights), so each SM fetches
+// half of B per MMA; barrier signals that concern both CTAs are multicast by tcgen05.commit, and loads of either CTA report
+// their bytes to the LEADER's full barrier (only the leader's MMA warps wait on it).
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {      // shared::cta address -> shared::cluster address in CTA `rank`
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t bar_cluster, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(bar_cluster), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
+  // default semantics (as CUTLASS ClusterBarrier::arrive): an explicit .release.cluster cost ~900 clocks per arrive (measured:
+  // drains 1306 instead of 415 clocks); the TMEM reads it orders are already complete (tcgen05.wait::ld + fence::before_thread_sync)
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
+__device__ __forceinline__ void tma2_load_3d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, uint32_t bar_cluster) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(dst), "l"((uint64_t)tm), "r"(c0), "r"(c1), "r"(c2), "r"(bar_cluster)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_4d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint32_t bar_cluster) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+      ::"r"(dst), "l"((uint64_t)tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar_cluster)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar_cluster) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"((uint64_t)tm), "r"(c0), "r"(c1), "r"(bar_cluster)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit2(uint32_t bar) {      // arrives on the barrier at this offset in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma2(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+#if PE_FP16
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+#else
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n"
+#endif
+      "}\n"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -293,16 +356,25 @@ __device__ __forceinline__ uint64_t desc64(uint32_t hi, uint32_t lo) {
   return d;
 }
 
-template <int NG, int MT, int TAPS, int KC>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <int NG, int MT, int TAPS, int KC, int CG, int SETS>
+__global__ void __launch_bounds__(tc_threads(SETS), 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR, const TcParams p) {
+  // CG = 2: CTA pairs (launched as clusters of 2).  A work item is a PAIR of adjacent M tiles of one n-slice: CTA `rank` of the
+  // pair owns tile 2*item + rank (rows, activation window, accumulators, epilogue all its own, exactly as in the CG = 1 form)
+  // and loads the weight rows [rank*NC/2, (rank+1)*NC/2) of the n-slice; the leader's two MMA warps issue M = 256 MMAs.
   constexpr int NC = NG * 16 / MT;                 // output channels per CTA
+  constexpr int NCB = NC / CG;                     // weight rows (B-operand rows) this CTA holds
+  constexpr int EPI_WARPS = epi_warps(SETS), EPI_PARTS = epi_parts(SETS);
+  constexpr int SET_WARPS = EPI_WARPS / SETS;      // warps that drain one tile
+  const uint32_t rank = (CG == 2) ? (blockIdx.x & 1u) : 0u;
+  const int wfirst = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;      // first work item, stride of the persistent schedule
+  const int wstep = (CG == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   constexpr uint32_t GC = NG * 16;                 // columns of one accumulator set (= MT*NC)
   constexpr uint32_t NMAIN = (NG <= 6) ? 3u : 2u;  // `main` accumulator buffers in flight (TMEM: (NMAIN+2)*GC <= 512 columns)
   constexpr int TAPW = TAPS == 9 ? 3 : (TAPS == 4 ? 2 : 1);   // taps per stencil row
   constexpr int ROWS = TAPS / TAPW;                            // stencil rows
-  constexpr uint32_t b_chunk_bytes = (uint32_t)TAPS * NC * CHB;   // weights of all taps of one 16-channel chunk
+  constexpr uint32_t b_chunk_bytes = (uint32_t)TAPS * NCB * CHB;  // weights of all taps of one 16-channel chunk (this CTA's rows)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -316,25 +388,35 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t bar_corr_empty = bar_main_empty + 32;      // [2]
   const uint32_t bar_corr_full = bar_corr_empty + 16;       // [2]
   const uint32_t bar_res = bar_corr_full + 16;              // [EPI_WARPS] residual chunks of a warp have landed in its staging buffers
-  const uint32_t s_tmem = bar_res + 8 * EPI_WARPS;
+  const uint32_t bar_turn = bar_res + 8 * EPI_WARPS;        // [2] SETS = 2: set s has finished the drains of its current tile
+  const uint32_t s_tmem = bar_turn + 16;
   uint8_t* gen = smem_raw + (base - raw);
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen + (s_tmem - base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < p.S; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 2); }   // empty: both MMA warps
-    for (int i = 0; i < (int)NMAIN; ++i) { mbar_init(bar_main_full + 8 * i, 1); mbar_init(bar_main_empty + 8 * i, EPI_WARPS); }
-    for (int i = 0; i < 2; ++i) { mbar_init(bar_corr_empty + 8 * i, EPI_WARPS); mbar_init(bar_corr_full + 8 * i, 1); }
+    // full: one arrival (with its byte count) per producer -- in pair mode both CTAs' producers report to the leader's barrier;
+    // empty: both MMA warps; main/corr empty: the epilogue warps of every CTA whose accumulators the MMA overwrites
+    for (int i = 0; i < p.S; ++i) { mbar_init(bar_full + 8 * i, CG); mbar_init(bar_empty + 8 * i, 2); }
+    for (int i = 0; i < (int)NMAIN; ++i) { mbar_init(bar_main_full + 8 * i, 1); mbar_init(bar_main_empty + 8 * i, SET_WARPS * CG); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_corr_empty + 8 * i, SET_WARPS * CG); mbar_init(bar_corr_full + 8 * i, 1); }
     for (int i = 0; i < EPI_WARPS; ++i) mbar_init(bar_res + 8 * i, 1);
+    for (int i = 0; i < 2; ++i) mbar_init(bar_turn + 8 * i, SET_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_tmem), "r"((uint32_t)p.tmem_cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CG == 2) {      // the same warp of both CTAs, the same destination offset
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_tmem), "r"((uint32_t)p.tmem_cols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_tmem), "r"((uint32_t)p.tmem_cols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();      // the peer's barriers are initialised before anything is signalled across the pair
+  else __syncthreads();
   tc_fence_after();
   // broadcast through a shuffle so the compiler knows the value is warp-uniform (UTCHMMA operands live in uniform registers)
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
@@ -345,12 +427,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmW) : "memory");
       Ring r;
-      int tile = blockIdx.x % p.tiles_m, nsl = blockIdx.x / p.tiles_m;
+      int tile = wfirst % p.tiles_m, nsl = wfirst / p.tiles_m;
       uint32_t tx = (uint32_t)KC * (a_bytes + b_chunk_bytes);
       const bool gather = TAPS == 4 && p.gather;
-      for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
-        const int m0 = tile * 128 * MT;            // row index fits 31 bits (asserted on the host)
-        const int n0 = nsl * NC;
+      const uint32_t full0 = (CG == 2) ? mapa_rank(bar_full, 0u) : bar_full;    // pair mode: the LEADER's full barriers (cluster address)
+      for (int w = wfirst; w < p.total_work; w += wstep) {
+        const int m0 = (tile * CG + (int)rank) * 128 * MT;            // row index fits 31 bits (asserted on the host)
+        const int n0 = nsl * NC + (int)rank * NCB;                    // first weight row this CTA loads
         // Gather mode (stride-2 3x3 convolution in its 2x2 space-to-depth form): the rows [m0, m0 + 128*MT + Wp + 1) of the
         // space-to-depth tensor S[a'][b'][(py,px,c)] = in[2(a'-1)+py][2(b'-1)+px][c] are never materialised; TMA gathers them
         // from the original tensor with element strides (2, 2), one box = two whole S image rows (a' = 2q, 2q+1) of one
@@ -367,37 +450,44 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int j = 0;
         for (int st = 0; st < p.nstage; ++st) {
           mbar_wait_relaxed(bar_empty + 8 * r.idx, r.phase ^ 1u, p.poll_ns);
-          const uint32_t full = bar_full + 8 * r.idx, dst = sRing + r.idx * stage_bytes;
-          mbar_expect_tx(full, tx);
+          const uint32_t full = full0 + 8 * r.idx, dst = sRing + r.idx * stage_bytes;
+          if (CG == 2) mbar_expect_tx_cluster(full, tx); else mbar_expect_tx(full, tx);
 #pragma unroll
           for (int kc = 0; kc < KC; ++kc, ++j) {
             if (gather) {
               const int par = j / p.cpp, jj = j - par * p.cpp;
               int qq = g_q, nn = g_n;
               for (int b = 0; b < g_nbox; ++b) {
-                tma_load_4d(dst + (uint32_t)b * 2u * (uint32_t)p.Wp * CHB, &tmA, (p.in_coff + jj) * (CHB / 4), (par & 1) - 2, 4 * qq - 2 + (par >> 1), nn, full);
+                const uint32_t da = dst + (uint32_t)b * 2u * (uint32_t)p.Wp * CHB;
+                if (CG == 2) tma2_load_4d(da, &tmA, (p.in_coff + jj) * (CHB / 4), (par & 1) - 2, 4 * qq - 2 + (par >> 1), nn, full);
+                else tma_load_4d(da, &tmA, (p.in_coff + jj) * (CHB / 4), (par & 1) - 2, 4 * qq - 2 + (par >> 1), nn, full);
                 if (++qq == (p.Hp >> 1)) { qq = 0; ++nn; }
               }
             } else
             for (int sg = 0; sg < p.nseg; ++sg)
-              for (int b = 0; b < p.nb_seg; ++b)
-                tma_load_2d(dst + (uint32_t)kc * a_bytes + (uint32_t)(sg * p.Rseg + b * p.RB) * CHB, &tmA, (p.in_coff + j) * (CHB / 4),
-                            m0 - p.halo + sg * p.seg_step + b * p.RB, full);
-            // weights: box {one chunk row, NC output channels, TAPS taps} of the [tap][chunk*Cout + n][CHB] tensor
-            tma_load_3d(dst + (uint32_t)KC * a_bytes + (uint32_t)kc * b_chunk_bytes, &tmW, 0, j * p.Cout + n0, 0, full);
+              for (int b = 0; b < p.nb_seg; ++b) {
+                const uint32_t da = dst + (uint32_t)kc * a_bytes + (uint32_t)(sg * p.Rseg + b * p.RB) * CHB;
+                if (CG == 2) tma2_load_2d(da, &tmA, (p.in_coff + j) * (CHB / 4), m0 - p.halo + sg * p.seg_step + b * p.RB, full);
+                else tma_load_2d(da, &tmA, (p.in_coff + j) * (CHB / 4), m0 - p.halo + sg * p.seg_step + b * p.RB, full);
+              }
+            // weights: box {one chunk row, NCB output channels, TAPS taps} of the [tap][chunk*Cout + n][CHB] tensor
+            if (CG == 2) tma2_load_3d(dst + (uint32_t)KC * a_bytes + (uint32_t)kc * b_chunk_bytes, &tmW, 0, j * p.Cout + n0, 0, full);
+            else tma_load_3d(dst + (uint32_t)KC * a_bytes + (uint32_t)kc * b_chunk_bytes, &tmW, 0, j * p.Cout + n0, 0, full);
           }
           r.advance(p.S);
         }
-        tile += gridDim.x;
+        tile += wstep;
         while (tile >= p.tiles_m) { tile -= p.tiles_m; ++nsl; }
       }
     }
-  } else if (warp == 1 || warp == 2 + EPI_WARPS) {
-    // ===================== MMA issuers: warp-uniform control flow, one elected lane issues =====================
+  } else if ((warp == 1 || warp == 2 + EPI_WARPS) && rank == 0) {
+    // ===================== MMA issuers: warp-uniform control flow, one elected lane issues (pair mode: the leader's only) =====
     const bool roleX = (warp == 1);
-    // instruction descriptor: D=F32, A/B format, K-major both, N = NC, M = 128
+    // instruction descriptor: D=F32, A/B format, K-major both, N = NC, M = 128 per CTA (256 over a pair)
     constexpr uint32_t FMT = PE_FP16 ? 0u : 2u;                       // A/B format: F16 = 0, TF32 = 2
-    constexpr uint32_t idesc = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(NC >> 3) << 17) | ((128u >> 4) << 24);
+    constexpr uint32_t idesc = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(NC >> 3) << 17) | (((128u * CG) >> 4) << 24);
+    auto mma = [](uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t acc) { if (CG == 2) tc_mma2(d, a, b, id, acc); else tc_mma_tf32(d, a, b, id, acc); };
+    auto commit = [](uint32_t bar) { if (CG == 2) tc_commit2(bar); else tc_commit(bar); };
     const uint64_t d0 = umma_desc(sRing);
     const uint32_t desc_hi = (uint32_t)(d0 >> 32);                    // identical for A and B tiles
     const uint32_t ring_lo0 = (uint32_t)d0;
@@ -413,13 +503,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t dg = 0, dgp = 0;             // drain-group buffer / phase
       uint32_t fresh = 1u;                  // the current drain group's accumulator has not been written yet
       const int total_rows = p.nstage * KC * ROWS;
-      int tile = blockIdx.x % p.tiles_m;
-      for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+      int tile = wfirst % p.tiles_m;
+      for (int w = wfirst; w < p.total_work; w += wstep) {
         uint32_t a_off16 = 0;               // gather mode: the tile's first row inside the gathered window (whole S image rows)
         if (TAPS == 4 && p.gather) {
-          const int m0 = tile * 128 * MT, g0 = m0 / p.Wp, gn = g0 / p.Hp, gq = (g0 - gn * p.Hp) >> 1;
+          const int m0 = tile * CG * 128 * MT, g0 = m0 / p.Wp, gn = g0 / p.Hp, gq = (g0 - gn * p.Hp) >> 1;
           a_off16 = (uint32_t)(m0 - (gn * p.Hp + 2 * gq) * p.Wp) * ROW16;
-          tile += gridDim.x;
+          tile += wstep;
           while (tile >= p.tiles_m) tile -= p.tiles_m;
         }
         int rig = 0, row_no = 0;            // stencil rows issued into the current drain group / in this tile
@@ -470,16 +560,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                   for (int mt = 0; mt < MT; ++mt) {
                     const uint32_t a = a_st + (uint32_t)kc * a16 + (uint32_t)row * wp16 + (uint32_t)(t * ROW16 + mt * 128 * ROW16);
-                    const uint32_t b = b_st + (uint32_t)((kc * TAPS + row * TAPW + t) * NC * ROW16);
+                    const uint32_t b = b_st + (uint32_t)((kc * TAPS + row * TAPW + t) * NCB * ROW16);
 #pragma unroll
                     for (int ks = 0; ks < KSTEPS; ++ks)
-                      tc_mma_tf32(d_main + (uint32_t)(mt * NC), desc64(desc_hi, a + 2 * ks), desc64(desc_hi, b + 2 * ks), idesc,
+                      mma(d_main + (uint32_t)(mt * NC), desc64(desc_hi, a + 2 * ks), desc64(desc_hi, b + 2 * ks), idesc,
                                   (fr && ks == 0) ? 0u : 1u);   // hi * hi
                   }
                   fr = 0u;
                 }
-                if (close) tc_commit(bar_main_full + 8 * dg);          // this drain group's partial sums are complete
-                if (kc == KC - 1 && row == ROWS - 1) tc_commit(empty_bar);   // stage free once these MMAs (and warp Y's) retire
+                if (close) commit(bar_main_full + 8 * dg);          // this drain group's partial sums are complete
+                if (kc == KC - 1 && row == ROWS - 1) commit(empty_bar);   // stage free once these MMAs (and warp Y's) retire
               }
               __syncwarp();
               if (skip != ((1u << TAPW) - 1u)) fresh = 0u;
@@ -495,13 +585,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else {
       // ---------------- Y: hi*lo + lo*hi into the tile's `corr` accumulator
       uint32_t tl = 0;
-      int tile = blockIdx.x % p.tiles_m;
-      for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++tl) {
+      int tile = wfirst % p.tiles_m;
+      for (int w = wfirst; w < p.total_work; w += wstep, ++tl) {
         uint32_t a_off16 = 0;               // gather mode: see warp X
         if (TAPS == 4 && p.gather) {
-          const int m0 = tile * 128 * MT, g0 = m0 / p.Wp, gn = g0 / p.Hp, gq = (g0 - gn * p.Hp) >> 1;
+          const int m0 = tile * CG * 128 * MT, g0 = m0 / p.Wp, gn = g0 / p.Hp, gq = (g0 - gn * p.Hp) >> 1;
           a_off16 = (uint32_t)(m0 - (gn * p.Hp + 2 * gq) * p.Wp) * ROW16;
-          tile += gridDim.x;
+          tile += wstep;
           while (tile >= p.tiles_m) tile -= p.tiles_m;
         }
         const uint32_t cbuf = tl & 1u;
@@ -549,22 +639,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                   for (int mt = 0; mt < MT; ++mt) {
                     const uint32_t a = a_st + (uint32_t)kc * a16 + (uint32_t)row * wp16 + (uint32_t)(t * ROW16 + mt * 128 * ROW16);
-                    const uint32_t b = b_st + (uint32_t)((kc * TAPS + row * TAPW + t) * NC * ROW16);
+                    const uint32_t b = b_st + (uint32_t)((kc * TAPS + row * TAPW + t) * NCB * ROW16);
                     // hi/h half at +0, lo/l half at +LO16 (16-byte units); tf32: two K=8 steps of 32 B, fp16: one K=16 step
 #pragma unroll
                     for (int ks = 0; ks < KSTEPS; ++ks) {
                       const uint32_t ak = a + 2 * ks, bk = b + 2 * ks;
-                      tc_mma_tf32(d_corr + (uint32_t)(mt * NC), desc64(desc_hi, ak), desc64(desc_hi, bk + LO16), idesc,
+                      mma(d_corr + (uint32_t)(mt * NC), desc64(desc_hi, ak), desc64(desc_hi, bk + LO16), idesc,
                                   (fr && ks == 0) ? 0u : 1u);                                                                          // hi * lo
-                      tc_mma_tf32(d_corr + (uint32_t)(mt * NC), desc64(desc_hi, ak + LO16), desc64(desc_hi, bk), idesc, 1u);            // lo * hi
+                      mma(d_corr + (uint32_t)(mt * NC), desc64(desc_hi, ak + LO16), desc64(desc_hi, bk), idesc, 1u);            // lo * hi
                     }
                   }
                   fr = 0u;
                 }
               }
             }
-            tc_commit(bar_empty + 8 * r.idx);
-            if (st == p.nstage - 1) tc_commit(bar_corr_full + 8 * cbuf);   // every cross-term MMA of this tile has retired
+            commit(bar_empty + 8 * r.idx);
+            if (st == p.nstage - 1) commit(bar_corr_full + 8 * cbuf);   // every cross-term MMA of this tile has retired
           }
           __syncwarp();
           if (TAPS != 4 || zmst != ((KC == 1) ? 0xFu : (KC == 2) ? 0xFFu : 0xFFFFu)) freshY = 0u;
@@ -585,7 +675,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================== epilogue (warps 2..13; TMEM lane quarter = warp & 3; the EPI_PARTS warps of a quarter take the
     // 16-column groups round-robin, so TMEM drains, residual adds, the split and the stores of one tile run on 12 warps) ====
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;                       // which of the EPI_PARTS warps of this quarter
+    const int eset = (SETS == 2) ? ((warp - 2) >> 3) : 0;   // SETS = 2: this warp's set takes the CTA's work items eset, eset + 2, ...
+    const int half = ((warp - 2) >> 2) % EPI_PARTS;         // which of the EPI_PARTS warps of this quarter (within the set)
+    const int ewfirst = wfirst + eset * wstep, ewstep = wstep * SETS;
     constexpr int NGH = (NG + EPI_PARTS - 1) / EPI_PARTS;                       // groups per warp (the odd warp of an odd NG has one fewer)
     const int rowF = p.res_rowF;                            // floats per row of the residual tensor (plain-load fallback)
     constexpr int CF = PS_CHUNK_FLOATS;                     // floats per 16-channel chunk of a row
@@ -595,9 +687,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int hpwp = p.Hp * p.Wp;
     const uint32_t st_base = sStage + (uint32_t)(warp - 2) * (uint32_t)p.nstg * 32u * CHB;
     uint32_t st_slot = 0;
-    uint32_t tl = 0, dg = 0, dgp = 0;
-    int tile = blockIdx.x % p.tiles_m, nsl = blockIdx.x / p.tiles_m;
+    // tl = ordinal of the tile among the CTA's work items (both sets count all of them: it selects the corr buffer);
+    // (dg, dgp) = `main` buffer / phase of the tile's first drain group: the other set's tiles advance it by ndrain each
+    uint32_t tl = (uint32_t)eset;
+    uint32_t dg = ((uint32_t)eset * (uint32_t)ndrain) % NMAIN, dgp = (((uint32_t)eset * (uint32_t)ndrain) / NMAIN) & 1u;
+    int tile = ewfirst % p.tiles_m, nsl = ewfirst / p.tiles_m;
     constexpr int NV = CHB / 16;                         // 16-byte vectors per row chunk
+    // "accumulator drained" signals go to the CTA whose warps issue the MMAs: the leader of the pair
+    const uint32_t main_empty0 = (CG == 2) ? mapa_rank(bar_main_empty, 0u) : bar_main_empty;
+    const uint32_t corr_empty0 = (CG == 2) ? mapa_rank(bar_corr_empty, 0u) : bar_corr_empty;
     // Residual rows.  Measured: per-lane row loads (lane = accumulator row, 64 B each, 192+ B apart) cost the SM's load/store
     // unit 32 line lookups per instruction -- ~3000 clocks per 256-row tile, which made every residual layer epilogue-bound
     // (warp X waited ~2000 clk per stage for a free `main` buffer).  So the rows come through TMA instead: each epilogue warp
@@ -617,7 +715,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int g = EPI_PARTS * gi + half;
           if (g < NG && gi < p.nstg)
             tma_load_2d(st_base + (uint32_t)gi * 32u * CHB, &tmR, (p.res_coff + (nsl_ * NC + (g % gpm) * 16) / 16) * CF,
-                        tile_ * 128 * MT + (g / gpm) * 128 + q * 32 + p.res_row_off, res_bar);
+                        (tile_ * CG + (int)rank) * 128 * MT + (g / gpm) * 128 + q * 32 + p.res_row_off, res_bar);
         }
       }
     };
@@ -627,7 +725,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // drains back to back, so the distance must be several drains); layers with fewer (1x1) request the next tile's at the end
     // of the current one.
     const bool res_lazy = p.res && (ndrain >= 3 || p.res_post);
-    if (p.res && !res_lazy && blockIdx.x < p.total_work) res_issue(tile, nsl);
+    if (p.res && !res_lazy && ewfirst < p.total_work) res_issue(tile, nsl);
 #if PE_TC_PROFILE
     long long e_wm = 0, e_dr = 0, e_rs = 0, e_wc = 0, e_co = 0, e_fi = 0, e_ri = 0, e_tc = 0, e_f1 = 0, e_f2 = 0, e_f3 = 0, e_f4 = 0, e_t = clock64();
     const long long e_t0 = e_t;
@@ -635,9 +733,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #else
 #define EPI_TICK(v)
 #endif
-    for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++tl) {
-      const long long m0 = (long long)tile * 128 * MT;
+    for (int w = ewfirst; w < p.total_work; w += ewstep, tl += SETS) {
+      const long long m0 = (long long)(tile * CG + (int)rank) * 128 * MT;
       const int n0 = nsl * NC;
+      const uint32_t mytl = tl / SETS;                     // ordinal among this set's own tiles (phase of the per-warp residual barrier)
       float acc[NGH][16];
       // interior test of this lane's row in each of the MT 128-row accumulators (bit mt)
       uint32_t interior = 0;
@@ -724,6 +823,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #endif
       };
       EPI_TICK(e_tc)
+      // SETS = 2: the drains of a tile start only after the other set has finished those of the previous tile.  A parity wait is
+      // only meaningful for a waiter that is at most one phase behind: without this hand-over a set would test a `main` barrier
+      // whose earlier phases (drained by the other set) it never observed and could pass on a stale phase.
+      if (SETS == 2) {
+        if (eset == 1) mbar_wait_relaxed(bar_turn, mytl & 1u, p.poll_ns);
+        else if (mytl > 0) mbar_wait_relaxed(bar_turn + 8, (mytl - 1u) & 1u, p.poll_ns);
+      }
       for (int d = 0; d < ndrain; ++d) {
         mbar_wait_relaxed(bar_main_full + 8 * dg, dgp, p.poll_ns);
         tc_fence_after();
@@ -747,12 +853,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_main_empty + 8 * dg);
+        if (lane == 0) { if (CG == 2) mbar_arrive_cluster(main_empty0 + 8 * dg); else mbar_arrive(bar_main_empty + 8 * dg); }
         if (++dg == NMAIN) { dg = 0; dgp ^= 1u; }
         EPI_TICK(e_dr)
         if (d == 0 && res_lazy) { res_issue(tile, nsl); __syncwarp(); }
         if (p.res && !p.res_post && d == (res_lazy ? ndrain - 1 : 0)) {
-          mbar_wait_relaxed(res_bar, tl & 1u, p.poll_ns);
+          mbar_wait_relaxed(res_bar, mytl & 1u, p.poll_ns);
 #pragma unroll
           for (int gi = 0; gi < NGH; ++gi) {
             const int g = EPI_PARTS * gi + half;
@@ -765,8 +871,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           EPI_TICK(e_rs)
         }
       }
+      if (SETS == 2) {                                     // the other set drains the next tile's groups
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_turn + 8 * (uint32_t)eset);
+        const uint32_t t = dg + (uint32_t)ndrain;
+        dgp ^= (t / NMAIN) & 1u;
+        dg = t % NMAIN;
+      }
       const uint32_t interior_cur = interior;
-      int tile_n = tile + gridDim.x, nsl_n = nsl;
+      int tile_n = tile + ewstep, nsl_n = nsl;
       while (tile_n >= p.tiles_m) { tile_n -= p.tiles_m; ++nsl_n; }
       // cross terms: committed by MMA warp Y at the end of the tile
       const uint32_t cbuf = tl & 1u;
@@ -784,9 +897,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_corr_empty + 8 * cbuf);
+      if (lane == 0) { if (CG == 2) mbar_arrive_cluster(corr_empty0 + 8 * cbuf); else mbar_arrive(bar_corr_empty + 8 * cbuf); }
       EPI_TICK(e_co)
-      if (p.res && p.res_post) mbar_wait_relaxed(res_bar, tl & 1u, p.poll_ns);
+      if (p.res && p.res_post) mbar_wait_relaxed(res_bar, mytl & 1u, p.poll_ns);
       // ---- bias / activation / split / store (the MMA warps are already on the next tile)
 #pragma unroll
       for (int gi = 0; gi < NGH; ++gi) {
@@ -894,35 +1007,41 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       tile = tile_n; nsl = nsl_n;
       EPI_TICK(e_fi)
-      if (p.res && !res_lazy && w + (int)gridDim.x < p.total_work) res_issue(tile, nsl);   // next tile's residual chunks, one tile ahead
+      if (p.res && !res_lazy && w + ewstep < p.total_work) res_issue(tile, nsl);   // next tile's residual chunks, one tile ahead
       __syncwarp();
       EPI_TICK(e_ri)
     }
 #if PE_TC_PROFILE
     if (p.prof && warp == 2 && lane == 0) {
       long long* o = p.prof + (size_t)blockIdx.x * 32 + 16;
-      o[0] = e_wm; o[1] = e_dr; o[2] = e_rs; o[3] = e_wc; o[4] = e_co; o[5] = e_fi; o[6] = e_ri; o[7] = e_tc; o[8] = clock64() - e_t0; o[9] = tl; o[10] = e_f1; o[11] = e_f2; o[12] = e_f3; o[13] = e_f4;
+      o[0] = e_wm; o[1] = e_dr; o[2] = e_rs; o[3] = e_wc; o[4] = e_co; o[5] = e_fi; o[6] = e_ri; o[7] = e_tc; o[8] = clock64() - e_t0; o[9] = tl / SETS; o[10] = e_f1; o[11] = e_f2; o[12] = e_f3; o[13] = e_f4;
     }
 #endif
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // staged rows fully written before smem goes away
   }
   tc_fence_before();
-  __syncthreads();
+  __syncwarp();
+  if (CG == 2) cluster_sync_all();      // neither CTA may leave (or free TMEM) while the pair's MMAs / signals still target it
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+    if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
   }
 }
 
 typedef void (*TcKernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams);
-// (MT, NC, TAPS, KC) instantiations: MT*NC in {16..128} columns; 3x3 (9 taps), 2x2 (4 taps) and 1-D (3 taps) stages hold one
-// 16-channel chunk, 1x1 stages hold up to four
-static TcKernelFn tc_kernel_for(int MT, int NC, int TAPS, int KC) {
-#define TCK(mt, nc, taps, kc) if (MT == mt && NC == nc && TAPS == taps && KC == kc) return conv_tc_kernel<(mt) * (nc) / 16, mt, taps, kc>;
-#define TCK_ALL(mt, nc) TCK(mt, nc, 9, 1) TCK(mt, nc, 4, 1) TCK(mt, nc, 3, 1) TCK(mt, nc, 1, 1) TCK(mt, nc, 1, 2) TCK(mt, nc, 1, 4)
-  TCK_ALL(1, 16) TCK_ALL(1, 32) TCK_ALL(2, 32) TCK_ALL(1, 48) TCK_ALL(2, 48) TCK_ALL(1, 64) TCK_ALL(2, 64) TCK_ALL(1, 80) TCK_ALL(1, 96)
+// (MT, NC, TAPS, KC, CG, SETS) instantiations: MT*NC in {16..128} columns; 3x3 (9 taps), 2x2 (4 taps) and 1-D (3 taps) stages hold
+// one 16-channel chunk, 1x1 stages hold up to four; CTA-pair forms (CG = 2) for N >= 32; two epilogue sets for the 3x3 and 1-D kinds
+static TcKernelFn tc_kernel_for(int MT, int NC, int TAPS, int KC, int CG, int SETS) {
+#define TCK(mt, nc, taps, kc, cg, sets) if (MT == mt && NC == nc && TAPS == taps && KC == kc && CG == cg && SETS == sets) return conv_tc_kernel<(mt) * (nc) / 16, mt, taps, kc, cg, sets>;
+#define TCK_CG(mt, nc, cg) TCK(mt, nc, 9, 1, cg, 1) TCK(mt, nc, 4, 1, cg, 1) TCK(mt, nc, 3, 1, cg, 1) TCK(mt, nc, 1, 1, cg, 1) TCK(mt, nc, 1, 2, cg, 1) TCK(mt, nc, 1, 4, cg, 1) \
+                           TCK(mt, nc, 9, 1, cg, 2) TCK(mt, nc, 3, 1, cg, 2)
+#define TCK_ALL(mt, nc) TCK_CG(mt, nc, 1) TCK_CG(mt, nc, 2)
+  TCK_CG(1, 16, 1) TCK_ALL(1, 32) TCK_ALL(2, 32) TCK_ALL(1, 48) TCK_ALL(2, 48) TCK_ALL(1, 64) TCK_ALL(2, 64) TCK_ALL(1, 80) TCK_ALL(1, 96)
   TCK_ALL(1, 128)
 #undef TCK_ALL
+#undef TCK_CG
 #undef TCK
   return nullptr;
 }
@@ -933,7 +1052,8 @@ struct TcConvPlan {
   TcParams p;
   int rows_per_img;
   size_t smem;
-  int ns, num_sms, MT, NC, TAPS, KC;
+  int ns, num_sms, MT, NC, TAPS, KC, CG, SETS;
+  int max_ctas;            // persistent grid size: SMs (CG = 1) or 2 x co-resident CTA pairs
   TcKernelFn kernel;
 };
 
@@ -993,7 +1113,7 @@ static bool tc_geom(int kind, int W, int dil, TcGeom* g) {
 // One feasible tiling of a layer: N-split, accumulators per CTA, chunks per stage, ring depth, window form.
 struct TcCand {
   TcParams p;
-  int ns, MT, NC, KC;
+  int ns, MT, NC, KC, CG, SETS;
   size_t smem;
   double cost;      // model estimate (clocks per CTA), used to rank and as the choice when auto-tuning is off
 };
@@ -1010,9 +1130,16 @@ static std::vector<TcCand> tc_enumerate(int kind, int Cin, int Cout, bool has_re
     const int ns = Cout / NC;
     if (ns > 8 && NC < 64) continue;                              // many thin slices re-read the activations ns times: never competitive
     for (int MT = 2; MT >= 1; --MT) {
-      for (int KC = (ntaps == 1 ? 4 : 1); KC >= 1; KC >>= 1) {
+      for (int KC = (ntaps == 1 ? 4 : 1); KC >= 1; KC >>= 1)
+      for (int CG = 1; CG <= 2; ++CG)
+      for (int SETS = 1; SETS <= 2; ++SETS) {
         if (nchunk % KC) continue;
-        if (!tc_kernel_for(MT, NC, ntaps, KC)) continue;
+        if (!tc_kernel_for(MT, NC, ntaps, KC, CG, SETS)) continue;
+        if (SETS == 2 && !env_int("PE_TC_SETS2", 1)) continue;
+        const int EPI_WARPS = epi_warps(SETS), EPI_PARTS = epi_parts(SETS);
+        // M = 256 MMAs: N multiple of 16; whole swizzle periods per CTA.  Not with the TMA gather: both CTAs of a pair use the
+        // SAME A descriptor, but a gathered window starts at a whole image-row pair, so the tile's offset in it differs per CTA
+        if (CG == 2 && (!env_int("PE_TC_PAIRS", 1) || NC % 16 || (NC / 2) % 8 || gather)) continue;
         // window forms: contiguous always; one run per stencil row as well when the rows are far apart
         const int nform = (!gather && g.nrows > 1 && g.halo_before + g.halo_after > 128 * MT) ? 2 : 1;
         for (int form = 0; form < nform; ++form) {
@@ -1051,7 +1178,7 @@ static std::vector<TcCand> tc_enumerate(int kind, int Cin, int Cout, bool has_re
             p.row_step = p.Rseg;
           }
           p.a_bytes = (uint32_t)p.Rpad * CHB;
-          const size_t b_chunk = (size_t)ntaps * NC * CHB;
+          const size_t b_chunk = (size_t)ntaps * (NC / CG) * CHB;       // pair mode: each CTA holds half of the weight rows
           p.stage_bytes = (uint32_t)(KC * (p.a_bytes + b_chunk));
           if (p.stage_bytes % (8 * CHB)) continue;                    // stage bases keep the swizzle phase (pattern period: 8 rows)
           // ring depth: as many stages as fit, at most 4.  Store-staging buffers per epilogue warp: two alternate for the output
@@ -1062,16 +1189,17 @@ static std::vector<TcCand> tc_enumerate(int kind, int Cin, int Cout, bool has_re
           while (cols < ((MT * NC / 16 <= 6) ? 5 : 4) * MT * NC) cols <<= 1;
           if (cols > 512) continue;
           p.tmem_cols = cols;
-          p.tiles_m = (int)((Mmax + 128LL * MT - 1) / (128LL * MT));
+          p.tiles_m = (int)((Mmax + 128LL * MT * CG - 1) / (128LL * MT * CG));     // pair mode: work items are pairs of M tiles
           p.total_work = p.tiles_m * ns;
-          const int ctas = p.total_work < num_sms ? p.total_work : num_sms;
+          const int slots = num_sms / CG;
+          const int ctas = p.total_work < slots ? p.total_work : slots;
           const double items = (double)((p.total_work + ctas - 1) / ctas);
           // clocks per work item.  Measured (tools/mma_bench.cu, issue_bench.cu): one M=128 SS tcgen05.mma occupies the
           // operand-fetch path for max(N/2, 32 + N/4) clocks (below N=128 the 4 KB A-operand read paces it); TMA ingest is
           // ~48 B/clk/SM from L2 with a few loads in flight (tools/tma_bench.cu); each stage costs the issuers ~300 clocks of
           // barrier hand-off that overlaps only partly
           const double n_mma = 3.0 * KSTEPS * ntaps * nchunk * MT;
-          const double mma = n_mma * std::max(NC / 2.0, 32.0 + NC / 4.0) + 300.0 * p.nstage;
+          const double mma = n_mma * std::max(NC / 2.0, 32.0 + NC / (4.0 * CG)) + 300.0 * p.nstage;
           const double bytes = (double)nchunk * (p.a_bytes + (double)b_chunk);
           const double epi = (double)MT * (NC / 16) * 130.0 * (1 + p.ndrain * 0.5) + 1500.0;
           // Ring depth S (2..4) against store-staging buffers per epilogue warp (1..4; residual layers land the residual chunks
@@ -1101,7 +1229,7 @@ static std::vector<TcCand> tc_enumerate(int kind, int Cin, int Cout, bool has_re
             const double item = std::max(std::max(mma, bytes / 40.0), epi) + (S < 3 ? 0.15 * mma : 0.0) + (nstg < 2 ? 0.1 * epi : 0.0)
                                 + ((has_res && MT * NC / 16 > 6) ? 0.5 * epi : 0.0);
             TcCand c;
-            c.p = p; c.ns = ns; c.MT = MT; c.NC = NC; c.KC = KC;
+            c.p = p; c.ns = ns; c.MT = MT; c.NC = NC; c.KC = KC; c.CG = CG; c.SETS = SETS;
             c.smem = (size_t)S * p.stage_bytes + (size_t)EPI_WARPS * nstg * 32 * CHB + 2048;
             c.cost = items * item + 4000.0;
             out.push_back(c);
@@ -1144,7 +1272,7 @@ static cudaError_t tc_build(TcConvPlan* pl, const TcCand& c, const TcConvDesc& d
   pl->p.poll_ns = env_int("PE_TC_POLL_NS", -1000);   // < 0: hardware-suspended waits with this time hint (ns); measured +1 % under the power cap
   pl->rows_per_img = g.two_d ? Hp * Wp : 1;
   pl->smem = c.smem;
-  pl->ns = c.ns; pl->MT = c.MT; pl->NC = c.NC; pl->TAPS = ntaps; pl->KC = c.KC;
+  pl->ns = c.ns; pl->MT = c.MT; pl->NC = c.NC; pl->TAPS = ntaps; pl->KC = c.KC; pl->CG = c.CG; pl->SETS = c.SETS;
   pl->num_sms = num_sms;
   const uint32_t cf = PS_CHUNK_FLOATS;    // tensor maps address 4-byte words: one 16-channel chunk = cf words
   CUresult r1, r2, r3;
@@ -1167,7 +1295,7 @@ static cudaError_t tc_build(TcConvPlan* pl, const TcCand& c, const TcConvDesc& d
   {
     // weights [tap][chunk*Cout + n][CHB bytes] as a 3-D tensor: one box = all taps of NC channels of one chunk
     const uint64_t dims[3] = {cf, (uint64_t)nchunk * Cout, (uint64_t)ntaps}, str[2] = {CHB, (uint64_t)nchunk * Cout * CHB};
-    const uint32_t box[3] = {cf, (uint32_t)c.NC, (uint32_t)ntaps};
+    const uint32_t box[3] = {cf, (uint32_t)(c.NC / c.CG), (uint32_t)ntaps};
     r2 = encode_nd(&pl->tmW, wpack, 3, dims, str, box);
   }
   {
@@ -1186,8 +1314,25 @@ static cudaError_t tc_build(TcConvPlan* pl, const TcCand& c, const TcConvDesc& d
     fprintf(stderr, "conv_tc: cuTensorMapEncodeTiled failed (%d, %d, %d) kind=%d Cin=%d Cout=%d RB=%d NC=%d\n", (int)r1, (int)r2, (int)r3, d.kind, d.Cin, Cout, c.p.RB, c.NC);
     return cudaErrorInvalidValue;
   }
-  pl->kernel = tc_kernel_for(c.MT, c.NC, ntaps, c.KC);
-  return pe_smem_optin((const void*)pl->kernel, (int)(227 * 1024));
+  pl->kernel = tc_kernel_for(c.MT, c.NC, ntaps, c.KC, c.CG, c.SETS);
+  cudaError_t e = pe_smem_optin((const void*)pl->kernel, (int)(227 * 1024));
+  if (e != cudaSuccess) return e;
+  pl->max_ctas = num_sms;
+  if (c.CG == 2) {
+    // co-resident CTA pairs (a pair needs both SMs of one TPC): the persistent grid must not exceed them
+    cudaLaunchConfig_t cfg{};
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.gridDim = dim3((unsigned)(num_sms & ~1), 1, 1); cfg.blockDim = dim3(tc_threads(c.SETS), 1, 1); cfg.dynamicSmemBytes = pl->smem;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int ncl = 0;
+    e = cudaOccupancyMaxActiveClusters(&ncl, (const void*)pl->kernel, &cfg);
+    if (e != cudaSuccess) return e;
+    if (ncl < 1) return cudaErrorInvalidConfiguration;
+    pl->max_ctas = 2 * std::min(ncl, num_sms / 2);
+  }
+  return cudaSuccess;
 }
 
 // Tiling choice.  The candidates compute bit-identical results (the accumulation order over K does not depend on the
@@ -1202,7 +1347,7 @@ static std::map<TcShapeKey, std::tuple<int, int, int, int>>& tc_choices() {   //
   static auto* m = new std::map<TcShapeKey, std::tuple<int, int, int, int>>();
   return *m;
 }
-static std::tuple<int, int, int, int> tc_cand_id(const TcCand& c) { return std::make_tuple(c.ns, c.MT, c.KC, (c.p.S * 8 + c.p.nstg) * 2 + (c.p.nseg > 1 ? 1 : 0)); }
+static std::tuple<int, int, int, int> tc_cand_id(const TcCand& c) { return std::make_tuple(c.ns, c.MT, c.KC, (((c.p.S * 8 + c.p.nstg) * 2 + (c.p.nseg > 1 ? 1 : 0)) * 2 + (c.CG - 1)) * 2 + (c.SETS - 1)); }
 
 cudaError_t tc_conv_plan_create_ex(TcConvPlan** out, const TcConvDesc* dp) {
   const TcConvDesc& d = *dp;
@@ -1239,15 +1384,24 @@ cudaError_t tc_conv_plan_create_ex(TcConvPlan** out, const TcConvDesc* dp) {
   }
   std::vector<TcCand> cands = tc_enumerate(d.kind, d.Cin, d.Cout, d.res != nullptr, d.H, d.W, d.dil, d.max_rows, num_sms, d.gather_src != nullptr);
   const int force_mt = env_int("PE_TC_MT", 0), force_ns = env_int("PE_TC_NS", 0), force_kc = env_int("PE_TC_KC", 0), force_seg = env_int("PE_TC_SEG", -1);
+  const int force_cg = env_int("PE_TC_CG", 0), force_sets = env_int("PE_TC_SETS", 0);
   cands.erase(std::remove_if(cands.begin(), cands.end(), [&](const TcCand& c) {
                 return (force_mt && c.MT != force_mt) || (force_ns && c.ns != force_ns) || (force_kc && c.KC != force_kc) ||
                        (force_seg >= 0 && (c.p.nseg > 1) != (force_seg != 0)); }),
               cands.end());
+  // PE_TC_CG / PE_TC_SETS pin the CTA-pair / two-epilogue-set forms where a layer kind has them (soft pins: kinds without such a
+  // form keep their other candidates)
+  for (int pass = 0; pass < 2; ++pass) {
+    const int want = pass == 0 ? force_cg : force_sets;
+    if (!want) continue;
+    auto miss = [&](const TcCand& c) { return (pass == 0 ? c.CG : c.SETS) != want; };
+    if (std::count_if(cands.begin(), cands.end(), miss) < (long)cands.size()) cands.erase(std::remove_if(cands.begin(), cands.end(), miss), cands.end());
+  }
   if (cands.empty()) return cudaErrorNotSupported;
   std::sort(cands.begin(), cands.end(), [](const TcCand& a, const TcCand& b) { return a.cost < b.cost; });
   const TcShapeKey key(d.kind * 1000 + d.dil, d.Cin, d.Cout, d.H, d.W, (d.res ? 1 : 0) + (d.gather_src ? 2 : 0) + 4 * d.act + 16 * d.res_post, d.max_rows,
                        (d.in_total != d.Cin) + 2 * (d.out_total != d.Cout));
-  const bool pinned = force_mt || force_ns || force_kc || force_seg >= 0;
+  const bool pinned = force_mt || force_ns || force_kc || force_seg >= 0 || force_cg || force_sets;
   size_t pick = 0;
   auto hit = tc_choices().find(key);
   if (!pinned && hit != tc_choices().end()) {
@@ -1258,7 +1412,7 @@ cudaError_t tc_conv_plan_create_ex(TcConvPlan** out, const TcConvDesc* dp) {
     cudaEvent_t e0, e1;
     if (cudaStreamCreateWithFlags(&ts, cudaStreamNonBlocking) != cudaSuccess) return cudaGetLastError();
     cudaEventCreate(&e0); cudaEventCreate(&e1);
-    const size_t ntry = std::min<size_t>(cands.size(), 10);
+    const size_t ntry = std::min<size_t>(cands.size(), 20);
     std::vector<TcConvPlan> tmp(ntry);
     std::vector<float> ms_min(ntry, 1e30f);
     std::vector<char> ok(ntry, 0);
@@ -1283,8 +1437,8 @@ cudaError_t tc_conv_plan_create_ex(TcConvPlan** out, const TcConvDesc* dp) {
     for (size_t i = 0; i < ntry; ++i) {
       if (!ok[i]) continue;
       if (env_int("PE_TC_VERBOSE", 0) > 1)
-        fprintf(stderr, "conv_tc tune: kind=%d Cin=%d Cout=%d %dx%d dil=%d res=%d gather=%d  NS=%d MT=%d KC=%d S=%d nstg=%d seg=%d -> %.3f ms (model %.0f)\n", d.kind, d.Cin, d.Cout,
-                d.H, d.W, d.dil, d.res ? 1 : 0, d.gather_src ? 1 : 0, cands[i].ns, cands[i].MT, cands[i].KC, cands[i].p.S, cands[i].p.nstg, cands[i].p.nseg, ms_min[i], cands[i].cost);
+        fprintf(stderr, "conv_tc tune: kind=%d Cin=%d Cout=%d %dx%d dil=%d res=%d gather=%d  NS=%d MT=%d KC=%d CG=%d SETS=%d S=%d nstg=%d seg=%d -> %.3f ms (model %.0f)\n", d.kind, d.Cin, d.Cout,
+                d.H, d.W, d.dil, d.res ? 1 : 0, d.gather_src ? 1 : 0, cands[i].ns, cands[i].MT, cands[i].KC, cands[i].CG, cands[i].SETS, cands[i].p.S, cands[i].p.nstg, cands[i].p.nseg, ms_min[i], cands[i].cost);
       if (ms_min[i] < best_ms) { best_ms = ms_min[i]; pick = i; }
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
@@ -1302,8 +1456,8 @@ cudaError_t tc_conv_plan_create_ex(TcConvPlan** out, const TcConvDesc* dp) {
 #endif
   const TcCand& c = cands[pick];
   if (env_int("PE_TC_VERBOSE", 0))
-    fprintf(stderr, "conv_tc plan: kind=%d Cin=%d Cout=%d %dx%d dil=%d res=%d  MT=%d NS=%d NC=%d KC=%d S=%d nstg=%d rpg=%d ndrain=%d Rpad=%d RB=%d nseg=%d stage=%u smem=%zu tmem=%d work=%d\n",
-            d.kind, d.Cin, d.Cout, d.H, d.W, d.dil, d.res ? 1 : 0, c.MT, c.ns, c.NC, c.KC, c.p.S, c.p.nstg, c.p.rpg, c.p.ndrain, c.p.Rpad, c.p.RB, c.p.nseg, c.p.stage_bytes, c.smem,
+    fprintf(stderr, "conv_tc plan: kind=%d Cin=%d Cout=%d %dx%d dil=%d res=%d  MT=%d NS=%d NC=%d KC=%d CG=%d SETS=%d S=%d nstg=%d rpg=%d ndrain=%d Rpad=%d RB=%d nseg=%d stage=%u smem=%zu tmem=%d work=%d\n",
+            d.kind, d.Cin, d.Cout, d.H, d.W, d.dil, d.res ? 1 : 0, c.MT, c.ns, c.NC, c.KC, c.CG, c.SETS, c.p.S, c.p.nstg, c.p.rpg, c.p.ndrain, c.p.Rpad, c.p.RB, c.p.nseg, c.p.stage_bytes, c.smem,
             c.p.tmem_cols, c.p.total_work);
   *out = pl;
   return cudaSuccess;
@@ -1333,9 +1487,9 @@ int tc_plan_candidates(int Cin, int Cout, int ks, int has_res, int H, int W, int
   int n = 0;
   for (const TcCand& k : c) {
     if (n >= cap) break;
-    int32_t* o = out + (size_t)n * 12;
+    int32_t* o = out + (size_t)n * 14;
     o[0] = k.ns; o[1] = k.MT; o[2] = k.NC; o[3] = k.KC; o[4] = k.p.S; o[5] = k.p.nstg; o[6] = (int32_t)k.p.stage_bytes;
-    o[7] = (int32_t)k.smem; o[8] = k.p.tmem_cols; o[9] = k.p.rpg; o[10] = k.p.ndrain; o[11] = k.p.Rpad;
+    o[7] = (int32_t)k.smem; o[8] = k.p.tmem_cols; o[9] = k.p.rpg; o[10] = k.p.ndrain; o[11] = k.p.Rpad; o[12] = k.CG; o[13] = k.SETS;
     ++n;
   }
   return n;
@@ -1349,10 +1503,24 @@ cudaError_t tc_conv_launch_rows(TcConvPlan* pl, long long rows, cudaStream_t st)
   TcParams p = pl->p;
   p.flag = pe_range_flag();
   p.M = rows;
-  p.tiles_m = (int)((p.M + 128LL * pl->MT - 1) / (128LL * pl->MT));
+  p.tiles_m = (int)((p.M + 128LL * pl->MT * pl->CG - 1) / (128LL * pl->MT * pl->CG));
   p.total_work = p.tiles_m * pl->ns;
-  const unsigned grid = (unsigned)(p.total_work < pl->num_sms ? p.total_work : pl->num_sms);
-  pl->kernel<<<grid, TC_THREADS, pl->smem, st>>>(pl->tmA, pl->tmW, pl->tmO, pl->tmR, p);
+  unsigned grid;
+  if (pl->CG == 2) {
+    grid = (unsigned)(2 * std::min(p.total_work, pl->max_ctas / 2));
+    cudaLaunchConfig_t cfg{};
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.gridDim = dim3(grid, 1, 1); cfg.blockDim = dim3(tc_threads(pl->SETS), 1, 1); cfg.dynamicSmemBytes = pl->smem; cfg.stream = st;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    void* args[5] = {(void*)&pl->tmA, (void*)&pl->tmW, (void*)&pl->tmO, (void*)&pl->tmR, (void*)&p};
+    const cudaError_t le = cudaLaunchKernelExC(&cfg, (const void*)pl->kernel, args);
+    if (le != cudaSuccess) return le;
+  } else {
+    grid = (unsigned)(p.total_work < pl->num_sms ? p.total_work : pl->num_sms);
+    pl->kernel<<<grid, tc_threads(pl->SETS), pl->smem, st>>>(pl->tmA, pl->tmW, pl->tmO, pl->tmR, p);
+  }
 #if PE_TC_PROFILE
   if (p.prof) {
     static long long h[148 * 32];

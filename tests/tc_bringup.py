@@ -24,6 +24,8 @@ CASES = [  # (Cin, Cout, ks, H, W, nimg, res, relu)
     (64, 64, 3, 192, 144, 1, False, True, 2),
     (192, 384, 3, 24, 18, 3, False, False, 2),
     (256, 96, 3, 96, 72, 2, False, True, 2),
+    (96, 96, 3, 48, 36, 40, True, True),          # several tiles per CTA (persistent schedule, alternating epilogue sets)
+    (48, 48, 3, 96, 72, 24, True, True),
 ]
 
 

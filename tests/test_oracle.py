@@ -187,7 +187,7 @@ def test_conv_planner_candidates_respect_hardware_limits():
     lib = _lib.load()
     fp16 = lib.pe_precision_mode() == 1
     chunk_bytes = 64 if fp16 else 128
-    buf = (C.c_int32 * (64 * 12))()
+    buf = (C.c_int32 * (64 * 14))()
     seen = set()
     for variant, (h, w) in (("w48", (384, 288)), ("w32", (256, 192))):
         prog = build_program(variant, h, w, 17)
@@ -208,10 +208,11 @@ def test_conv_planner_candidates_respect_hardware_limits():
                     continue                                            # gather mode is optional (s2d copy is the fallback)
                 assert n > 0 or not fp16, key                          # (tf32x3 build: 128-byte chunks, a few shapes fall back to the SIMT conv)
                 for i in range(n):
-                    ns, mt, nc, kc, S, nstg, stage, smem, tmem, rpg, ndrain, rows = buf[12 * i:12 * i + 12]
+                    ns, mt, nc, kc, S, nstg, stage, smem, tmem, rpg, ndrain, rows, cg, sets = buf[14 * i:14 * i + 14]
+                    assert cg in (1, 2) and (cg == 1 or (nc % 16 == 0 and (nc // 2) % 8 == 0))
                     assert ns * nc == op.cout and nc % 16 == 0 and nc <= 128 and mt in (1, 2)
                     assert 2 <= S <= 4 and 1 <= nstg <= 4
-                    assert smem <= 227 * 1024 and S * stage + 12 * nstg * 32 * chunk_bytes <= smem
+                    assert sets in (1, 2) and smem <= 227 * 1024 and S * stage + (12 if sets == 1 else 16) * nstg * 32 * chunk_bytes <= smem
                     assert stage % (8 * chunk_bytes) == 0 and rows % 8 == 0
                     n_main = 3 if mt * nc // 16 <= 6 else 2
                     assert (n_main + 2) * mt * nc <= tmem <= 512
