@@ -195,7 +195,8 @@ int pe_conv_test(pe_engine* e, const float* in_nchw, int32_t nimg, int32_t Cin, 
  * stride-2 3x3 layer, Cin already x4); gather: 1 = TMA gather mode of that form.  Each candidate fills PE_TC_CAND_FIELDS
  * int32 values: n_split, MT, NC, KC, stages, staging_buffers, stage_bytes, smem_bytes, tmem_cols, rows_per_group, n_drain,
  * window_rows, cta_group (1, or 2 = CTA-pair form: M = 256 MMAs over the two SMs of a TPC),
- * epilogue_sets (1 = 12 epilogue warps on every tile, 2 = two sets of 8 warps on alternate tiles).  Returns the number of candidates (<= cap) or a negative error. */
+ * epilogue_sets (1 = 12 epilogue warps on every tile, 2 = two sets of 8 warps on alternate tiles, 3 / 4 = 8 drain warps + 4 / 8
+ * finalize warps).  Returns the number of candidates (<= cap) or a negative error. */
 #define PE_TC_CAND_FIELDS 14
 int pe_tc_plan_candidates(int32_t Cin, int32_t Cout, int32_t ks, int32_t has_residual, int32_t H, int32_t W, int32_t max_img,
                           int32_t gather, int32_t* out, int32_t cap);

@@ -9,8 +9,9 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
-SOURCES = ["engine.cu", "kernels_simt.cu", "decode.cu", "lifter.cu", "conv_tc.cu", "bytetrack.cu", "detector.cu", "vit.cu"]
-HEADERS = ["kernels.h", "pe_common.cuh", "engine_internal.h", os.path.join("..", "..", "include", "poseengine.h")]
+SOURCES = ["conv_tc_inst_a.cu", "conv_tc_inst_b.cu", "conv_tc_inst_c.cu", "conv_tc_inst_d.cu", "conv_tc_inst_e.cu", "conv_tc_inst_f.cu",
+           "engine.cu", "kernels_simt.cu", "decode.cu", "lifter.cu", "conv_tc.cu", "bytetrack.cu", "detector.cu", "vit.cu"]
+HEADERS = ["kernels.h", "pe_common.cuh", "conv_tc_kernel.cuh", "engine_internal.h", os.path.join("..", "..", "include", "poseengine.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 # PE_PRECISION=tf32 builds the wide-range TF32x3 variant (8 B/element); default fp16x2 (4 B/element, half the MMAs)
 PRECISION = os.environ.get("PE_PRECISION", "fp16")

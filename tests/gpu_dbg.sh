@@ -1,6 +1,3 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for cfg in "PE_TC_CG=1 PE_TC_SETS=2 PE_TC_AUTOTUNE=0" "PE_TC_CG=1 PE_TC_SETS=2 PE_TC_AUTOTUNE=1"; do
-echo "== $cfg"
-env $cfg PE_TC_VERBOSE=2 timeout 120 python tests/layer_perf.py 16 1 2>&1 | grep -E "conv_tc|forward|rror" | tail -8 | cut -c1-260
-done
+PE_TC_CG=1 PE_TC_SETS=3 PE_TC_POLL_NS=0 PE_TC_VERBOSE=1 timeout 600 compute-sanitizer --tool memcheck --print-limit 5 python tests/tc_bringup.py 17 2>&1 | grep -v "^conv_tc tune" | head -60

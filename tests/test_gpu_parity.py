@@ -420,7 +420,9 @@ def test_conv_tilings_are_bit_identical(eng):
 
     checked = 0
     for env in ({"PE_TC_MT": 1}, {"PE_TC_MT": 2}, {"PE_TC_NS": 2}, {"PE_TC_AUTOTUNE": 1}, {"PE_TC_CG": 1}, {"PE_TC_CG": 2},
-                {"PE_TC_CG": 2, "PE_TC_NS": 1}, {"PE_TC_CG": 2, "PE_TC_MT": 2}):       # CG = 2: CTA-pair form (M = 256 MMAs)
+                {"PE_TC_CG": 2, "PE_TC_NS": 1}, {"PE_TC_CG": 2, "PE_TC_MT": 2},        # CG = 2: CTA-pair form (M = 256 MMAs)
+                {"PE_TC_SETS": 2}, {"PE_TC_SETS": 3}, {"PE_TC_SETS": 4}, {"PE_TC_CG": 2, "PE_TC_SETS": 2},     # epilogue organisations
+                {"PE_TC_CG": 2, "PE_TC_SETS": 3}, {"PE_TC_CG": 2, "PE_TC_SETS": 4, "PE_TC_MT": 2}, {"PE_TC_SETS": 1, "PE_TC_DSTORE": 1}):
         got = forced(run, env)
         if got is not None:
             checked += 1

@@ -211,8 +211,8 @@ def test_conv_planner_candidates_respect_hardware_limits():
                     ns, mt, nc, kc, S, nstg, stage, smem, tmem, rpg, ndrain, rows, cg, sets = buf[14 * i:14 * i + 14]
                     assert cg in (1, 2) and (cg == 1 or (nc % 16 == 0 and (nc // 2) % 8 == 0))
                     assert ns * nc == op.cout and nc % 16 == 0 and nc <= 128 and mt in (1, 2)
-                    assert 2 <= S <= 4 and 1 <= nstg <= 4
-                    assert sets in (1, 2) and smem <= 227 * 1024 and S * stage + (12 if sets == 1 else 16) * nstg * 32 * chunk_bytes <= smem
+                    assert 2 <= S <= 4 and 1 <= nstg <= (8 if sets == 3 else 4)
+                    assert sets in (1, 2, 3, 4) and smem <= 227 * 1024 and S * stage + {1: 12, 2: 16, 3: 4, 4: 8}[sets] * nstg * 32 * chunk_bytes <= smem
                     assert stage % (8 * chunk_bytes) == 0 and rows % 8 == 0
                     n_main = 3 if mt * nc // 16 <= 6 else 2
                     assert (n_main + 2) * mt * nc <= tmem <= 512
