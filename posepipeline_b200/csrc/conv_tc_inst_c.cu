@@ -13,6 +13,6 @@
   TCK(2, 64, taps, kc, 2, sets) TCK(1, 80, taps, kc, 2, sets) TCK(1, 96, taps, kc, 2, sets) TCK(1, 128, taps, kc, 2, sets)
 
 TcKernelFn tc_kernel_for_c(int MT, int NC, int TAPS, int KC, int CG, int SETS) {
-  TCK_SHAPES(4, 1, 1)
+  TCK_SHAPES(4, 1, 1) TCK_SHAPES(4, 1, 3) TCK_SHAPES(4, 1, 4)
   return nullptr;
 }

@@ -110,6 +110,12 @@ struct TcParams {
   // packed weights at plan creation, so any channel order / pruned block is handled): the MMA warps skip those steps.
   // Adding an exact zero product leaves an accumulator unchanged, so the results are bit-identical.
   uint32_t zmask[32];
+  // With skipped taps a drain group of p.rpg stencil rows holds fewer than MAX_ACC_STEPS MMA steps (3.4 on average instead of 6), so
+  // the 2x2 layers drained 1.8x as often per useful MMA as the 3x3 layers.  closemask (bit r = stencil row r of a tile, r = 2 *
+  // chunk + dy, closes its drain group) regroups the rows greedily by ISSUED steps; a function of the layer's weights only, so every
+  // tiling of the layer still sums in the same order.
+  uint32_t closemask[16];
+  int use_closemask;
   // Direct output stores: the epilogue warp stages its 32 rows x one chunk in shared memory as before, reads them back
   // TRANSPOSED (CHB/16 lanes per row) and writes them with plain 16-byte global stores -- 32/(CHB/16) whole row chunks per
   // instruction -- instead of one TMA store per group.  Measured: issuing a bulk tensor store blocks the warp for 300-850 clocks
@@ -583,7 +589,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const uint32_t d_main = tmem_base + dg * GC;
               if (rig == 0) fresh = 1u;         // no MMA has written this drain group's accumulator yet
               ++row_no;
-              const bool close = (++rig == p.rpg) || (row_no == total_rows);
+              ++rig;
+              const bool close = (TAPS == 4 && p.use_closemask) ? (((p.closemask[((row_no - 1) >> 5) & 15] >> ((row_no - 1) & 31)) & 1u) != 0u)
+                                                                 : ((rig == p.rpg) || (row_no == total_rows));
               // 2x2 form: taps of this stencil row whose weights are all zero for this chunk are skipped -- except that a
               // drain group must not close without a single MMA (its accumulator would hold stale sums)
               uint32_t skip = 0u;

@@ -310,6 +310,7 @@ static int nms_host(std::vector<const float*>& c, float iou_thr, float* out, int
 }
 
 extern "C" int pe_detect(pe_detector* d, const int32_t* frame_idx, int32_t n_frames, float* out_dets, int32_t* out_counts, int32_t max_det) {
+  PeRange whole("pe_detect");
   if (!d || !pe_handle_alive(PE_H_DETECTOR, d)) return pe_fail(PE_ERR_STATE, "detector handle is NULL or was destroyed (with its engine?)");
   if (!frame_idx || n_frames < 0 || !out_dets || !out_counts || max_det <= 0) return pe_fail(PE_ERR_INVALID, "bad argument to pe_detect");
   pe_engine* e = d->e;

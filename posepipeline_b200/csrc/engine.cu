@@ -827,6 +827,7 @@ static int run_decode(pe_model* m, const float* d_hm, const float* d_hm_flip, co
 }
 
 extern "C" int pe_topdown(pe_model* m, const int32_t* frame_idx, const double* bbox_xywh, int32_t n, float* out_kpts) {
+  PeRange whole("pe_topdown");
   int rc = check_crops(m, frame_idx, bbox_xywh, n);
   if (rc) return rc;
   if (!out_kpts) return fail(PE_ERR_INVALID, "out_kpts is NULL");
@@ -837,12 +838,13 @@ extern "C" int pe_topdown(pe_model* m, const int32_t* frame_idx, const double* b
   for (int i0 = 0; i0 < n; i0 += maxc) {
     const int nc = std::min(maxc, n - i0);
     const int nimg = nc * (m->d.flip_test ? 2 : 1);
-    if ((rc = stage_crops(m, frame_idx, bbox_xywh, i0, nc))) return rc;
-    if ((rc = forward(m, nc, nimg))) return rc;
-    if ((rc = run_decode(m, m->d_hm, m->d.flip_test ? m->d_hm + hm_img * nc : nullptr, m->d_cs, m->d_cs + 2 * maxc, nc, m->d_out))) return rc;
+    { PeRange r("pe_topdown/stage_crops"); if ((rc = stage_crops(m, frame_idx, bbox_xywh, i0, nc))) return rc; }
+    { PeRange r("pe_topdown/forward"); if ((rc = forward(m, nc, nimg))) return rc; }
+    { PeRange r("pe_topdown/decode");
+      if ((rc = run_decode(m, m->d_hm, m->d.flip_test ? m->d_hm + hm_img * nc : nullptr, m->d_cs, m->d_cs + 2 * maxc, nc, m->d_out))) return rc; }
     CU(cudaMemcpyAsync(m->h_out, m->d_out, sizeof(float) * (size_t)nc * K * 3, cudaMemcpyDeviceToHost, st));
     CU(flag_fetch(m));
-    CU(cudaStreamSynchronize(st));
+    { PeRange r("pe_topdown/wait"); CU(cudaStreamSynchronize(st)); }
     if ((rc = profile_collect(m))) return rc;
     if ((rc = flag_check(m))) return rc;
     memcpy(out_kpts + (size_t)i0 * K * 3, m->h_out, sizeof(float) * (size_t)nc * K * 3);

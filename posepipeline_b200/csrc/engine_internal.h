@@ -3,6 +3,16 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <vector>
+#include <nvtx3/nvToolsExt.h>      // header-only NVTX v3: the ranges cost nothing unless a profiler (nsys / ncu --nvtx) is attached
+
+// NVTX range for one host-side stage of an entry point ("pe_topdown/forward", ...): shows up on the timeline next to the
+// per-stage CUDA-event timers (pe_model_profile)
+struct PeRange {
+  explicit PeRange(const char* name) { nvtxRangePushA(name); }
+  ~PeRange() { nvtxRangePop(); }
+  PeRange(const PeRange&) = delete;
+  PeRange& operator=(const PeRange&) = delete;
+};
 
 #include "../../include/poseengine.h"
 

@@ -131,6 +131,7 @@ extern "C" int pe_lifter_uses_tensor_cores(pe_lifter* l) {
 }
 
 extern "C" int pe_lift3d(pe_lifter* l, const float* kp2d_norm, int32_t n_frames, float* out3d) {
+  PeRange whole("pe_lift3d");
   if (!l || !pe_handle_alive(PE_H_LIFTER, l)) return pe_set_error(PE_ERR_STATE, "lifter handle is NULL or was destroyed (with its engine?)");
   if (!kp2d_norm || !out3d || n_frames <= 0) return pe_set_error(PE_ERR_INVALID, "bad argument to pe_lift3d");
   cudaSetDevice(l->device);

@@ -17,13 +17,17 @@ open("gpurun_out/launches_$TAG.csv", "w").write(hdr + "".join(last))
 print("launch list: %d launches in total, last step has %d" % (len(body), len(last)))
 PY
 python profiles/summarize_launches.py gpurun_out/launches_$TAG.csv --by-grid > gpurun_out/launches_$TAG.md; head -24 gpurun_out/launches_$TAG.md
-for spec in "6, 2, 9, 1:400:4:k48" "8, 1, 1, 1:40:4:l1" "6, 1, 9, 1:400:6:k96"; do
+# ncu --set full captures: the 48 -> 48 3x3 layers (one-CTA form), the 96 / 192-channel 3x3 layers (CTA-pair forms, whichever epilogue
+# organisation the tuner picked), layer1's 1x1 + residual.  Template arguments: <NG, MT, TAPS, KC, CG, SETS>
+I='\\(int\\)'
+for spec in "6, 2, 9, 1, [12], [1234]:400:4:k48" "6, 1, 9, 1, 2, [1234]:600:6:k96" "8, 1, 1, [124], [12], 1:40:3:l1"; do
   IFS=: read tpl skip cnt name <<< "$spec"
-  tpl=$(echo "$tpl" | sed -E 's/([0-9]+)/\\(int\\)\1/g')          # demangled names read conv_tc_kernel<(int)6, (int)2, ...>
+  tpl=$(echo "$tpl" | sed -E "s/(\\[[0-9]+\\]|[0-9]+)/$I\\1/g")          # demangled names read conv_tc_kernel<(int)6, (int)2, ...>
   timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:conv_tc_kernel<$tpl>" --launch-skip $skip --launch-count $cnt -o gpurun_out/full_${TAG}_$name -f \
       python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-secondary --no-parity > gpurun_out/ncu_full_${TAG}_$name.log 2>&1
   ncu -i gpurun_out/full_${TAG}_$name.ncu-rep --page raw --csv > gpurun_out/full_${TAG}_$name.csv 2>/dev/null
   python profiles/ncu_summary.py gpurun_out/full_${TAG}_$name.csv $( [ $name = k48 ] && echo --json gpurun_out/top_kernel_traffic_$TAG.json ) > gpurun_out/full_${TAG}_$name.md; head -14 gpurun_out/full_${TAG}_$name.md | cut -c1-260
+  rm -f gpurun_out/full_${TAG}_$name.ncu-rep
 done
 # BASELINE configs[3] through the wrappers on one GPU (N>1: tests/gpu_pipeline_ngpu.sh under gpurun --gpus N)
 timeout 900 python tools/bench_pipeline.py --frames 256 > gpurun_out/pipeline_${TAG}_n1.json 2> gpurun_out/pipeline_${TAG}_n1.err; tail -c 1500 gpurun_out/pipeline_${TAG}_n1.json; tail -3 gpurun_out/pipeline_${TAG}_n1.err
