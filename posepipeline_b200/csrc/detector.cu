@@ -199,13 +199,19 @@ extern "C" int pe_detector_create(pe_engine* e, const pe_det_desc* desc, const p
   return PE_OK;
 }
 
-// the layer program for nimg frames whose staged-frame indices are in d_fidx; candidates land in d_cand / d_count
-static int det_forward_eager(pe_detector* d, int nimg) {
+// the layer program for nimg frames whose staged-frame indices are in d_fidx; candidates land in d_cand / d_count.
+// part: DET_INPUT = only the input ops (resize / pad / Focus from the STAGED FRAMES), DET_NET = everything else, DET_ALL = both.
+// The input ops take the engine's current staged-frames pointer as a kernel argument, and that pointer changes from block to
+// block (upload slots, resident frame cache): they must never be part of a captured graph -- a replay would read the frames
+// that were staged when the graph was captured.
+enum { DET_INPUT = 1, DET_NET = 2, DET_ALL = 3 };
+static int det_forward_eager(pe_detector* d, int nimg, int part = DET_ALL) {
   cudaStream_t st = d->e->stream;
   const pe_det_desc& dd = d->d;
-  CUD(cudaMemsetAsync(d->d_count, 0, sizeof(int) * nimg, st));
+  if (part & DET_NET) CUD(cudaMemsetAsync(d->d_count, 0, sizeof(int) * nimg, st));
   for (size_t i = 0; i < d->ops.size(); ++i) {
     const pe_gop_desc& op = d->ops[i];
+    if (!(part & (op.kind == PE_GOP_INPUT ? DET_INPUT : DET_NET))) continue;
     switch (op.kind) {
       case PE_GOP_INPUT: {
         const pe_tensor_desc& to = d->tensors[op.out];
@@ -253,28 +259,32 @@ static int det_forward(pe_detector* d, int nimg) {
   static const bool use_graph = !(getenv("PE_GRAPH") && atoi(getenv("PE_GRAPH")) == 0);
   if (!use_graph) return det_forward_eager(d, nimg);
   cudaStream_t st = d->e->stream;
+  if (d->graphs[nimg] || d->graph_seen[nimg] != 0) {        // graph path: the input ops run eagerly in front of the (replayed / captured) network
+    const int rci = det_forward_eager(d, nimg, DET_INPUT);
+    if (rci != PE_OK) return rci;
+  }
   if (d->graphs[nimg]) {
     CUD(cudaGraphLaunch(d->graphs[nimg], st));
     d->launches += d->graph_launches[nimg];
     return PE_OK;
   }
   if (d->graph_seen[nimg]++ == 0) return det_forward_eager(d, nimg);      // first time eager: one-time attribute calls, warm-up
-  if (d->graph_seen[nimg] < 0) return det_forward_eager(d, nimg);
+  if (d->graph_seen[nimg] < 0) return det_forward_eager(d, nimg, DET_NET);
   const int64_t l0 = d->launches;
   cudaGraph_t graph = nullptr;
   CUD(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-  const int rc = det_forward_eager(d, nimg);
+  const int rc = det_forward_eager(d, nimg, DET_NET);
   const cudaError_t ce = cudaStreamEndCapture(st, &graph);
   if (rc != PE_OK || ce != cudaSuccess || !graph) {
     if (graph) cudaGraphDestroy(graph);
     cudaGetLastError();
     d->graph_seen[nimg] = -1000000;
-    return rc != PE_OK ? rc : det_forward_eager(d, nimg);
+    return rc != PE_OK ? rc : det_forward_eager(d, nimg, DET_NET);
   }
   d->graph_launches[nimg] = d->launches - l0;
   const cudaError_t ci = cudaGraphInstantiate(&d->graphs[nimg], graph, 0);
   cudaGraphDestroy(graph);
-  if (ci != cudaSuccess) { d->graphs[nimg] = nullptr; d->graph_seen[nimg] = -1000000; cudaGetLastError(); return det_forward_eager(d, nimg); }
+  if (ci != cudaSuccess) { d->graphs[nimg] = nullptr; d->graph_seen[nimg] = -1000000; cudaGetLastError(); return det_forward_eager(d, nimg, DET_NET); }
   CUD(cudaGraphLaunch(d->graphs[nimg], st));
   return PE_OK;
 }

@@ -177,3 +177,45 @@ def test_mmtrack_bounding_boxes_on_video(tmp_path, monkeypatch, eng, sd, oracle_
     print(f"bytetrack on video: {len(n_ids)} track ids, frames with differing id lists: {mismatched}/10")
     assert mismatched == 0 and len(n_ids) >= 1
     W._detector.close()
+
+
+def test_block_reader_detections_equal_host_frame_detections(tmp_path, eng, sd):
+    """Many blocks through the frame source (upload slots / the resident frame cache: the staged-frames pointer changes from
+    block to block) against the same detector on host frames, bit for bit, from the very first call on.  Regression: the
+    detector's input kernel used to be inside the captured CUDA graph with the staged-frames pointer baked in, so from the third
+    forward of a batch size on every block was computed on the frames staged at capture time (found by the 2-GPU
+    sharded-vs-single check of tools/bench_pipeline.py)."""
+    from posepipeline_b200 import frames as F
+    base = synthetic_frame(9, 360, 640)
+    frames = [np.ascontiguousarray(np.roll(base, (2 * i, 7 * i), axis=(0, 1))) for i in range(44)]
+    path = str(tmp_path / "blocks.mp4")
+    fakes.write_video(path, frames)
+    decoded = np.stack(fakes.read_video(path))
+    assert len(decoded) == 44
+    for use_cache in (False, True):
+        pool = D.DetectorPool(eng, sd, max_frames=4)
+        try:
+            writer = F.CACHE.begin("test-blocks-%d" % use_cache, len(decoded), 360, 640, eng.device, first=0) if use_cache else None
+            reader = F.BlockReader(path, eng, 8, 0, len(decoded), cache_writer=writer)
+            got = []
+            try:
+                for blk in reader:
+                    got.extend(pool.detect_block(reader, blk))
+            finally:
+                reader.close()
+            ref = [d for i in range(0, len(decoded), 4) for d in pool.detect(decoded[i:i + 4])]
+            again = []
+            reader = F.BlockReader(path, eng, 8, 0, len(decoded))
+            try:
+                for blk in reader:
+                    again.extend(pool.detect_block(reader, blk))
+            finally:
+                reader.close()
+        finally:
+            pool.close()
+        assert len(got) == len(ref) == len(again) == 44
+        assert sum(len(d) for d in ref) > 0
+        for f in range(44):
+            assert got[f].shape == ref[f].shape and np.array_equal(got[f], ref[f]), (use_cache, f)
+            assert np.array_equal(again[f], ref[f]), (use_cache, f)
+    F.CACHE.clear()

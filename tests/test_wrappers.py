@@ -135,7 +135,7 @@ def test_frame_sharding_world2_gloo_matches_single_rank(tmp_path, monkeypatch):
     procs = [ctx.Process(target=_worker, args=(r, 2, port, str(tmp_path), q)) for r in range(2)]
     for p in procs:
         p.start()
-    got = [q.get(timeout=120) for _ in procs]
+    got = [q.get(timeout=400) for _ in procs]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -197,7 +197,7 @@ def test_mmtrack_sharded_detector_world2_matches_single_rank(tmp_path, monkeypat
     procs = [ctx.Process(target=_track_worker, args=(r, 2, port, str(tmp_path), q)) for r in range(2)]
     for p in procs:
         p.start()
-    got = [q.get(timeout=120) for _ in procs]
+    got = [q.get(timeout=400) for _ in procs]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
