@@ -20,7 +20,7 @@ python profiles/summarize_launches.py gpurun_out/launches_$TAG.csv --by-grid > g
 # ncu --set full captures: the 48 -> 48 3x3 layers (one-CTA form), the 96 / 192-channel 3x3 layers (CTA-pair forms, whichever epilogue
 # organisation the tuner picked), layer1's 1x1 + residual.  Template arguments: <NG, MT, TAPS, KC, CG, SETS>
 I='\\(int\\)'
-for spec in "6, 2, 9, 1, [12], [1234]:400:4:k48" "6, 1, 9, 1, 2, [1234]:600:6:k96" "8, 1, 1, [124], [12], 1:40:3:l1"; do
+for spec in "6, 2, 9, 1, [12], [1234]:750:4:k48" "6, 1, 9, 1, 2, [1234]:700:6:k96"; do
   IFS=: read tpl skip cnt name <<< "$spec"
   tpl=$(echo "$tpl" | sed -E "s/(\\[[0-9]+\\]|[0-9]+)/$I\\1/g")          # demangled names read conv_tc_kernel<(int)6, (int)2, ...>
   timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:conv_tc_kernel<$tpl>" --launch-skip $skip --launch-count $cnt -o gpurun_out/full_${TAG}_$name -f \
