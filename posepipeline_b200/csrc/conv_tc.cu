@@ -518,6 +518,18 @@ cudaError_t tc_conv_launch_rows(TcConvPlan* pl, long long rows, cudaStream_t st)
   p.M = rows;
   p.tiles_m = (int)((p.M + 128LL * pl->MT * pl->CG - 1) / (128LL * pl->MT * pl->CG));
   p.total_work = p.tiles_m * pl->ns;
+  // schedule (tc_work_item): with several N slices, groups of M tiles whose activation rows (<= 48 MB) stay in L2 while the
+  // CTAs walk through the slices; PE_TC_GROUP=0 keeps the n-major order, PE_TC_GROUP_KB sets the budget (tests).  Gather layers index windows by tile in the MMA warps
+  // (n-major arithmetic) and have at most a few slices: unchanged.
+  p.nsplit = pl->ns; p.grp = 0;
+  // Only where the repeated activation reads weigh at least as much as the output itself, Cin * (ns - 1) >= Cout: the wide 1x1
+  // layers of HRNet's layer1 (64 -> 256, HBM-bound on the output and the residual) measured 8 % slower grouped.
+  const int group_mode = env_int("PE_TC_GROUP", 1);            // 0 never, 1 by the rule, 2 whenever there are several slices
+  if (pl->ns > 1 && !p.gather && group_mode && (group_mode > 1 || (long long)p.nchunk * 16 * (pl->ns - 1) >= p.Cout)) {
+    const double tile_bytes = 128.0 * pl->MT * pl->CG * p.nchunk * CHB;
+    const long long g = (long long)(env_int("PE_TC_GROUP_KB", 48 * 1024) * 1024.0 / tile_bytes);
+    p.grp = (int)std::max<long long>(1, std::min<long long>(g, p.tiles_m));
+  }
   unsigned grid;
   if (pl->CG == 2) {
     grid = (unsigned)(2 * std::min(p.total_work, pl->max_ctas / 2));

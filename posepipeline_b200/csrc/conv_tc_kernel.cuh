@@ -100,7 +100,8 @@ struct TcParams {
   uint32_t div_hpwp_mul, div_hpwp_sh, div_wp_mul, div_wp_sh;   // exact n / (Hp*Wp) and n / Wp for n < 2^31: (n * mul) >> sh (64-bit product)
   int mma_wait_ns;           // MMA warps: 0 = spin on test_wait (default), > 0 = suspended try_wait with this time hint
   int poll_ns;               // producer / epilogue waits: > 0 nanosleep back-off between polls, < 0 suspended try_wait with that time hint, 0 spin
-  int tiles_m, total_work;   // persistent schedule: work item w -> (tile = w % tiles_m, n-slice = w / tiles_m)
+  int tiles_m, total_work;   // persistent schedule: work item w -> (tile = w % tiles_m, n-slice = w / tiles_m) when grp == 0
+  int grp, nsplit;           // grp > 0: groups of grp M tiles, all nsplit N slices of a group before the next group (tc_work_item)
   uint32_t a_bytes, stage_bytes;
   unsigned int* flag;        // range flag of the forward (kernels.h pe_range_flag), or nullptr
   long long* prof;
@@ -397,6 +398,19 @@ __device__ __forceinline__ uint64_t desc64(uint32_t hi, uint32_t lo) {
   return d;
 }
 
+// Persistent schedule.  n-major (grp == 0): the CTAs sweep all M tiles for one N slice, then the next slice -- every slice
+// streams the whole activation matrix again, which is free while that matrix stays in L2 (HRNet: at most two slices) and was
+// the bound of the ViT / lifter / detector GEMMs (fc1: 24 slices x 302 MB = 7.2 GB per launch, 213 TFLOP/s).  Grouped
+// (grp > 0): groups of grp M tiles whose activation rows fit in L2, every N slice of a group before the next group; the
+// weight matrix (a few MB) stays resident.  The per-tile arithmetic does not depend on the order: bit-identical results.
+__device__ __forceinline__ void tc_work_item(const TcParams& p, int w, int& tile, int& nsl) {
+  if (p.grp <= 0) { tile = w % p.tiles_m; nsl = w / p.tiles_m; return; }
+  const int span = p.grp * p.nsplit, g = w / span, base = g * p.grp;
+  const int gc = min(p.grp, p.tiles_m - base), r = w - g * span;
+  nsl = r / gc;
+  tile = base + r - nsl * gc;
+}
+
 template <int NG, int MT, int TAPS, int KC, int CG, int SETS>
 __global__ void __launch_bounds__(tc_threads(SETS), 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
@@ -472,7 +486,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmW) : "memory");
       Ring r;
-      int tile = wfirst % p.tiles_m, nsl = wfirst / p.tiles_m;
+      int tile = 0, nsl = 0;
+      if (wfirst < p.total_work) tc_work_item(p, wfirst, tile, nsl);
       uint32_t tx = (uint32_t)KC * (a_bytes + b_chunk_bytes);
       const bool gather = TAPS == 4 && p.gather;
       const uint32_t full0 = (CG == 2) ? mapa_rank(bar_full, 0u) : bar_full;    // pair mode: the LEADER's full barriers (cluster address)
@@ -521,8 +536,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           r.advance(p.S);
         }
-        tile += wstep;
-        while (tile >= p.tiles_m) { tile -= p.tiles_m; ++nsl; }
+        if (p.grp > 0) { if (w + wstep < p.total_work) tc_work_item(p, w + wstep, tile, nsl); }
+        else { tile += wstep; while (tile >= p.tiles_m) { tile -= p.tiles_m; ++nsl; } }
       }
     }
   } else if ((warp == 1 || warp == 2 + EPI_WARPS) && rank == 0) {
@@ -746,7 +761,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // (dg, dgp) = `main` buffer / phase of the tile's first drain group: the other set's tiles advance it by ndrain each
     uint32_t tl = (uint32_t)eset;
     uint32_t dg = ((uint32_t)eset * (uint32_t)ndrain) % NMAIN, dgp = (((uint32_t)eset * (uint32_t)ndrain) / NMAIN) & 1u;
-    int tile = ewfirst % p.tiles_m, nsl = ewfirst / p.tiles_m;
+    int tile = 0, nsl = 0;
+    if (ewfirst < p.total_work) tc_work_item(p, ewfirst, tile, nsl);
     constexpr int NV = CHB / 16;                         // 16-byte vectors per row chunk
     // "accumulator drained" signals go to the CTA whose warps issue the MMAs: the leader of the pair
     const uint32_t main_empty0 = (CG == 2) ? mapa_rank(bar_main_empty, 0u) : bar_main_empty;
@@ -933,7 +949,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       const uint32_t interior_cur = interior;
       int tile_n = tile + ewstep, nsl_n = nsl;
-      while (tile_n >= p.tiles_m) { tile_n -= p.tiles_m; ++nsl_n; }
+      if (p.grp > 0) { if (w + ewstep < p.total_work) tc_work_item(p, w + ewstep, tile_n, nsl_n); }
+      else { while (tile_n >= p.tiles_m) { tile_n -= p.tiles_m; ++nsl_n; } }
       // cross terms: committed by MMA warp Y at the end of the tile
       const uint32_t cbuf = tl & 1u;
       if (ROLE == 2) mbar_wait_relaxed(bar_sum + 8 * cbuf, (tl >> 1) & 1u, p.poll_ns);       // the drain warps' sums are in corr buffer cbuf

@@ -8,6 +8,7 @@
 #include <string>
 #include <vector>
 #include <map>
+#include <tuple>
 #include <mutex>
 #include <set>
 #include <algorithm>
@@ -513,6 +514,9 @@ extern "C" int pe_model_create(pe_engine* e, const pe_model_desc* desc, const pe
   if (desc->max_crops <= 0 || desc->n_ops <= 0) return fail(PE_ERR_INVALID, "bad model description");
   if ((desc->post_process == PE_POST_UNBIASED || desc->post_process == PE_POST_UDP) && (desc->blur_kernel < 3 || desc->blur_kernel > 63 || desc->blur_kernel % 2 == 0))
     return fail(PE_ERR_INVALID, "blur kernel must be odd and in [3,63]");
+  for (int i = 0; i < desc->n_ops; ++i)
+    if (ops[i].kind == PE_OP_CONV && ops[i].stride == 2 && ops[i].residual >= 0)
+      return fail(PE_ERR_INVALID, "op %d: a stride-2 convolution cannot carry a residual (neither stride-2 plan reads one)", i);
   CU(cudaSetDevice(e->device));
   pe_model* m = new pe_model();
   m->e = e; m->d = *desc;
@@ -572,6 +576,7 @@ extern "C" int pe_model_create(pe_engine* e, const pe_model_desc* desc, const pe
     if (s2d_floats) { CUM(cudaMalloc(&m->d_s2d, s2d_floats * sizeof(float))); CUM(cudaMemsetAsync(m->d_s2d, 0, s2d_floats * sizeof(float), e->stream)); }
     CUM(cudaStreamSynchronize(e->stream));   // weights and zeroed slots are in place: plan creation times candidate tilings on them
     m->const_res.assign(desc->n_ops, nullptr);
+    int s2d_last_in = -1;                    // input tensor of the most recent stride-2 op that uses the s2d scratch
     for (int i = 0; i < desc->n_ops; ++i) {
       const pe_op_desc& op = m->ops[i];
       if (op.kind == PE_OP_GEMM) {
@@ -607,15 +612,70 @@ extern "C" int pe_model_create(pe_engine* e, const pe_model_desc* desc, const pe
       TcConvPlan* plan = nullptr;
       const bool s2 = op.stride == 2;
       cudaError_t ce = cudaErrorNotSupported;
-      if (s2)   // first choice: TMA gathers the strided rows from the input tensor itself
-        ce = tc_conv_plan_create(&plan, nullptr, act_ptr(m, op.out), nullptr, m->d_w + op.wtc_off, m->d_w + op.b_off, 4 * op.cin, op.cout, 2,
-                                 op.relu, to.H, to.W, maximg, act_ptr(m, op.in[0]));
-      if (ce == cudaErrorNotSupported) {
-        ce = tc_conv_plan_create(&plan, s2 ? m->d_s2d : act_ptr(m, op.in[0]), act_ptr(m, op.out),
+      if (s2) {
+        // Two forms of a stride-2 layer, bit-identical (tests/test_gpu_parity.py::test_stride2_tma_gather_equals_space_to_depth_copy):
+        // TMA gathers the strided rows from the input tensor itself (no copy, but one-CTA forms only and element-stride TMA is
+        // slow), or the s2d_kernel copy + the plain 2x2 layer (every CTA-pair / split-epilogue form; the copy is skipped when the
+        // scratch already holds this input: HRNet's fuse layers feed one tensor to up to three stride-2 convolutions).
+        // Chosen by measurement per op; PE_TC_S2D=0 / 1 pins the gather / the copy form.
+        static const int s2d_mode = getenv("PE_TC_S2D") ? atoi(getenv("PE_TC_S2D")) : -1;
+        const pe_tensor_desc& ti = m->tensors[op.in[0]];
+        TcConvPlan *pg = nullptr, *ps = nullptr;
+        cudaError_t cg = cudaErrorNotSupported, cs = cudaErrorNotSupported;
+        if (s2d_mode != 1)
+          cg = tc_conv_plan_create(&pg, nullptr, act_ptr(m, op.out), nullptr, m->d_w + op.wtc_off, m->d_w + op.b_off, 4 * op.cin, op.cout, 2,
+                                   op.relu, to.H, to.W, maximg, act_ptr(m, op.in[0]));
+        // measured (profiles/r02_stride2_forms.txt): the copy form wins only at the smallest output grids (12x9: 0.42 vs 0.49 ms
+        // for 192 -> 384); elsewhere the copy's own HBM traffic costs more than the gather loses, so it is not even tuned there
+        if (s2d_mode == 1 || cg == cudaErrorNotSupported || (s2d_mode != 0 && to.H * to.W <= 160))
+          cs = tc_conv_plan_create(&ps, m->d_s2d, act_ptr(m, op.out), nullptr, m->d_w + op.wtc_off, m->d_w + op.b_off, 4 * op.cin, op.cout, 2,
+                                   op.relu, to.H, to.W, maximg);
+        bool use_copy = cs == cudaSuccess && cg != cudaSuccess;
+        const bool reuse = s2d_last_in == op.in[0];
+        if (cs == cudaSuccess && cg == cudaSuccess) {
+          typedef std::tuple<int, int, int, int, int, int> S2Key;
+          static std::map<S2Key, bool>* choice = new std::map<S2Key, bool>();
+          const S2Key key(op.cin, op.cout, to.H, to.W, maximg, reuse ? 1 : 0);
+          auto hit = choice->find(key);
+          if (hit != choice->end()) use_copy = hit->second;
+          else {
+            unsigned int* const saved_flag = pe_range_flag();
+            pe_range_flag() = nullptr;                                   // timing runs read uninitialised buffers
+            cudaEvent_t e0, e1;
+            cudaEventCreate(&e0); cudaEventCreate(&e1);
+            float med[2] = {0.f, 0.f};
+            for (int form = 0; form < 2; ++form) {
+              std::vector<float> t;
+              for (int rep = 0; rep < 8; ++rep) {
+                cudaEventRecord(e0, e->stream);
+                if (form == 1 && !reuse) launch_s2d(act_ptr(m, op.in[0]), op.cin, ti.H, ti.W, maximg, m->d_s2d, to.H, to.W, e->stream);
+                tc_conv_launch(form ? ps : pg, maximg, e->stream);
+                cudaEventRecord(e1, e->stream);
+                cudaEventSynchronize(e1);
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, e0, e1);
+                if (rep) t.push_back(ms);
+              }
+              std::sort(t.begin(), t.end());
+              med[form] = t[t.size() / 2];
+            }
+            cudaEventDestroy(e0); cudaEventDestroy(e1);
+            pe_range_flag() = saved_flag;
+            use_copy = med[1] < med[0];
+            (*choice)[key] = use_copy;
+            if (getenv("PE_TC_VERBOSE") && atoi(getenv("PE_TC_VERBOSE")))
+              fprintf(stderr, "stride-2 %d -> %d @%dx%d (%d images%s): gather %.3f ms, s2d copy + 2x2 %.3f ms -> %s\n", op.cin, op.cout, to.H, to.W,
+                      maximg, reuse ? ", copy reused" : "", med[0], med[1], use_copy ? "copy" : "gather");
+            if (cudaGetLastError() != cudaSuccess) use_copy = false;
+          }
+        }
+        if (use_copy) { plan = ps; ce = cs; tc_conv_plan_destroy(pg); m->tc_s2d[i] = 1; s2d_last_in = op.in[0]; }
+        else { plan = pg; ce = cg; tc_conv_plan_destroy(ps); }
+        if (ce == cudaErrorNotSupported && cs != cudaErrorNotSupported) ce = cs;
+      } else {
+        ce = tc_conv_plan_create(&plan, act_ptr(m, op.in[0]), act_ptr(m, op.out),
                                  op.residual >= 0 ? act_ptr(m, op.residual) : nullptr, m->d_w + op.wtc_off,
-                                 m->d_w + op.b_off, s2 ? 4 * op.cin : op.cin, op.cout, s2 ? 2 : op.ksize, op.relu,
-                                 to.H, to.W, maximg);
-        if (ce == cudaSuccess && s2) m->tc_s2d[i] = 1;
+                                 m->d_w + op.b_off, op.cin, op.cout, op.ksize, op.relu, to.H, to.W, maximg);
       }
       if (ce == cudaSuccess) m->tc[i] = plan;
       else if (ce != cudaErrorNotSupported) {
@@ -674,8 +734,10 @@ static int forward_eager(pe_model* m, int ncrop, int nimg) {
   const pe_model_desc& d = m->d;
   m->ev_used = 0;
   if (m->profile) cudaEventRecord(m->ev_fwd0, st);
+  int s2d_src = -1;                          // tensor whose space-to-depth copy the scratch holds
   for (size_t i = 0; i < m->ops.size(); ++i) {
     const pe_op_desc& op = m->ops[i];
+    if (op.out == s2d_src) s2d_src = -1;
     const pe_tensor_desc& to = m->tensors[op.out];
     const bool is_conv = (op.kind == PE_OP_CONV || op.kind == PE_OP_GEMM);
     const bool timed = m->profile && (is_conv || m->profile > 1);
@@ -697,7 +759,11 @@ static int forward_eager(pe_model* m, int ncrop, int nimg) {
       case PE_OP_CONV: {
         const pe_tensor_desc& ti = m->tensors[op.in[0]];
         if (m->tc[i]) {
-          if (m->tc_s2d[i]) { launch_s2d(act_ptr(m, op.in[0]), op.cin, ti.H, ti.W, nimg, m->d_s2d, to.H, to.W, st); ++m->launches; }
+          if (m->tc_s2d[i] && s2d_src != op.in[0]) {           // the scratch may still hold this tensor's copy (see pe_model_create)
+            launch_s2d(act_ptr(m, op.in[0]), op.cin, ti.H, ti.W, nimg, m->d_s2d, to.H, to.W, st);
+            ++m->launches;
+            s2d_src = op.in[0];
+          }
           cudaError_t ce = tc_conv_launch(m->tc[i], nimg, st);
           if (ce != cudaSuccess) return fail(PE_ERR_CUDA, "tensor-core conv op %zu: %s", i, cudaGetErrorString(ce));
         } else {

@@ -373,88 +373,56 @@ struct FuseArgs {
   unsigned int* flag;
 };
 
-// One thread per (padded position, 16-channel chunk): a chunk is PS_CHUNK_BYTES contiguous bytes, so every access is a
-// run of 16-byte vectors and consecutive threads touch consecutive chunks (HBM-bound op: 4-channel threads with 8-byte
-// accesses reached 27 % of the copy bandwidth).
-__device__ __forceinline__ void chunk_load16(const float* row, int chunk, float (&v)[16]) {
-  const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(row) + (size_t)chunk * PS_CHUNK_BYTES);
-#if PE_FP16
-  const uint4 h0 = __ldg(p), h1 = __ldg(p + 1), l0 = __ldg(p + 2), l1 = __ldg(p + 3);
-  const uint32_t hw[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-  const uint32_t lw[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[i]));
-    const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[i]));
-    v[2 * i] = fmaf(lf.x, PS_LO_INV, hf.x); v[2 * i + 1] = fmaf(lf.y, PS_LO_INV, hf.y);
-  }
-#else
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const uint4 h = __ldg(p + i), l = __ldg(p + 4 + i);
-    v[4 * i + 0] = __uint_as_float(h.x) + __uint_as_float(l.x); v[4 * i + 1] = __uint_as_float(h.y) + __uint_as_float(l.y);
-    v[4 * i + 2] = __uint_as_float(h.z) + __uint_as_float(l.z); v[4 * i + 3] = __uint_as_float(h.w) + __uint_as_float(l.w);
-  }
-#endif
-}
-
-__device__ __forceinline__ void chunk_store16(float* row, int chunk, const float (&v)[16]) {
-  uint4* p = reinterpret_cast<uint4*>(reinterpret_cast<char*>(row) + (size_t)chunk * PS_CHUNK_BYTES);
-#if PE_FP16
-  uint2 h[4], l[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) split4_h(make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]), h[i], l[i]);
-  p[0] = make_uint4(h[0].x, h[0].y, h[1].x, h[1].y); p[1] = make_uint4(h[2].x, h[2].y, h[3].x, h[3].y);
-  p[2] = make_uint4(l[0].x, l[0].y, l[1].x, l[1].y); p[3] = make_uint4(l[2].x, l[2].y, l[3].x, l[3].y);
-#else
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float4 hi, lo;
-    split4(make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]), hi, lo);
-    p[i] = make_uint4(__float_as_uint(hi.x), __float_as_uint(hi.y), __float_as_uint(hi.z), __float_as_uint(hi.w));
-    p[4 + i] = make_uint4(__float_as_uint(lo.x), __float_as_uint(lo.y), __float_as_uint(lo.z), __float_as_uint(lo.w));
-  }
-#endif
-}
-
+// Work unit = (padded position, 16-channel chunk): a chunk is PS_CHUNK_BYTES contiguous bytes, so every access is a run of
+// 16-byte vectors and consecutive threads touch consecutive chunks (4-channel threads with 8-byte accesses reached 27 % of
+// the copy bandwidth).  One CTA per padded output row (img, py), threads over (px, chunk); N_IN is a template parameter so that the loads of all
+// branches are in flight before the first addition (the round-1 kernel looped over the branches at run time behind three
+// 64-bit divisions per thread: 3.1 TB/s at 96x72).  The sum runs in branch order (the reference's fp32 addition order).
+template <int N_IN>
 __global__ void __launch_bounds__(256) fuse_kernel(FuseArgs a) {
   const int nch = a.C >> 4;
-  const long long total = (long long)a.nimg * (a.H + 2) * (a.W + 2) * nch;
-  const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
-  if (t >= total) return;
-  const int chunk = (int)(t % nch);
-  const long long m = t / nch;
   const int Hp = a.H + 2, Wp = a.W + 2;
-  const int img = (int)(m / (Hp * Wp));
-  const int r = (int)(m % (Hp * Wp));
-  const int py = r / Wp, px = r % Wp;
-  const int rowF = ps_row_floats(a.C);
-  float* orow = a.out + m * rowF;
-  uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<char*>(orow) + (size_t)chunk * PS_CHUNK_BYTES);
-  if (py < 1 || py > a.H || px < 1 || px > a.W) {
+  const int img = blockIdx.x / Hp, py = blockIdx.x - img * Hp;
+  const size_t rowB = (size_t)nch * PS_CHUNK_BYTES;
+  char* orow0 = reinterpret_cast<char*>(a.out) + (size_t)blockIdx.x * Wp * rowB;
+  const int n = Wp * nch;
+  const bool yin = py >= 1 && py <= a.H;
+  const char* irow0[N_IN];
+  int sh[N_IN];
 #pragma unroll
-    for (int i = 0; i < PS_CHUNK_BYTES / 16; ++i) op[i] = make_uint4(0u, 0u, 0u, 0u);
-    return;
+  for (int j = 0; j < N_IN; ++j) {                     // first interior position of the source row that feeds output row py
+    sh[j] = 31 - __clz(a.up[j]);                       // up in {1, 2, 4, 8}
+    const int h = a.H >> sh[j], w = a.W >> sh[j];
+    irow0[j] = reinterpret_cast<const char*>(a.in[j]) + (((size_t)img * (h + 2) + ((py - 1) >> sh[j]) + 1) * (w + 2) + 1) * rowB;
   }
-  float s[16];
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const int px = i / nch, chunk = i - px * nch;
+    float* orow = reinterpret_cast<float*>(orow0 + (size_t)px * rowB);
+    if (!yin || px < 1 || px > a.W) {
+      uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<char*>(orow) + (size_t)chunk * PS_CHUNK_BYTES);
 #pragma unroll
-  for (int i = 0; i < 16; ++i) s[i] = 0.f;
-  for (int j = 0; j < a.n_in; ++j) {                   // summed in branch order (fp32 addition order of the reference)
-    const int u = a.up[j];
-    const int h = a.H / u, w = a.W / u;
-    const long long row = ((long long)img * (h + 2) + (py - 1) / u + 1) * (w + 2) + (px - 1) / u + 1;
-    float v[16];
-    chunk_load16(a.in[j] + row * rowF, chunk, v);
+      for (int k = 0; k < PS_CHUNK_BYTES / 16; ++k) op[k] = make_uint4(0u, 0u, 0u, 0u);
+      continue;
+    }
+    float v[N_IN][16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) s[i] += v[i];
+    for (int j = 0; j < N_IN; ++j)
+      chunk_load16(reinterpret_cast<const float*>(irow0[j] + (size_t)((px - 1) >> sh[j]) * rowB), chunk, v[j]);
+    float s[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) s[k] = 0.f;
+#pragma unroll
+    for (int j = 0; j < N_IN; ++j)
+#pragma unroll
+      for (int k = 0; k < 16; ++k) s[k] += v[j][k];
+    if (a.relu) {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) s[k] = fmaxf(s[k], 0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) ps_range_check4(make_float4(s[4 * k], s[4 * k + 1], s[4 * k + 2], s[4 * k + 3]), a.flag);
+    chunk_store16(orow, chunk, s);
   }
-  if (a.relu) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) s[i] = fmaxf(s[i], 0.f);
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) ps_range_check4(make_float4(s[4 * i], s[4 * i + 1], s[4 * i + 2], s[4 * i + 3]), a.flag);
-  chunk_store16(orow, chunk, s);
 }
 
 void launch_fuse(const float* const* in, const int* up, int n_in, float* out, int C, int H, int W, int nimg, int relu,
@@ -462,17 +430,68 @@ void launch_fuse(const float* const* in, const int* up, int n_in, float* out, in
   FuseArgs a;
   for (int j = 0; j < 4; ++j) { a.in[j] = j < n_in ? in[j] : nullptr; a.up[j] = j < n_in ? up[j] : 1; }
   a.n_in = n_in; a.out = out; a.C = C; a.H = H; a.W = W; a.nimg = nimg; a.relu = relu; a.flag = pe_range_flag();
-  long long total = (long long)nimg * (H + 2) * (W + 2) * (C / 16);
-  fuse_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a);
+  const unsigned grid = (unsigned)(nimg * (H + 2));
+  switch (n_in) {
+    case 1: fuse_kernel<1><<<grid, 256, 0, st>>>(a); break;
+    case 2: fuse_kernel<2><<<grid, 256, 0, st>>>(a); break;
+    case 3: fuse_kernel<3><<<grid, 256, 0, st>>>(a); break;
+    default: fuse_kernel<4><<<grid, 256, 0, st>>>(a); break;
+  }
 }
 
 // =============================================================================================
 // Head: final_layer 1x1 conv Cin->K with bias (cfg :73-79) -> planar fp32 heatmaps [img][K][H][W].
 // =============================================================================================
+// One thread = two horizontally adjacent positions x KB output channels: every weight read from shared memory (a broadcast
+// LDS) feeds two FMAs, the input rows arrive as whole 16-channel chunks (16-byte loads), and KB = 17 has no predicated-off
+// lanes for the COCO head (the round-1 kernel issued 32 FMAs + 32 LDS per input channel for 17 joints: 1.3 ms per forward).
+// Accumulation order over the input channels is unchanged (c ascending, bias added last).
+template <int KB>
 __global__ void __launch_bounds__(128) head_kernel(const float* __restrict__ in, int Cin, int H, int W, int nimg,
                                                    const float* __restrict__ w,  // [Cin][K]
                                                    const float* __restrict__ bias, int K, float* __restrict__ out) {
   extern __shared__ float s_w[];  // Cin*K + K
+  for (int i = threadIdx.x; i < Cin * K; i += 128) s_w[i] = w[i];
+  for (int i = threadIdx.x; i < K; i += 128) s_w[Cin * K + i] = bias[i];
+  __syncthreads();
+  const int HW = H * W;                                   // even (W is even: checked by the launcher)
+  const long long t = ((long long)blockIdx.x * 128 + threadIdx.x) * 2;
+  if (t >= (long long)nimg * HW) return;
+  const int img = (int)(t / HW);
+  const int r = (int)(t - (long long)img * HW);
+  const int y = r / W, x = r - y * W;                     // x even: x + 1 is in the same image row
+  const float* row = in + (((long long)img * (H + 2) + y + 1) * (W + 2) + x + 1) * ps_row_floats(Cin);
+  const int rowF = ps_row_floats(Cin);
+  for (int k0 = 0; k0 < K; k0 += KB) {
+    float acc0[KB], acc1[KB];
+    const int kn = min(KB, K - k0);
+#pragma unroll
+    for (int k = 0; k < KB; ++k) { acc0[k] = 0.f; acc1[k] = 0.f; }
+    for (int ch = 0; ch < (Cin >> 4); ++ch) {
+      float v0[16], v1[16];
+      chunk_load16(row, ch, v0);
+      chunk_load16(row + rowF, ch, v1);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float* wr = s_w + (ch * 16 + i) * K + k0;
+#pragma unroll
+        for (int k = 0; k < KB; ++k)
+          if (KB == 17 || k < kn) { const float wk = wr[k]; acc0[k] = fmaf(v0[i], wk, acc0[k]); acc1[k] = fmaf(v1[i], wk, acc1[k]); }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < KB; ++k)
+      if (KB == 17 || k < kn) {
+        const float b = s_w[Cin * K + k0 + k];
+        *reinterpret_cast<float2*>(out + (((long long)img * K + k0 + k) * H + y) * W + x) = make_float2(acc0[k] + b, acc1[k] + b);
+      }
+  }
+}
+
+// one position per thread: odd widths (not used by the shipped models)
+__global__ void __launch_bounds__(128) head_kernel_1(const float* __restrict__ in, int Cin, int H, int W, int nimg,
+                                                     const float* __restrict__ w, const float* __restrict__ bias, int K, float* __restrict__ out) {
+  extern __shared__ float s_w[];
   for (int i = threadIdx.x; i < Cin * K; i += 128) s_w[i] = w[i];
   for (int i = threadIdx.x; i < K; i += 128) s_w[Cin * K + i] = bias[i];
   __syncthreads();
@@ -482,33 +501,25 @@ __global__ void __launch_bounds__(128) head_kernel(const float* __restrict__ in,
   const int r = (int)(t % (H * W));
   const int y = r / W, x = r % W;
   const float* row = in + (((long long)img * (H + 2) + y + 1) * (W + 2) + x + 1) * ps_row_floats(Cin);
-  for (int k0 = 0; k0 < K; k0 += 32) {
-    float acc[32];
-    const int kn = min(32, K - k0);
-#pragma unroll
-    for (int k = 0; k < 32; ++k) acc[k] = 0.f;
+  for (int k = 0; k < K; ++k) {
+    float acc = 0.f;
     for (int c = 0; c < Cin; c += 4) {
       const float4 v = ps_load4(row, c);
-      const float vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float* wr = s_w + (c + i) * K + k0;
-#pragma unroll
-        for (int k = 0; k < 32; ++k)
-          if (k < kn) acc[k] = fmaf(vv[i], wr[k], acc[k]);
-      }
+      acc = fmaf(v.x, s_w[c * K + k], acc); acc = fmaf(v.y, s_w[(c + 1) * K + k], acc);
+      acc = fmaf(v.z, s_w[(c + 2) * K + k], acc); acc = fmaf(v.w, s_w[(c + 3) * K + k], acc);
     }
-#pragma unroll
-    for (int k = 0; k < 32; ++k)
-      if (k < kn) out[(((long long)img * K + k0 + k) * H + y) * W + x] = acc[k] + s_w[Cin * K + k0 + k];
+    out[(((long long)img * K + k) * H + y) * W + x] = acc + s_w[Cin * K + k];
   }
 }
 
 void launch_head(const float* in, int Cin, int H, int W, int nimg, const float* w, const float* bias, int K, float* out,
                  cudaStream_t st) {
-  long long total = (long long)nimg * H * W;
-  size_t smem = (size_t)(Cin * K + K) * sizeof(float);
-  head_kernel<<<(unsigned)((total + 127) / 128), 128, smem, st>>>(in, Cin, H, W, nimg, w, bias, K, out);
+  const long long total = (long long)nimg * H * W;
+  const size_t smem = (size_t)(Cin * K + K) * sizeof(float);
+  if (W % 2) { head_kernel_1<<<(unsigned)((total + 127) / 128), 128, smem, st>>>(in, Cin, H, W, nimg, w, bias, K, out); return; }
+  const unsigned grid = (unsigned)((total / 2 + 127) / 128);
+  if (K == 17) head_kernel<17><<<grid, 128, smem, st>>>(in, Cin, H, W, nimg, w, bias, K, out);
+  else head_kernel<32><<<grid, 128, smem, st>>>(in, Cin, H, W, nimg, w, bias, K, out);
 }
 
 // debug: PS tensor image -> dense CHW fp32
@@ -557,31 +568,32 @@ void launch_chw_to_ps(const float* in, int C, int H, int W, int nimg, float* out
 // W'[dy][dx][(py,px,c)] = w[2dy+py][2dx+px][c] (zero when the tap index exceeds 2): a 2x2, stride-1, tap-shifted
 // GEMM over 4*C channels that runs on the tensor-core kernel.  Pure data movement: hi/lo pairs are copied.
 // =============================================================================================
+// One CTA per padded output row (img, a'), threads over (b', 16-byte unit of the 4C-channel row): consecutive threads copy
+// consecutive 16-byte units, so a warp writes 512 contiguous bytes and reads runs of C/16 chunks from four source rows.
+// (The first version moved 8 bytes per thread behind three 64-bit divisions: 0.33 ms for a 0.75 GB copy.)
 __global__ void __launch_bounds__(256) s2d_kernel(const float* __restrict__ in, int C, int Hin, int Win, int nimg,
                                                   float* __restrict__ out, int Hout, int Wout) {
-  const int C4 = 4 * C, g4 = C4 >> 2;
+  constexpr int UPC = PS_CHUNK_BYTES / 16;                     // 16-byte units per 16-channel chunk
   const int Hp = Hout + 2, Wp = Wout + 2, HpI = Hin + 2, WpI = Win + 2;
-  const long long total = (long long)nimg * Hp * Wp * g4;
-  const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
-  if (t >= total) return;
-  const int ce = (int)(t % g4) * 4;            // channel of the 4C-channel tensor
-  const long long m = t / g4;
-  const int img = (int)(m / (Hp * Wp));
-  const int r = (int)(m % (Hp * Wp));
-  const int ap = r / Wp, bp = r % Wp;
-  const int par = ce / C, c = ce % C;
-  const int py = par >> 1, px = par & 1;
-  const int sy = 2 * (ap - 1) + py, sx = 2 * (bp - 1) + px;
-  float* drow = out + m * ps_row_floats(C4);
-  if (ap >= 1 && bp >= 1 && sy < HpI && sx < WpI)
-    ps_copy4(drow, ce, in + (((long long)img * HpI + sy) * WpI + sx) * ps_row_floats(C), c);
-  else
-    ps_zero4(drow, ce);
+  const int upp = (C >> 4) * UPC;                              // units per parity block = units of a source row
+  const int upr = 4 * upp;                                     // units per output row
+  const int img = blockIdx.x / Hp, ap = blockIdx.x - img * Hp;
+  const uint4* __restrict__ src = reinterpret_cast<const uint4*>(in) + (size_t)img * HpI * WpI * upp;
+  uint4* __restrict__ dst = reinterpret_cast<uint4*>(out) + (size_t)blockIdx.x * Wp * upr;
+  const int n = Wp * upr;
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const int bp = i / upr, u = i - bp * upr;
+    const int par = u / upp, k = u - par * upp;
+    const int sy = 2 * (ap - 1) + (par >> 1), sx = 2 * (bp - 1) + (par & 1);
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (ap >= 1 && bp >= 1 && sy < HpI && sx < WpI) v = __ldg(src + ((size_t)sy * WpI + sx) * upp + k);
+    dst[i] = v;
+  }
+  (void)nimg;
 }
 
 void launch_s2d(const float* in, int C, int Hin, int Win, int nimg, float* out, int Hout, int Wout, cudaStream_t st) {
-  long long total = (long long)nimg * (Hout + 2) * (Wout + 2) * C;
-  s2d_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, C, Hin, Win, nimg, out, Hout, Wout);
+  s2d_kernel<<<(unsigned)(nimg * (Hout + 2)), 256, 0, st>>>(in, C, Hin, Win, nimg, out, Hout, Wout);
 }
 
 // =============================================================================================

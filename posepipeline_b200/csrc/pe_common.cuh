@@ -134,6 +134,48 @@ __device__ __forceinline__ void ps_zero4(float* row, int c) {
 #endif
 }
 
+// the fp32 values of one whole 16-channel chunk of a row (16-byte loads) / the split store of 16 values into a chunk
+__device__ __forceinline__ void chunk_load16(const float* row, int chunk, float (&v)[16]) {
+  const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(row) + (size_t)chunk * PS_CHUNK_BYTES);
+#if PE_FP16
+  const uint4 h0 = __ldg(p), h1 = __ldg(p + 1), l0 = __ldg(p + 2), l1 = __ldg(p + 3);
+  const uint32_t hw[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+  const uint32_t lw[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[i]));
+    const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[i]));
+    v[2 * i] = fmaf(lf.x, PS_LO_INV, hf.x); v[2 * i + 1] = fmaf(lf.y, PS_LO_INV, hf.y);
+  }
+#else
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint4 h = __ldg(p + i), l = __ldg(p + 4 + i);
+    v[4 * i + 0] = __uint_as_float(h.x) + __uint_as_float(l.x); v[4 * i + 1] = __uint_as_float(h.y) + __uint_as_float(l.y);
+    v[4 * i + 2] = __uint_as_float(h.z) + __uint_as_float(l.z); v[4 * i + 3] = __uint_as_float(h.w) + __uint_as_float(l.w);
+  }
+#endif
+}
+
+__device__ __forceinline__ void chunk_store16(float* row, int chunk, const float (&v)[16]) {
+  uint4* p = reinterpret_cast<uint4*>(reinterpret_cast<char*>(row) + (size_t)chunk * PS_CHUNK_BYTES);
+#if PE_FP16
+  uint2 h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) split4_h(make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]), h[i], l[i]);
+  p[0] = make_uint4(h[0].x, h[0].y, h[1].x, h[1].y); p[1] = make_uint4(h[2].x, h[2].y, h[3].x, h[3].y);
+  p[2] = make_uint4(l[0].x, l[0].y, l[1].x, l[1].y); p[3] = make_uint4(l[2].x, l[2].y, l[3].x, l[3].y);
+#else
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float4 hi, lo;
+    split4(make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]), hi, lo);
+    p[i] = make_uint4(__float_as_uint(hi.x), __float_as_uint(hi.y), __float_as_uint(hi.z), __float_as_uint(hi.w));
+    p[4 + i] = make_uint4(__float_as_uint(lo.x), __float_as_uint(lo.y), __float_as_uint(lo.z), __float_as_uint(lo.w));
+  }
+#endif
+}
+
 // raw copy of 4 channels (both halves) between rows: no arithmetic, used by the space-to-depth repack
 __device__ __forceinline__ void ps_copy4(float* drow, int cd, const float* srow, int cs) {
   char* d = reinterpret_cast<char*>(drow) + ps_chan_byte(cd);

@@ -202,7 +202,147 @@ __global__ void __launch_bounds__(256) attention_kernel(const float* __restrict_
   }
 }
 
+// Register-tiled form (T = 64 * NI tokens, NI <= 3; head dim 64): one CTA per (image, head), 256 threads.  K (transposed),
+// V and a 64-row query block live in shared memory; per query block
+//   A. S = (q * scale) k^T : each thread a 4-row x (4 * NI)-column tile, per head dimension one float4 of q (broadcast) and NI
+//      float4 of k feed 16 * NI FMAs (the row-wise kernel above issued two LDS per FMA: 83 ms of the 160 ms ViTPose-B step),
+//   B. row softmax numerators exp(s - max) in place (one warp per row, shuffle max / sum), 1 / sum kept per row,
+//   C. O = P v : each thread 4 rows x 4 dims, four keys per step (float4 of p per row, float4 of v per key), scaled by 1 / sum.
+// fp32 throughout; only the summation order differs from the row-wise kernel.
+template <int NI, int QB>
+__global__ void __launch_bounds__(4 * QB, 1) attention_tiled_kernel(const float* __restrict__ qkv, int heads, float scale, float* __restrict__ out) {
+  constexpr int T = 64 * NI, TS = T + 4, NT = 4 * QB;         // NT threads = QB / 4 row groups x 16 column groups
+  extern __shared__ __align__(16) float sm[];
+  float* sKt = sm;                         // [64][T]   k transposed: [d][token]
+  float* sV = sKt + 64 * T;                // [T][64]
+  float* sQt = sV + T * 64;                // [64][QB]  q * scale transposed: [d][row]
+  float* sS = sQt + 64 * QB;               // [QB][TS]  scores, then softmax numerators
+  float* sInv = sS + QB * TS;              // [QB]
+  const int C = heads * ATT_D;
+  const int img = blockIdx.x / heads, head = blockIdx.x - img * heads;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long row0 = (long long)img * T;
+  const int rowF = ps_row_floats(3 * C);
+  const int kch = (C + head * ATT_D) >> 4, vch = (2 * C + head * ATT_D) >> 4, qch = (head * ATT_D) >> 4;
+  for (int i = tid; i < 4 * T; i += NT) {                      // K: consecutive lanes = consecutive tokens (conflict-free transposed stores)
+    const int c = i / T, t = i - c * T;
+    float v[16];
+    chunk_load16(qkv + (row0 + t) * rowF, kch + c, v);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) sKt[(c * 16 + k) * T + t] = v[k];
+  }
+  for (int i = tid; i < 4 * T; i += NT) {                      // V: row-major
+    const int t = i >> 2, c = i & 3;
+    float v[16];
+    chunk_load16(qkv + (row0 + t) * rowF, vch + c, v);
+    float4* d = reinterpret_cast<float4*>(sV + t * 64 + c * 16);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const int kk = (k + lane) & 3; d[kk] = make_float4(v[4 * kk], v[4 * kk + 1], v[4 * kk + 2], v[4 * kk + 3]); }
+  }
+  const int rg = tid >> 4, cg = tid & 15;
+  for (int qb = 0; qb < T / QB; ++qb) {
+    __syncthreads();                                           // K / V visible; previous block's sS / sQt no longer read
+    {
+      const int i = tid, c = i / QB, r = i - c * QB;           // 4 * QB chunks = one per thread
+      float v[16];
+      chunk_load16(qkv + (row0 + qb * QB + r) * rowF, qch + c, v);
+#pragma unroll
+      for (int k = 0; k < 16; ++k) sQt[(c * 16 + k) * QB + r] = v[k] * scale;
+    }
+    __syncthreads();
+    {                                                          // A: scores
+      float acc[4][4 * NI];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4 * NI; ++c) acc[r][c] = 0.f;
+#pragma unroll 4
+      for (int d = 0; d < 64; ++d) {
+        const float4 q4 = *reinterpret_cast<const float4*>(sQt + d * QB + 4 * rg);
+        const float q[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+          const float4 k4 = *reinterpret_cast<const float4*>(sKt + d * T + 64 * i + 4 * cg);
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            acc[r][4 * i + 0] = fmaf(q[r], k4.x, acc[r][4 * i + 0]); acc[r][4 * i + 1] = fmaf(q[r], k4.y, acc[r][4 * i + 1]);
+            acc[r][4 * i + 2] = fmaf(q[r], k4.z, acc[r][4 * i + 2]); acc[r][4 * i + 3] = fmaf(q[r], k4.w, acc[r][4 * i + 3]);
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int i = 0; i < NI; ++i)
+          *reinterpret_cast<float4*>(sS + (4 * rg + r) * TS + 64 * i + 4 * cg) = make_float4(acc[r][4 * i], acc[r][4 * i + 1], acc[r][4 * i + 2], acc[r][4 * i + 3]);
+    }
+    __syncthreads();
+    for (int r = warp * 8; r < warp * 8 + 8; ++r) {            // B: softmax numerators
+      float* srow = sS + r * TS;
+      float v[2 * NI];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 2 * NI; ++i) { v[i] = srow[lane + 32 * i]; mx = fmaxf(mx, v[i]); }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < 2 * NI; ++i) { const float e = expf(v[i] - mx); srow[lane + 32 * i] = e; sum += e; }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      if (lane == 0) sInv[r] = 1.0f / sum;
+    }
+    __syncthreads();
+    {                                                          // C: O = P v
+      float acc[4][4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) { acc[r][0] = 0.f; acc[r][1] = 0.f; acc[r][2] = 0.f; acc[r][3] = 0.f; }
+#pragma unroll 2
+      for (int j = 0; j < T; j += 4) {
+        float4 p4[4], v4[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) p4[r] = *reinterpret_cast<const float4*>(sS + (4 * rg + r) * TS + j);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v4[k] = *reinterpret_cast<const float4*>(sV + (j + k) * 64 + 4 * cg);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const float p[4] = {p4[r].x, p4[r].y, p4[r].z, p4[r].w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            acc[r][0] = fmaf(p[k], v4[k].x, acc[r][0]); acc[r][1] = fmaf(p[k], v4[k].y, acc[r][1]);
+            acc[r][2] = fmaf(p[k], v4[k].z, acc[r][2]); acc[r][3] = fmaf(p[k], v4[k].w, acc[r][3]);
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float inv = sInv[4 * rg + r];
+        ps_store4(out + (row0 + qb * QB + 4 * rg + r) * ps_row_floats(C), head * ATT_D + 4 * cg,
+                  make_float4(acc[r][0] * inv, acc[r][1] * inv, acc[r][2] * inv, acc[r][3] * inv));
+      }
+    }
+  }
+}
+
+template <int NI, int QB>
+static cudaError_t launch_attention_tiled(const float* qkv, int nimg, int heads, float scale, float* out, cudaStream_t st) {
+  constexpr int T = 64 * NI;
+  static_assert(T % QB == 0 && QB % 32 == 0, "query blocks tile the tokens; one warp per 8 rows");
+  const size_t smem = sizeof(float) * (64 * T + T * 64 + 64 * QB + QB * (T + 4) + QB);
+  cudaError_t e = pe_smem_optin((const void*)attention_tiled_kernel<NI, QB>, (int)smem);
+  if (e != cudaSuccess) return e;
+  attention_tiled_kernel<NI, QB><<<(unsigned)(nimg * heads), 4 * QB, smem, st>>>(qkv, heads, scale, out);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_attention(const float* qkv, int nimg, int T, int heads, float scale, float* out, cudaStream_t st) {
+  static const bool rowwise = getenv("PE_ATT_ROWWISE") && atoi(getenv("PE_ATT_ROWWISE"));      // A/B knob: the round-2 first version
+  if (!rowwise) {
+    static const int qb = getenv("PE_ATT_QB") ? atoi(getenv("PE_ATT_QB")) : 96;                // 96: 12 warps per SM; 64: the first tiled form (8 warps)
+    if (T == 192) return qb == 64 ? launch_attention_tiled<3, 64>(qkv, nimg, heads, scale, out, st) : launch_attention_tiled<3, 96>(qkv, nimg, heads, scale, out, st);
+    if (T == 128) return launch_attention_tiled<2, 64>(qkv, nimg, heads, scale, out, st);
+    if (T == 64) return launch_attention_tiled<1, 64>(qkv, nimg, heads, scale, out, st);
+  }
   const size_t smem = sizeof(float) * ((size_t)T * 65 + (size_t)T * 64 + 8 * (size_t)T + 8 * ATT_D);
   cudaError_t e = pe_smem_optin((const void*)attention_kernel, (int)smem);
   if (e != cudaSuccess) return e;

@@ -422,14 +422,17 @@ def test_conv_tilings_are_bit_identical(eng):
     for env in ({"PE_TC_MT": 1}, {"PE_TC_MT": 2}, {"PE_TC_NS": 2}, {"PE_TC_AUTOTUNE": 1}, {"PE_TC_CG": 1}, {"PE_TC_CG": 2},
                 {"PE_TC_CG": 2, "PE_TC_NS": 1}, {"PE_TC_CG": 2, "PE_TC_MT": 2},        # CG = 2: CTA-pair form (M = 256 MMAs)
                 {"PE_TC_SETS": 2}, {"PE_TC_SETS": 3}, {"PE_TC_SETS": 4}, {"PE_TC_CG": 2, "PE_TC_SETS": 2},     # epilogue organisations
-                {"PE_TC_CG": 2, "PE_TC_SETS": 3}, {"PE_TC_CG": 2, "PE_TC_SETS": 4, "PE_TC_MT": 2}, {"PE_TC_SETS": 1, "PE_TC_DSTORE": 1}):
+                {"PE_TC_CG": 2, "PE_TC_SETS": 3}, {"PE_TC_CG": 2, "PE_TC_SETS": 4, "PE_TC_MT": 2}, {"PE_TC_SETS": 1, "PE_TC_DSTORE": 1},
+                # work-item order: n-major, and groups of M tiles small enough that the last group is partial
+                {"PE_TC_NS": 2, "PE_TC_GROUP": 0}, {"PE_TC_NS": 2, "PE_TC_GROUP_KB": 700}, {"PE_TC_NS": 2, "PE_TC_CG": 2, "PE_TC_SETS": 3, "PE_TC_GROUP_KB": 300}):
         got = forced(run, env)
         if got is not None:
             checked += 1
             assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), env
     run1 = _conv_case(eng, 64, 256, 1, 96, 72, 2, True, 1, 12)
     ref1 = _with_env(run1, PE_TC_AUTOTUNE=0)
-    for env in ({"PE_TC_KC": 1}, {"PE_TC_KC": 4}, {"PE_TC_NS": 4}, {"PE_TC_CG": 2}, {"PE_TC_CG": 2, "PE_TC_KC": 1}):
+    for env in ({"PE_TC_KC": 1}, {"PE_TC_KC": 4}, {"PE_TC_NS": 4}, {"PE_TC_CG": 2}, {"PE_TC_CG": 2, "PE_TC_KC": 1},
+                {"PE_TC_NS": 4, "PE_TC_GROUP": 0}, {"PE_TC_NS": 4, "PE_TC_GROUP": 2, "PE_TC_GROUP_KB": 500}, {"PE_TC_NS": 2, "PE_TC_CG": 2, "PE_TC_GROUP": 2, "PE_TC_GROUP_KB": 200}):
         got = forced(run1, env)
         if got is not None:
             checked += 1
