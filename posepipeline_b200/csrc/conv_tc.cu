@@ -521,6 +521,8 @@ cudaError_t tc_conv_launch_rows(TcConvPlan* pl, long long rows, cudaStream_t st)
   // schedule (tc_work_item): with several N slices, groups of M tiles whose activation rows (<= 48 MB) stay in L2 while the
   // CTAs walk through the slices; PE_TC_GROUP=0 keeps the n-major order, PE_TC_GROUP_KB sets the budget (tests).  Gather layers index windows by tile in the MMA warps
   // (n-major arithmetic) and have at most a few slices: unchanged.
+  // gather forms need at most 15 lanes (boxes of two S image rows + the weight box); the others KC * (activation boxes + 1)
+  p.prod_par = env_int("PE_TC_PLANES", 32) > 1 && (p.gather || pl->KC * (p.nseg * p.nb_seg + 1) <= 32) ? 1 : 0;
   p.nsplit = pl->ns; p.grp = 0;
   // Only where the repeated activation reads weigh at least as much as the output itself, Cin * (ns - 1) >= Cout: the wide 1x1
   // layers of HRNet's layer1 (64 -> 256, HBM-bound on the output and the residual) measured 8 % slower grouped.

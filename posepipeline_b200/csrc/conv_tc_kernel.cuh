@@ -101,6 +101,7 @@ struct TcParams {
   int mma_wait_ns;           // MMA warps: 0 = spin on test_wait (default), > 0 = suspended try_wait with this time hint
   int poll_ns;               // producer / epilogue waits: > 0 nanosleep back-off between polls, < 0 suspended try_wait with that time hint, 0 spin
   int tiles_m, total_work;   // persistent schedule: work item w -> (tile = w % tiles_m, n-slice = w / tiles_m) when grp == 0
+  int prod_par;              // 1 = the producer warp issues the TMA operations of a stage from one lane each (else lane 0 issues all)
   int grp, nsplit;           // grp > 0: groups of grp M tiles, all nsplit N slices of a group before the next group (tc_work_item)
   uint32_t a_bytes, stage_bytes;
   unsigned int* flag;        // range flag of the forward (kernels.h pe_range_flag), or nullptr
@@ -481,8 +482,81 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp == 0) {
-    // ===================== TMA producer (one lane) =====================
-    if (lane == 0) {
+    // ===================== TMA producer =====================
+    if (p.prod_par) {
+      // Lane-parallel issue.  Measured (profiles/r02_producer_notes.md): the single-lane loop below spends ~100 clocks of dependent
+      // address arithmetic + issue per TMA operation; layers with many small operations per stage and little MMA work per stage
+      // (the stride-2 gather: 5-14 boxes + weights per ~400-800 clocks of MMAs) were paced by the producer THREAD, not by bytes.
+      // Here lane 0 waits for the free stage and posts the byte count, then every operation of the stage is issued by its own
+      // lane in one pass (per-lane box coordinates are fixed per tile, or for the whole kernel in the non-gather forms).
+      if (lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmW) : "memory");
+      }
+      Ring r;
+      int tile = 0, nsl = 0;
+      if (wfirst < p.total_work) tc_work_item(p, wfirst, tile, nsl);
+      const bool gather = TAPS == 4 && p.gather;
+      const uint32_t full0 = (CG == 2) ? mapa_rank(bar_full, 0u) : bar_full;
+      // non-gather forms: lane -> (chunk of the stage, operation of the chunk); the last operation of a chunk is its weight box
+      const int opk = p.nseg * p.nb_seg + 1;
+      const int my_kc = lane / opk, my_o = lane - my_kc * opk;
+      const bool my_on = my_kc < KC, my_w = my_o == opk - 1;
+      const int my_sg = my_w ? 0 : my_o / p.nb_seg, my_b = my_w ? 0 : my_o - my_sg * p.nb_seg;
+      const uint32_t my_off = my_w ? (uint32_t)KC * a_bytes + (uint32_t)my_kc * b_chunk_bytes
+                                   : (uint32_t)my_kc * a_bytes + (uint32_t)(my_sg * p.Rseg + my_b * p.RB) * CHB;
+      const int my_row = my_sg * p.seg_step + my_b * p.RB - p.halo;
+      for (int w = wfirst; w < p.total_work; w += wstep) {
+        const int m0 = (tile * CG + (int)rank) * 128 * MT;
+        const int n0 = nsl * NC + (int)rank * NCB;
+        uint32_t tx = (uint32_t)KC * (a_bytes + b_chunk_bytes);
+        int g_nbox = 0, my_q = 0, my_n = 0;
+        if (gather) {                                                   // see the single-lane form below for the geometry
+          const int g0 = m0 / p.Wp, g_n = g0 / p.Hp, g_q = (g0 - g_n * p.Hp) >> 1, hq = p.Hp >> 1;
+          const int off = m0 - (g_n * p.Hp + 2 * g_q) * p.Wp;
+          g_nbox = (off + 128 * MT + p.Wp + 1 + 2 * p.Wp - 1) / (2 * p.Wp);
+          tx = (uint32_t)g_nbox * 2u * (uint32_t)p.Wp * CHB + b_chunk_bytes;
+          my_q = g_q + lane; my_n = g_n;                                // box `lane`: S image-row pair my_q of image my_n
+          while (my_q >= hq) { my_q -= hq; ++my_n; }
+        }
+        int j = 0, gpar = 0, gjj = 0;
+        for (int st = 0; st < p.nstage; ++st) {
+          const uint32_t full = full0 + 8 * r.idx, dst = sRing + r.idx * stage_bytes;
+          if (lane == 0) {
+            mbar_wait_relaxed(bar_empty + 8 * r.idx, r.phase ^ 1u, p.poll_ns);
+            if (CG == 2) mbar_expect_tx_cluster(full, tx); else mbar_expect_tx(full, tx);
+          }
+          __syncwarp();
+          if (gather) {                                                 // one chunk per stage (KC = 1)
+            if (lane < g_nbox) {
+              const uint32_t da = dst + (uint32_t)lane * 2u * (uint32_t)p.Wp * CHB;
+              if (CG == 2) tma2_load_4d(da, &tmA, (p.in_coff + gjj) * (CHB / 4), (gpar & 1) - 2, 4 * my_q - 2 + (gpar >> 1), my_n, full);
+              else tma_load_4d(da, &tmA, (p.in_coff + gjj) * (CHB / 4), (gpar & 1) - 2, 4 * my_q - 2 + (gpar >> 1), my_n, full);
+            } else if (lane == g_nbox) {
+              if (CG == 2) tma2_load_3d(dst + (uint32_t)KC * a_bytes, &tmW, 0, j * p.Cout + n0, 0, full);
+              else tma_load_3d(dst + (uint32_t)KC * a_bytes, &tmW, 0, j * p.Cout + n0, 0, full);
+            }
+            ++j;
+            if (++gjj == p.cpp) { gjj = 0; ++gpar; }
+          } else {
+            if (my_on) {
+              const int jc = j + my_kc;
+              if (my_w) {
+                if (CG == 2) tma2_load_3d(dst + my_off, &tmW, 0, jc * p.Cout + n0, 0, full);
+                else tma_load_3d(dst + my_off, &tmW, 0, jc * p.Cout + n0, 0, full);
+              } else {
+                if (CG == 2) tma2_load_2d(dst + my_off, &tmA, (p.in_coff + jc) * (CHB / 4), m0 + my_row, full);
+                else tma_load_2d(dst + my_off, &tmA, (p.in_coff + jc) * (CHB / 4), m0 + my_row, full);
+              }
+            }
+            j += KC;
+          }
+          r.advance(p.S);
+        }
+        if (p.grp > 0) { if (w + wstep < p.total_work) tc_work_item(p, w + wstep, tile, nsl); }
+        else { tile += wstep; while (tile >= p.tiles_m) { tile -= p.tiles_m; ++nsl; } }
+      }
+    } else if (lane == 0) {                 // single-lane form (PE_TC_PLANES=1, or more than 32 operations per stage)
       asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmW) : "memory");
       Ring r;
