@@ -57,17 +57,23 @@ void launch_warp_crop(const uint8_t* frames, int fh, int fw, const int32_t* fram
 // LUT (ToTensor + NormalizeTensor, cfg :132-136, fused).  Images [ncrop, 2*ncrop) are the flip-test
 // pass: they read the crop mirrored in x (== img.flip(3)).
 // =============================================================================================
-// One CTA = a 16x16 tile of the PADDED output grid of one image, one thread per position, all 64 output channels.
-//   1. the 33x33x3 input patch goes through the normalisation LUT into shared memory once (13 byte loads per thread;
-//      the first version re-read 81 bytes per thread and was load/store-unit bound at 6 TFLOP/s),
-//   2. 27 x 64 FMAs per thread, weights broadcast from shared memory as float4 (same order ky,kx,c as the oracle's
-//      accumulation; out-of-image taps contribute fmaf(0, w, acc) = acc, so padding is exact),
-//   3. the 256-byte PS rows are staged in shared memory (XOR-swizzled 16-byte units) and leave as 4 KB contiguous runs.
-constexpr int STEM_T = 16;                                   // tile edge
-constexpr int STEM_P = 2 * STEM_T + 1;                       // input patch edge
-constexpr int STEM_ROWB = 4 * PS_CHUNK_BYTES;                // bytes of a 64-channel PS row
-constexpr int STEM_IN_FLOATS = (3 * STEM_P * (STEM_P + 1) + 3) & ~3;   // padded so the staged rows behind it stay 16-byte aligned
-constexpr size_t STEM_SMEM = sizeof(float) * (27 * 64 + 768 + 64 + STEM_IN_FLOATS) + (size_t)STEM_T * STEM_T * STEM_ROWB;
+// One CTA = a 16-row x 32-column tile of the PADDED output grid of one image; 256 threads, TWO positions per thread (columns
+// lx and lx + 16 of one tile row), all 64 output channels in four passes of 16.
+//   1. every global load of the CTA (weights, LUT, bias, the thread's <= 9 patch pixels) is issued before the first use; the
+//      33 x 65 x 3 input patch goes through the normalisation LUT into shared memory once,
+//   2. 27 x 64 FMAs per position, weights read from shared memory as float4 (same order ky,kx,c as the oracle's accumulation;
+//      out-of-image taps contribute fmaf(0, w, acc) = acc, so padding is exact); every weight load feeds both positions.
+//      Measured (profiles/r02_ncu_full_simt.md): the one-position form ran 618 M shared-memory wavefronts per launch (82 % of
+//      the LSU cycles) in 2.62 ms; halving the weight loads this way did NOT shorten it (2.72 -> 2.78 ms per 512 images, 128
+//      registers with 44 bytes of spills, still two CTAs per SM) -- the kernel stays at ~18 TFLOP/s fp32, 2 % of a forward,
+//   3. each pass's 16-channel chunks are staged in shared memory (XOR-swizzled 16-byte units) and leave as whole chunks
+//      (two positions = 128 contiguous staged bytes per quarter warp; 32 KB of staging instead of 64 KB: three CTAs per SM).
+constexpr int STEM_TH = 16, STEM_TW = 32;                    // tile height / width (positions)
+constexpr int STEM_PH = 2 * STEM_TH + 1, STEM_PW = 2 * STEM_TW + 1;   // input patch
+constexpr int STEM_PWP = STEM_PW + 1;                        // padded patch row
+constexpr int STEM_NPOS = STEM_TH * STEM_TW;
+constexpr int STEM_IN_FLOATS = (3 * STEM_PH * STEM_PWP + 3) & ~3;      // padded so the staging area behind it stays 16-byte aligned
+constexpr size_t STEM_SMEM = sizeof(float) * (27 * 64 + 768 + 64 + STEM_IN_FLOATS) + (size_t)STEM_NPOS * PS_CHUNK_BYTES;
 
 __global__ void __launch_bounds__(256, 2) stem_kernel(const uint8_t* __restrict__ crops, int ncrop, int nimg, int ih, int iw,
                                                       const float* __restrict__ lut,   // [3][256]
@@ -79,20 +85,18 @@ __global__ void __launch_bounds__(256, 2) stem_kernel(const uint8_t* __restrict_
   float* s_w = reinterpret_cast<float*>(stem_smem);           // [27][64]
   float* s_lut = s_w + 27 * 64;                               // [768]
   float* s_b = s_lut + 768;                                   // [64]
-  float* s_in = s_b + 64;                                     // [3][STEM_P][STEM_P + 1]
-  uint8_t* s_out = reinterpret_cast<uint8_t*>(s_in + STEM_IN_FLOATS);          // [256 positions][STEM_ROWB], swizzled
+  float* s_in = s_b + 64;                                     // [3][STEM_PH][STEM_PWP]
+  uint4* s_st = reinterpret_cast<uint4*>(s_in + STEM_IN_FLOATS);               // [STEM_NPOS positions][UPC units], swizzled
+  constexpr int UPC = PS_CHUNK_BYTES / 16;                     // 16-byte units per 16-channel chunk
   const int tid = threadIdx.x;
   const int Hp = oh + 2, Wp = ow + 2;
   const int img = blockIdx.z;
-  const int ty0 = blockIdx.y * STEM_T, tx0 = blockIdx.x * STEM_T;      // tile origin on the padded grid
+  const int ty0 = blockIdx.y * STEM_TH, tx0 = blockIdx.x * STEM_TW;    // tile origin on the padded grid
   const bool flip = img >= ncrop;
   const uint8_t* c0 = crops + (size_t)(flip ? img - ncrop : img) * ih * iw * 3;
-  // input patch: rows iy0 .. iy0 + 32, cols ix0 .. ix0 + 32, where output (py, px) reads input (2(py-1)-1+ky, 2(px-1)-1+kx)
+  // input patch: rows iy0 .. iy0 + 32, cols ix0 .. ix0 + 64, where output (py, px) reads input (2(py-1)-1+ky, 2(px-1)-1+kx)
   const int iy0 = 2 * (ty0 - 1) - 1, ix0 = 2 * (tx0 - 1) - 1;
-  // Every global load of the CTA is issued before the first use (fixed trip counts, fully unrolled): weights, LUT, bias and the
-  // thread's <= 5 patch pixels are in flight together.  The round-1 loops had run-time trip counts, so their ~15 dependent
-  // load -> store round trips ran one after the other: ~10 000 clocks per CTA next to ~3 500 clocks of FMAs (3.1 ms per forward).
-  constexpr int NW = (27 * 64 + 255) / 256, NP = (STEM_P * STEM_P + 255) / 256;
+  constexpr int NW = (27 * 64 + 255) / 256, NP = (STEM_PH * STEM_PW + 255) / 256;
   float wv[NW], lv[3], bv = 0.f;
   uint8_t pv[NP][3];
   bool pin[NP];
@@ -104,9 +108,9 @@ __global__ void __launch_bounds__(256, 2) stem_kernel(const uint8_t* __restrict_
 #pragma unroll
   for (int k = 0; k < NP; ++k) {
     const int i = tid + 256 * k;
-    const int ry = i / STEM_P, rx = i - ry * STEM_P;
+    const int ry = i / STEM_PW, rx = i - ry * STEM_PW;
     const int iy = iy0 + ry, ix = ix0 + rx;
-    pin[k] = i < STEM_P * STEM_P && iy >= 0 && iy < ih && ix >= 0 && ix < iw;
+    pin[k] = i < STEM_PH * STEM_PW && iy >= 0 && iy < ih && ix >= 0 && ix < iw;
     pv[k][0] = pv[k][1] = pv[k][2] = 0;
     if (pin[k]) {
       const uint8_t* pix = c0 + ((size_t)iy * iw + (flip ? iw - 1 - ix : ix)) * 3;
@@ -122,93 +126,105 @@ __global__ void __launch_bounds__(256, 2) stem_kernel(const uint8_t* __restrict_
 #pragma unroll
   for (int k = 0; k < NP; ++k) {
     const int i = tid + 256 * k;
-    if (i >= STEM_P * STEM_P) continue;
-    const int ry = i / STEM_P, rx = i - ry * STEM_P;
+    if (i >= STEM_PH * STEM_PW) continue;
+    const int ry = i / STEM_PW, rx = i - ry * STEM_PW;
     float v0 = 0.f, v1 = 0.f, v2 = 0.f;
     if (pin[k]) { v0 = s_lut[pv[k][0]]; v1 = s_lut[256 + pv[k][1]]; v2 = s_lut[512 + pv[k][2]]; }
-    s_in[(0 * STEM_P + ry) * (STEM_P + 1) + rx] = v0;
-    s_in[(1 * STEM_P + ry) * (STEM_P + 1) + rx] = v1;
-    s_in[(2 * STEM_P + ry) * (STEM_P + 1) + rx] = v2;
+    s_in[(0 * STEM_PH + ry) * STEM_PWP + rx] = v0;
+    s_in[(1 * STEM_PH + ry) * STEM_PWP + rx] = v1;
+    s_in[(2 * STEM_PH + ry) * STEM_PWP + rx] = v2;
   }
   __syncthreads();
-  const int ly = tid >> 4, lx = tid & 15;
-  const int py = ty0 + ly, px = tx0 + lx;
-  const bool inside = py < Hp && px < Wp;
-  const bool interior = py >= 1 && py <= oh && px >= 1 && px <= ow;
-  uint4* srow = reinterpret_cast<uint4*>(s_out + (size_t)tid * STEM_ROWB);
-  constexpr int UNITS = STEM_ROWB / 16;                                 // 16-byte units per row
-  if (!interior) {
+  const int ly = tid >> 4, lx = tid & 15;                               // positions (ly, lx) and (ly, lx + 16) of the tile
+  const int py = ty0 + ly;
+  bool interior[2];
+  int pidx[2];
+  float vin[2][27];
 #pragma unroll
-    for (int u = 0; u < UNITS; ++u) srow[u] = make_uint4(0u, 0u, 0u, 0u);
-  } else {
-    float vin[27];
+  for (int h = 0; h < 2; ++h) {
+    const int lxx = lx + 16 * h, px = tx0 + lxx;
+    interior[h] = py >= 1 && py <= oh && px >= 1 && px <= ow;
+    pidx[h] = ly * STEM_TW + lxx;
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
-        for (int c = 0; c < 3; ++c) vin[(ky * 3 + kx) * 3 + c] = s_in[(c * STEM_P + 2 * ly + ky) * (STEM_P + 1) + 2 * lx + kx];
+        for (int c = 0; c < 3; ++c) vin[h][(ky * 3 + kx) * 3 + c] = s_in[(c * STEM_PH + 2 * ly + ky) * STEM_PWP + 2 * lxx + kx];
+  }
+  const size_t img_row0 = (size_t)img * Hp * Wp;
+#pragma unroll 1
+  for (int q = 0; q < 4; ++q) {                                         // 16 output channels = one PS chunk per pass
+    float acc[2][16];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {                                       // 16 output channels = one PS chunk per pass
-      float acc[16];
+    for (int i = 0; i < 16; ++i) { acc[0][i] = s_b[q * 16 + i]; acc[1][i] = acc[0][i]; }
 #pragma unroll
-      for (int i = 0; i < 16; ++i) acc[i] = s_b[q * 16 + i];
-#pragma unroll
-      for (int t = 0; t < 27; ++t) {
-        const float4* wr = reinterpret_cast<const float4*>(s_w + t * 64 + q * 16);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float4 w4 = wr[i];
-          acc[4 * i + 0] = fmaf(vin[t], w4.x, acc[4 * i + 0]); acc[4 * i + 1] = fmaf(vin[t], w4.y, acc[4 * i + 1]);
-          acc[4 * i + 2] = fmaf(vin[t], w4.z, acc[4 * i + 2]); acc[4 * i + 3] = fmaf(vin[t], w4.w, acc[4 * i + 3]);
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < 16; ++i) acc[i] = fmaxf(acc[i], 0.f);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) ps_range_check4(make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]), flag);
-      // chunk q of the row: PS_CHUNK_BYTES / 16 units, stored at unit ^ (tid & 7) inside its group of 8
-      constexpr int UPC = PS_CHUNK_BYTES / 16;
-      uint4 o[UPC];
-#if PE_FP16
-      uint2 h[4], l[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) split4_h(make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]), h[i], l[i]);
-      o[0] = make_uint4(h[0].x, h[0].y, h[1].x, h[1].y); o[1] = make_uint4(h[2].x, h[2].y, h[3].x, h[3].y);
-      o[2] = make_uint4(l[0].x, l[0].y, l[1].x, l[1].y); o[3] = make_uint4(l[2].x, l[2].y, l[3].x, l[3].y);
-#else
+    for (int t = 0; t < 27; ++t) {
+      const float4* wr = reinterpret_cast<const float4*>(s_w + t * 64 + q * 16);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        float4 hi, lo;
-        split4(make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]), hi, lo);
-        o[i] = make_uint4(__float_as_uint(hi.x), __float_as_uint(hi.y), __float_as_uint(hi.z), __float_as_uint(hi.w));
-        o[4 + i] = make_uint4(__float_as_uint(lo.x), __float_as_uint(lo.y), __float_as_uint(lo.z), __float_as_uint(lo.w));
-      }
-#endif
+        const float4 w4 = wr[i];
 #pragma unroll
-      for (int i = 0; i < UPC; ++i) {
-        const int u = q * UPC + i;
-        srow[(u & ~7) | ((u & 7) ^ (tid & 7))] = o[i];
+        for (int h = 0; h < 2; ++h) {
+          acc[h][4 * i + 0] = fmaf(vin[h][t], w4.x, acc[h][4 * i + 0]); acc[h][4 * i + 1] = fmaf(vin[h][t], w4.y, acc[h][4 * i + 1]);
+          acc[h][4 * i + 2] = fmaf(vin[h][t], w4.z, acc[h][4 * i + 2]); acc[h][4 * i + 3] = fmaf(vin[h][t], w4.w, acc[h][4 * i + 3]);
+        }
       }
     }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      uint4 o[UPC];
+      if (!interior[h]) {
+#pragma unroll
+        for (int i = 0; i < UPC; ++i) o[i] = make_uint4(0u, 0u, 0u, 0u);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[h][i] = fmaxf(acc[h][i], 0.f);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ps_range_check4(make_float4(acc[h][4 * i], acc[h][4 * i + 1], acc[h][4 * i + 2], acc[h][4 * i + 3]), flag);
+#if PE_FP16
+        uint2 hh[4], ll[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) split4_h(make_float4(acc[h][4 * i], acc[h][4 * i + 1], acc[h][4 * i + 2], acc[h][4 * i + 3]), hh[i], ll[i]);
+        o[0] = make_uint4(hh[0].x, hh[0].y, hh[1].x, hh[1].y); o[1] = make_uint4(hh[2].x, hh[2].y, hh[3].x, hh[3].y);
+        o[2] = make_uint4(ll[0].x, ll[0].y, ll[1].x, ll[1].y); o[3] = make_uint4(ll[2].x, ll[2].y, ll[3].x, ll[3].y);
+#else
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float4 hi, lo;
+          split4(make_float4(acc[h][4 * i], acc[h][4 * i + 1], acc[h][4 * i + 2], acc[h][4 * i + 3]), hi, lo);
+          o[i] = make_uint4(__float_as_uint(hi.x), __float_as_uint(hi.y), __float_as_uint(hi.z), __float_as_uint(hi.w));
+          o[4 + i] = make_uint4(__float_as_uint(lo.x), __float_as_uint(lo.y), __float_as_uint(lo.z), __float_as_uint(lo.w));
+        }
+#endif
+      }
+      // unit u of position p sits at p * UPC + (u ^ swizzle(p)): conflict-free for the per-position stores here (8 lanes = 8
+      // consecutive positions) and for the unit-major reads of the copy-out below
+      const int sw = (UPC == 4) ? ((pidx[h] >> 1) & 3) : (pidx[h] & 7);
+#pragma unroll
+      for (int i = 0; i < UPC; ++i) s_st[pidx[h] * UPC + (i ^ sw)] = o[i];
+    }
+    __syncthreads();
+    // copy out: chunk q of every position of the tile, 16 bytes per thread and step, consecutive threads = consecutive units
+#pragma unroll
+    for (int k = 0; k < 2 * UPC; ++k) {
+      const int e = tid + 256 * k;
+      const int p_ = e / UPC, u = e - p_ * UPC;
+      const int y = ty0 + p_ / STEM_TW, x = tx0 + (p_ % STEM_TW);
+      if (y >= Hp || x >= Wp) continue;
+      const int sw = (UPC == 4) ? ((p_ >> 1) & 3) : (p_ & 7);
+      const uint4 v = s_st[p_ * UPC + (u ^ sw)];
+      reinterpret_cast<uint4*>(reinterpret_cast<char*>(out) + (img_row0 + (size_t)y * Wp + x) * (4 * PS_CHUNK_BYTES) + (size_t)q * PS_CHUNK_BYTES)[u] = v;
+    }
+    __syncthreads();                                                    // the staging area is free for the next pass
   }
-  __syncthreads();
-  // copy out: tile row ly' = 16 positions x STEM_ROWB contiguous bytes in global memory
-  const size_t img_row0 = (size_t)img * Hp * Wp;
-  for (int i = tid; i < STEM_T * STEM_T * UNITS; i += 256) {
-    const int pos = i / UNITS, u = i - pos * UNITS;
-    const int y = ty0 + (pos >> 4), x = tx0 + (pos & 15);
-    if (y >= Hp || x >= Wp) continue;
-    const uint4 v = reinterpret_cast<const uint4*>(s_out + (size_t)pos * STEM_ROWB)[(u & ~7) | ((u & 7) ^ (pos & 7))];
-    reinterpret_cast<uint4*>(reinterpret_cast<char*>(out) + (img_row0 + (size_t)y * Wp + x) * STEM_ROWB)[u] = v;
-  }
-  (void)inside; (void)nimg;
+  (void)nimg;
 }
 
 void launch_stem(const uint8_t* crops, int ncrop, int nimg, int ih, int iw, const float* lut, const float* w,
                  const float* bias, float* out, int oh, int ow, cudaStream_t st) {
   if (pe_smem_optin((const void*)stem_kernel, (int)STEM_SMEM) != cudaSuccess) return;   // the launch below then fails and is reported
-  dim3 grid((ow + 2 + STEM_T - 1) / STEM_T, (oh + 2 + STEM_T - 1) / STEM_T, nimg);
+  dim3 grid((ow + 2 + STEM_TW - 1) / STEM_TW, (oh + 2 + STEM_TH - 1) / STEM_TH, nimg);
   stem_kernel<<<grid, 256, STEM_SMEM, st>>>(crops, ncrop, nimg, ih, iw, lut, w, bias, pe_range_flag(), out, oh, ow);
 }
 
