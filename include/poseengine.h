@@ -201,6 +201,13 @@ int pe_conv_test(pe_engine* e, const float* in_nchw, int32_t nimg, int32_t Cin, 
 int pe_tc_plan_candidates(int32_t Cin, int32_t Cout, int32_t ks, int32_t has_residual, int32_t H, int32_t W, int32_t max_img,
                           int32_t gather, int32_t* out, int32_t cap);
 
+/* Host-only view of conv_tc's persistent schedule (nothing in the reference): work item w of a layer with n_split N slices and
+ * tiles_m M tiles (tile_rows rows each) -> (*tile, *n_slice).  mode / budget_kb as PE_TC_GROUP / PE_TC_GROUP_KB (1, 49152 are the
+ * defaults).  Returns the group size in M tiles (0 = n-major order: every slice sweeps all tiles) or a negative error.  CPU test:
+ * every (tile, slice) pair is visited exactly once, whatever the group size. */
+int pe_tc_work_item(int32_t Cin, int32_t Cout, int32_t n_split, int32_t tile_rows, int32_t tiles_m, int32_t mode, int32_t budget_kb,
+                    int32_t w, int32_t* tile, int32_t* n_slice);
+
 /* ---- VideoPose3D lifter (wrappers/videopose3d.py:46-85; TemporalModelOptimized1f 243 frames) ---- */
 /* offsets: 10 layers (expand_conv, layers_conv[0..7], shrink) x 3 float offsets into `weights`: SIMT packing
  * [tap][Cin][Cout], folded bias [Cout], tensor-core packing (engine.pack_tc_weights) or -1. */

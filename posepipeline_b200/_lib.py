@@ -109,6 +109,7 @@ def load():
         "pe_model_profile_ops": (C.c_int, [vp, vp, i32]),
         "pe_conv_test": (C.c_int, [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
         "pe_tc_plan_candidates": (C.c_int, [i32, i32, i32, i32, i32, i32, i32, i32, vp, i32]),
+        "pe_tc_work_item": (C.c_int, [i32, i32, i32, i32, i32, i32, i32, i32, vp, vp]),
         "pe_lifter_create": (C.c_int, [vp, vp, i64, vp, i32, i32, P(vp)]),
         "pe_lifter_destroy": (C.c_int, [vp]),
         "pe_lift3d": (C.c_int, [vp, vp, i32, vp]),

@@ -510,6 +510,17 @@ int tc_plan_candidates(int Cin, int Cout, int ks, int has_res, int H, int W, int
 
 void tc_conv_plan_destroy(TcConvPlan* plan, bool cuda_ok) { if (plan && plan->p.prof && cuda_ok) cudaFree(plan->p.prof); delete plan; }
 
+// M tiles per schedule group (0 = n-major order): see tc_conv_launch_rows.  mode 0 never, 1 when the repeated activation reads
+// weigh at least as much as the output (Cin * (ns - 1) >= Cout), 2 whenever there are several N slices.
+int tc_group_size(int Cin, int Cout, int ns, int tile_rows, int tiles_m, int mode, int budget_kb) {
+  if (ns <= 1 || mode <= 0 || tiles_m <= 0) return 0;
+  if (mode == 1 && (long long)Cin * (ns - 1) < Cout) return 0;
+  const double tile_bytes = (double)tile_rows * (Cin / 16) * CHB;
+  const long long g = (long long)(budget_kb * 1024.0 / tile_bytes);
+  return (int)std::max<long long>(1, std::min<long long>(g, tiles_m));
+}
+void tc_work_item_host(int tiles_m, int nsplit, int grp, int w, int* tile, int* nsl) { tc_work_item_map(tiles_m, nsplit, grp, w, *tile, *nsl); }
+
 cudaError_t tc_conv_launch(TcConvPlan* pl, int nimg, cudaStream_t st) { return tc_conv_launch_rows(pl, (long long)nimg * pl->rows_per_img, st); }
 
 cudaError_t tc_conv_launch_rows(TcConvPlan* pl, long long rows, cudaStream_t st) {
@@ -518,20 +529,18 @@ cudaError_t tc_conv_launch_rows(TcConvPlan* pl, long long rows, cudaStream_t st)
   p.M = rows;
   p.tiles_m = (int)((p.M + 128LL * pl->MT * pl->CG - 1) / (128LL * pl->MT * pl->CG));
   p.total_work = p.tiles_m * pl->ns;
-  // schedule (tc_work_item): with several N slices, groups of M tiles whose activation rows (<= 48 MB) stay in L2 while the
-  // CTAs walk through the slices; PE_TC_GROUP=0 keeps the n-major order, PE_TC_GROUP_KB sets the budget (tests).  Gather layers index windows by tile in the MMA warps
-  // (n-major arithmetic) and have at most a few slices: unchanged.
-  // gather forms need at most 15 lanes (boxes of two S image rows + the weight box); the others KC * (activation boxes + 1)
+  // lane-parallel producer: gather forms need at most 15 lanes (boxes of two S image rows + the weight box), the others
+  // KC * (activation boxes + 1); PE_TC_PLANES=1 selects the single-lane producer
   p.prod_par = env_int("PE_TC_PLANES", 32) > 1 && (p.gather || pl->KC * (p.nseg * p.nb_seg + 1) <= 32) ? 1 : 0;
-  p.nsplit = pl->ns; p.grp = 0;
-  // Only where the repeated activation reads weigh at least as much as the output itself, Cin * (ns - 1) >= Cout: the wide 1x1
-  // layers of HRNet's layer1 (64 -> 256, HBM-bound on the output and the residual) measured 8 % slower grouped.
-  const int group_mode = env_int("PE_TC_GROUP", 1);            // 0 never, 1 by the rule, 2 whenever there are several slices
-  if (pl->ns > 1 && !p.gather && group_mode && (group_mode > 1 || (long long)p.nchunk * 16 * (pl->ns - 1) >= p.Cout)) {
-    const double tile_bytes = 128.0 * pl->MT * pl->CG * p.nchunk * CHB;
-    const long long g = (long long)(env_int("PE_TC_GROUP_KB", 48 * 1024) * 1024.0 / tile_bytes);
-    p.grp = (int)std::max<long long>(1, std::min<long long>(g, p.tiles_m));
-  }
+  // schedule (tc_work_item): with several N slices, groups of M tiles whose activation rows (<= 48 MB) stay in L2 while the
+  // CTAs walk through the slices -- only where the repeated activation reads weigh at least as much as the output itself,
+  // Cin * (ns - 1) >= Cout: the wide 1x1 layers of HRNet's layer1 (64 -> 256, HBM-bound on the output and the residual)
+  // measured 8 % slower grouped.  PE_TC_GROUP = 0 never / 1 by that rule / 2 whenever there are several slices; PE_TC_GROUP_KB
+  // sets the budget (tests).  Gather layers index windows by tile in the MMA warps (n-major arithmetic) and have at most a
+  // few slices: unchanged.
+  p.nsplit = pl->ns;
+  p.grp = p.gather ? 0 : tc_group_size(p.nchunk * 16, p.Cout, pl->ns, 128 * pl->MT * pl->CG, p.tiles_m, env_int("PE_TC_GROUP", 1),
+                                       env_int("PE_TC_GROUP_KB", 48 * 1024));
   unsigned grid;
   if (pl->CG == 2) {
     grid = (unsigned)(2 * std::min(p.total_work, pl->max_ctas / 2));

@@ -404,12 +404,15 @@ __device__ __forceinline__ uint64_t desc64(uint32_t hi, uint32_t lo) {
 // the bound of the ViT / lifter / detector GEMMs (fc1: 24 slices x 302 MB = 7.2 GB per launch, 213 TFLOP/s).  Grouped
 // (grp > 0): groups of grp M tiles whose activation rows fit in L2, every N slice of a group before the next group; the
 // weight matrix (a few MB) stays resident.  The per-tile arithmetic does not depend on the order: bit-identical results.
-__device__ __forceinline__ void tc_work_item(const TcParams& p, int w, int& tile, int& nsl) {
-  if (p.grp <= 0) { tile = w % p.tiles_m; nsl = w / p.tiles_m; return; }
-  const int span = p.grp * p.nsplit, g = w / span, base = g * p.grp;
-  const int gc = min(p.grp, p.tiles_m - base), r = w - g * span;
+__host__ __device__ __forceinline__ void tc_work_item_map(int tiles_m, int nsplit, int grp, int w, int& tile, int& nsl) {
+  if (grp <= 0) { tile = w % tiles_m; nsl = w / tiles_m; return; }
+  const int span = grp * nsplit, g = w / span, base = g * grp;
+  const int left = tiles_m - base, gc = grp < left ? grp : left, r = w - g * span;      // the last group may be partial
   nsl = r / gc;
   tile = base + r - nsl * gc;
+}
+__device__ __forceinline__ void tc_work_item(const TcParams& p, int w, int& tile, int& nsl) {
+  tc_work_item_map(p.tiles_m, p.nsplit, p.grp, w, tile, nsl);
 }
 
 template <int NG, int MT, int TAPS, int KC, int CG, int SETS>

@@ -1145,6 +1145,18 @@ done:
   return rc;
 }
 
+extern "C" int pe_tc_work_item(int32_t Cin, int32_t Cout, int32_t n_split, int32_t tile_rows, int32_t tiles_m, int32_t mode, int32_t budget_kb,
+                               int32_t w, int32_t* tile, int32_t* n_slice) {
+  if (Cin <= 0 || Cin % 16 || Cout <= 0 || n_split <= 0 || tile_rows <= 0 || tiles_m <= 0 || budget_kb <= 0 || !tile || !n_slice)
+    return fail(PE_ERR_INVALID, "pe_tc_work_item: bad arguments");
+  if (w < 0 || (long long)w >= (long long)tiles_m * n_split) return fail(PE_ERR_INVALID, "pe_tc_work_item: work item out of range");
+  const int grp = tc_group_size(Cin, Cout, n_split, tile_rows, tiles_m, mode, budget_kb);
+  int t = 0, n = 0;
+  tc_work_item_host(tiles_m, n_split, grp, w, &t, &n);
+  *tile = t; *n_slice = n;
+  return grp;
+}
+
 extern "C" int pe_tc_plan_candidates(int32_t Cin, int32_t Cout, int32_t ks, int32_t has_residual, int32_t H, int32_t W, int32_t max_img,
                                      int32_t gather, int32_t* out, int32_t cap) {
   const int n = tc_plan_candidates(Cin, Cout, ks, has_residual, H, W, max_img, gather, out, cap);

@@ -75,3 +75,6 @@ cudaError_t tc_conv_launch_rows(TcConvPlan* plan, long long rows, cudaStream_t s
 void tc_conv_plan_destroy(TcConvPlan* plan, bool cuda_ok = true);
 int tc_plan_candidates(int Cin, int Cout, int ks, int has_res, int H, int W, int max_img, int gather, int32_t* out, int cap);
 cudaError_t tc_conv_launch(TcConvPlan* plan, int nimg, cudaStream_t st);
+// host views of the persistent schedule (conv_tc_kernel.cuh tc_work_item): group size rule and work item -> (M tile, N slice)
+int tc_group_size(int Cin, int Cout, int ns, int tile_rows, int tiles_m, int mode, int budget_kb);
+void tc_work_item_host(int tiles_m, int nsplit, int grp, int w, int* tile, int* nsl);
