@@ -56,8 +56,9 @@ def _patch_module(name: str):
         return ours, "replaced"
     for attr in PROVIDED[name]:
         if hasattr(ours, attr):
-            if name == "mmtrack" and attr == "mmtrack_bounding_boxes" and not hasattr(ours, "_reference_impl_set"):
-                # methods this engine does not build (tracktor / deepsort / qdtrack) keep going to the reference
+            if (name, attr) in (("mmtrack", "mmtrack_bounding_boxes"), ("mmpose", "mmpose_top_down_person")) and not hasattr(ours, "_reference_impl_set"):
+                # methods this engine does not build (tracktor / deepsort / qdtrack; HRFormer_COCO / HRNet_TCFormer_COCOWholeBody)
+                # keep going to the reference's own function: install() never breaks a path that worked before it
                 ours._reference_impl = getattr(ref, attr)
                 ours._reference_impl_set = True
             setattr(ref, attr, getattr(ours, attr))

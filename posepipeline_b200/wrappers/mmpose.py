@@ -43,6 +43,7 @@ mmpose_joint_dictionary = {
 # tags the reference accepts (:33-52) that this build does not implement yet (HRFormer / TCFormer are
 # different backbones and out of the hot-path scope)
 _REFERENCE_ONLY = {"HRFormer_COCO": 17, "HRNet_TCFormer_COCOWholeBody": 133}
+_reference_impl = None                 # set by posepipeline_b200.install when the reference's mmpose wrapper is importable
 
 FRAME_BLOCK = int(os.environ.get("PE_FRAME_BLOCK", "32"))
 _models: Dict[str, "E.TopDownModel"] = {}
@@ -86,6 +87,8 @@ def mmpose_top_down_person(key, method='HRNet_W48_COCO'):
     from pose_pipeline import Video, PersonBbox      # the reference's own tables (pipeline.py:24, :648)
 
     if method in _REFERENCE_ONLY:
+        if _reference_impl is not None:          # the reference's own mmpose install serves the backbones this engine does not build
+            return _reference_impl(key, method)
         raise NotImplementedError(f"top-down method {method} is not built in this engine yet (HRNet_W48_COCO / _COCOWholeBody / _HALPE, HRNet_W32_COCO and ViTPose_B_COCO are)")
     if method not in E.METHODS:
         # the reference falls through its if/elif chain and dies on an unbound `pose_cfg`

@@ -31,7 +31,16 @@ def ref_pipeline(monkeypatch, tmp_path):
             del sys.modules[m]
         for m in ("posepipeline_b200.wrappers.mmtrack", "posepipeline_b200.wrappers.mmpose", "posepipeline_b200.wrappers.videopose3d",
                   "posepipeline_b200.install"):
-            sys.modules.pop(m, None)
+            mod = sys.modules.pop(m, None)
+            if mod is not None:                      # `from posepipeline_b200.wrappers import mmpose` elsewhere still finds this object
+                for a in ("_reference_impl_set",):
+                    if hasattr(mod, a):
+                        delattr(mod, a)
+                if hasattr(mod, "_reference_impl"):
+                    mod._reference_impl = None
+            pkg, _, name = m.rpartition(".")
+            if pkg in sys.modules and hasattr(sys.modules[pkg], name):
+                delattr(sys.modules[pkg], name)
     purge()
     monkeypatch.syspath_prepend(REF)
     monkeypatch.syspath_prepend(os.path.join(ROOT, "tests", "dj_stub"))
@@ -103,6 +112,12 @@ def test_install_patches_reference_modules_in_place(ref_pipeline):
     assert M.mmpose_top_down_person is ours.mmpose_top_down_person
     # what BottomUpPeople.make does (pipeline.py:210) must still import
     from pose_pipeline.wrappers.mmpose import mmpose_bottom_up  # noqa: F401
+    # the two backbones this engine does not build keep going to the REFERENCE's function (which then needs its own mmpose install:
+    # here the lazy `from mmpose.apis import ...` inside it, wrappers/mmpose.py:28, fails -- proof that the call was delegated)
+    assert ours._reference_impl is not None and ours._reference_impl.__module__ == "pose_pipeline.wrappers.mmpose"
+    assert ours._reference_impl is not ours.mmpose_top_down_person
+    with pytest.raises(ImportError):
+        M.mmpose_top_down_person({"video_project": "p"}, "HRFormer_COCO")
     # mmtrack.py does `import mmtrack.apis` at module level (:5): not importable here -> replaced by ours
     assert status["mmtrack"] == "replaced"
     T = importlib.import_module("pose_pipeline.wrappers.mmtrack")
