@@ -59,7 +59,7 @@ def _patch_module(name: str):
             if (name, attr) in (("mmtrack", "mmtrack_bounding_boxes"), ("mmpose", "mmpose_top_down_person")) and not hasattr(ours, "_reference_impl_set"):
                 # methods this engine does not build (tracktor / deepsort / qdtrack; HRFormer_COCO / HRNet_TCFormer_COCOWholeBody)
                 # keep going to the reference's own function: install() never breaks a path that worked before it
-                ours._reference_impl = getattr(ref, attr)
+                ours._reference_impl = getattr(ref, attr, None)
                 ours._reference_impl_set = True
             setattr(ref, attr, getattr(ours, attr))
     return ref, "patched"
