@@ -529,9 +529,11 @@ cudaError_t tc_conv_launch_rows(TcConvPlan* pl, long long rows, cudaStream_t st)
   p.M = rows;
   p.tiles_m = (int)((p.M + 128LL * pl->MT * pl->CG - 1) / (128LL * pl->MT * pl->CG));
   p.total_work = p.tiles_m * pl->ns;
-  // lane-parallel producer: gather forms need at most 15 lanes (boxes of two S image rows + the weight box), the others
+  // lane-parallel producer when a stage has at most 32 operations: gather forms issue the boxes of two S image rows + the weight
+  // box (15 lanes at HRNet's / YOLOX's widths; feature maps narrower than 3 columns would need more), the others
   // KC * (activation boxes + 1); PE_TC_PLANES=1 selects the single-lane producer
-  p.prod_par = env_int("PE_TC_PLANES", 32) > 1 && (p.gather || pl->KC * (p.nseg * p.nb_seg + 1) <= 32) ? 1 : 0;
+  const int gather_ops = p.gather ? (2 * p.Wp - 1 + 128 * pl->MT + p.Wp + 1 + 2 * p.Wp - 1) / (2 * p.Wp) + 1 : 0;   // most boxes of a tile + the weight box
+  p.prod_par = env_int("PE_TC_PLANES", 32) > 1 && (p.gather ? gather_ops <= 32 : pl->KC * (p.nseg * p.nb_seg + 1) <= 32) ? 1 : 0;
   // schedule (tc_work_item): with several N slices, groups of M tiles whose activation rows (<= 48 MB) stay in L2 while the
   // CTAs walk through the slices -- only where the repeated activation reads weigh at least as much as the output itself,
   // Cin * (ns - 1) >= Cout: the wide 1x1 layers of HRNet's layer1 (64 -> 256, HBM-bound on the output and the residual)
